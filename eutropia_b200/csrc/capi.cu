@@ -1,0 +1,407 @@
+// extern "C" surface of libeutropia_b200.so (include/eutropia_b200.h) and the one-shot tier that
+// reproduces the two Rcpp entry points call for call.
+#include <algorithm>
+#include <cmath>
+#include <memory>
+#include <mutex>
+
+#include "common.h"
+
+using namespace eut;
+
+extern "C" {
+
+const char *eut_last_error(void) { return last_error_cstr(); }
+int eut_abi_version(void) { return 1000; }
+
+int eut_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// ---- plan ------------------------------------------------------------------------------------
+int eut_plan_create(eut_plan **out, const int32_t *from, const int32_t *to, int64_t n_edges,
+                    const int32_t *nn_id, const int32_t *nn_cnt, int64_t n_nn, int64_t n_points,
+                    int device, uint32_t flags)
+{
+    clear_error();
+    if (!out) { set_error("eut_plan_create: out is NULL"); return EUT_ERR_ARG; }
+    *out = nullptr;
+    eut_plan *p = new eut_plan();
+    int rc = plan_build(p, from, to, n_edges, nn_id, nn_cnt, n_nn, n_points, device, flags);
+    if (rc != EUT_OK) {
+        plan_free(p);
+        delete p;
+        return rc;
+    }
+    *out = p;
+    return EUT_OK;
+}
+
+int eut_plan_destroy(eut_plan *plan)
+{
+    if (!plan) return EUT_OK;
+    plan_free(plan);
+    delete plan;
+    return EUT_OK;
+}
+
+int eut_plan_get_info(const eut_plan *p, eut_plan_info *info)
+{
+    if (!p || !info) { set_error("eut_plan_get_info: NULL argument"); return EUT_ERR_ARG; }
+    info->n_points = p->N; info->n_edges = p->E; info->n_padded = p->Np;
+    info->max_in_degree = p->max_in; info->ell_width = p->ell_w; info->order = p->order;
+    info->regular_outflow = p->regular_out; info->device = p->device; info->n_tiles = p->n_tiles;
+    info->device_bytes = p->device_bytes; info->build_ms = p->build_ms;
+    return EUT_OK;
+}
+
+// The map is read back FROM THE DEVICE tables and translated to reference ids, so the comparison in
+// tests/ covers what the kernels actually index with.
+int eut_plan_get_csr(const eut_plan *p, int64_t *row_ptr, int32_t *col)
+{
+    clear_error();
+    if (!p || !row_ptr || (!col && p->E > 0)) { set_error("eut_plan_get_csr: NULL argument"); return EUT_ERR_ARG; }
+    EUT_TRY(ensure_device(p->device));
+    const int64_t N = p->N;
+    if (p->ell_w > 0) {
+        std::vector<int32_t> nbr((size_t)p->ell_w * p->Np);
+        std::vector<uint8_t> deg(p->Np);
+        EUT_CUDA(cudaMemcpy(nbr.data(), p->d_nbr, nbr.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        EUT_CUDA(cudaMemcpy(deg.data(), p->d_deg, deg.size(), cudaMemcpyDeviceToHost));
+        row_ptr[0] = 0;
+        for (int64_t i = 0; i < N; i++) row_ptr[i + 1] = row_ptr[i] + deg[p->perm[i]];
+        for (int64_t i = 0; i < N; i++) {
+            const int64_t q = p->perm[i];
+            for (int k = 0; k < deg[q]; k++)
+                col[row_ptr[i] + k] = p->iperm[nbr[(size_t)k * p->Np + q]] + 1;
+        }
+    } else {
+        std::vector<int64_t> rp(N + 1);
+        std::vector<int32_t> cl(p->E);
+        EUT_CUDA(cudaMemcpy(rp.data(), p->d_row_ptr, rp.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
+        if (p->E) EUT_CUDA(cudaMemcpy(cl.data(), p->d_col, cl.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        row_ptr[0] = 0;
+        for (int64_t i = 0; i < N; i++) {
+            const int64_t q = p->perm[i];
+            row_ptr[i + 1] = row_ptr[i] + (rp[q + 1] - rp[q]);
+        }
+        for (int64_t i = 0; i < N; i++) {
+            const int64_t q = p->perm[i];
+            for (int64_t k = rp[q], o = row_ptr[i]; k < rp[q + 1]; k++, o++) col[o] = p->iperm[cl[k]] + 1;
+        }
+    }
+    return EUT_OK;
+}
+
+int eut_plan_get_perm(const eut_plan *p, int32_t *perm)
+{
+    if (!p || (!perm && p->N > 0)) { set_error("eut_plan_get_perm: NULL argument"); return EUT_ERR_ARG; }
+    std::copy(p->perm.begin(), p->perm.end(), perm);
+    return EUT_OK;
+}
+
+// ---- field -----------------------------------------------------------------------------------
+int eut_field_create(eut_field **out, eut_plan *plan, int64_t n_cols)
+{
+    clear_error();
+    if (out) *out = nullptr;
+    return field_create(out, plan, n_cols);
+}
+int eut_field_destroy(eut_field *f) { return field_destroy(f); }
+
+int eut_field_upload(eut_field *f, const double *host, int64_t ld, const int32_t *cols, int64_t n_cols)
+{
+    clear_error();
+    if (!f) { set_error("eut_field_upload: field is NULL"); return EUT_ERR_ARG; }
+    EUT_TRY(field_upload(f, host, ld, cols, n_cols));
+    // the caller may free / overwrite `host` right after this returns
+    EUT_CUDA(cudaStreamSynchronize(f->copy_stream));
+    return EUT_OK;
+}
+
+int eut_field_download(eut_field *f, double *host, int64_t ld, const int32_t *cols, int64_t n_cols)
+{
+    clear_error();
+    if (!f) { set_error("eut_field_download: field is NULL"); return EUT_ERR_ARG; }
+    EUT_TRY(field_download_async(f, host, ld, cols, n_cols));
+    return field_sync_down(f);
+}
+
+int eut_field_diffuse(eut_field *f, const int32_t *niter, const int32_t *indvar, int64_t n_indvar)
+{
+    clear_error();
+    if (!f) { set_error("eut_field_diffuse: field is NULL"); return EUT_ERR_ARG; }
+    return field_diffuse(f, niter, indvar, n_indvar);
+}
+
+int eut_field_sync(eut_field *f)
+{
+    if (!f) return EUT_ERR_ARG;
+    EUT_TRY(ensure_device(f->plan->device));
+    EUT_CUDA(cudaStreamSynchronize(f->copy_stream));
+    EUT_CUDA(cudaStreamSynchronize(f->stream));
+    EUT_CUDA(cudaStreamSynchronize(f->down_stream));
+    return EUT_OK;
+}
+
+void *eut_field_stream(eut_field *f) { return f ? (void *)f->stream : nullptr; }
+
+int eut_field_set_stream(eut_field *f, void *cuda_stream)
+{
+    if (!f) return EUT_ERR_ARG;
+    EUT_TRY(eut_field_sync(f));
+    if (f->own_stream && f->stream) cudaStreamDestroy(f->stream);
+    f->stream = (cudaStream_t)cuda_stream;
+    f->own_stream = false;
+    return EUT_OK;
+}
+
+int64_t eut_field_launch_count(const eut_field *f) { return f ? f->launches : 0; }
+
+int eut_field_set_option(eut_field *f, const char *name, int64_t value)
+{
+    if (!f || !name) return EUT_ERR_ARG;
+    std::string n(name);
+    if (n == "cpt") f->opt_cpt = (int)value;
+    else if (n == "variant") f->opt_variant = (int)value;
+    else if (n == "group_cols") f->opt_group_cols = (int)value;
+    else { set_error("eut_field_set_option: unknown option '%s'", name); return EUT_ERR_ARG; }
+    return EUT_OK;
+}
+
+int eut_field_column_stats(eut_field *f, double *col_min, double *col_max, double *col_mean)
+{
+    clear_error();
+    if (!f) return EUT_ERR_ARG;
+    EUT_TRY(ensure_device(f->plan->device));
+    EUT_TRY(launch_column_stats(f, f->d_cur));
+    std::vector<double> h(3 * std::max<int64_t>(f->C, 1));
+    EUT_CUDA(cudaMemcpyAsync(h.data(), f->d_stats, 3 * f->C * sizeof(double), cudaMemcpyDeviceToHost,
+                             f->stream));
+    EUT_CUDA(cudaStreamSynchronize(f->stream));
+    for (int64_t c = 0; c < f->C; c++) {
+        if (col_min) col_min[c] = h[c];
+        if (col_max) col_max[c] = h[f->C + c];
+        if (col_mean) col_mean[c] = h[2 * f->C + c];
+    }
+    return EUT_OK;
+}
+
+int eut_field_fill_column(eut_field *f, int32_t col, double value)
+{
+    clear_error();
+    if (!f) return EUT_ERR_ARG;
+    if (col < 1 || col > f->C) { set_error("eut_field_fill_column: column %d out of bounds", col); return EUT_ERR_INDEX; }
+    EUT_TRY(ensure_device(f->plan->device));
+    return launch_fill_column(f, col - 1, value);
+}
+
+// ---- one-shot tier ---------------------------------------------------------------------------
+namespace {
+
+struct CachedPlan {
+    uint64_t h_edges = 0, h_nn = 0;
+    int64_t n_edges = 0, n_nn = 0, n_rows = 0;
+    int device = 0;
+    eut_plan *plan = nullptr;
+    eut_field *field = nullptr;
+    int64_t field_cols = 0;
+    uint64_t stamp = 0;
+};
+
+std::mutex g_mu;
+std::vector<CachedPlan> g_cache;
+uint64_t g_stamp = 0;
+constexpr size_t kMaxCached = 4;
+
+void drop(CachedPlan &c)
+{
+    if (c.field) field_destroy(c.field);
+    if (c.plan) { plan_free(c.plan); delete c.plan; }
+    c.field = nullptr; c.plan = nullptr;
+}
+
+// R calls diffChangePar every round with the same mat.in / mat.out (R/growthEnvironment.R:385-390);
+// the graph analysis and its device tables are kept and recognised by content hash.
+int get_cached(const int32_t *adj, int64_t n_edges, const int32_t *nn, int64_t n_nn, int64_t n_rows,
+               int device, CachedPlan **out)
+{
+    const uint64_t he = hash_bytes(adj, (size_t)n_edges * 2 * sizeof(int32_t), 0x5eedull);
+    const uint64_t hn = hash_bytes(nn, (size_t)n_nn * 2 * sizeof(int32_t), 0xfeedull);
+    for (auto &c : g_cache)
+        if (c.h_edges == he && c.h_nn == hn && c.n_edges == n_edges && c.n_nn == n_nn &&
+            c.n_rows == n_rows && c.device == device) {
+            c.stamp = ++g_stamp;
+            *out = &c;
+            return EUT_OK;
+        }
+    if (g_cache.size() >= kMaxCached) {
+        auto it = std::min_element(g_cache.begin(), g_cache.end(),
+                                   [](const CachedPlan &a, const CachedPlan &b) { return a.stamp < b.stamp; });
+        drop(*it);
+        g_cache.erase(it);
+    }
+    CachedPlan c;
+    c.h_edges = he; c.h_nn = hn; c.n_edges = n_edges; c.n_nn = n_nn; c.n_rows = n_rows;
+    c.device = device; c.stamp = ++g_stamp;
+    c.plan = new eut_plan();
+    int rc = plan_build(c.plan, adj, adj + n_edges, n_edges, nn, nn + n_nn, n_nn, n_rows, device,
+                        EUT_ORDER_AUTO);
+    if (rc != EUT_OK) {
+        plan_free(c.plan);
+        delete c.plan;
+        return rc;
+    }
+    g_cache.push_back(c);
+    *out = &g_cache.back();
+    return EUT_OK;
+}
+
+// Shared body: `niter[i]` substeps on 1-based column `indvar[i]`; all other columns pass through.
+int oneshot_run(const int32_t *adj, int64_t n_edges, const int32_t *nn, int64_t n_nn,
+                const double *conc_in, int64_t n_rows, int64_t n_cols, const int32_t *niter,
+                const int32_t *indvar, int64_t n_indvar, double *conc_out, int device)
+{
+    if (n_rows < 0 || n_cols < 0 || n_edges < 0 || n_nn < 0 || n_indvar < 0 ||
+        (n_rows * n_cols > 0 && (!conc_in || !conc_out)) || (n_edges > 0 && !adj) ||
+        (n_nn > 0 && !nn) || (n_indvar > 0 && (!niter || !indvar))) {
+        set_error("one-shot call: NULL pointer or negative size");
+        return EUT_ERR_ARG;
+    }
+    if (conc_in == conc_out && n_rows * n_cols > 0) {
+        set_error("one-shot call: conc_out must not alias conc_in (R value semantics)");
+        return EUT_ERR_ARG;
+    }
+    std::lock_guard<std::mutex> lock(g_mu);
+    EUT_TRY(ensure_device(device));
+    CachedPlan *cp = nullptr;
+    EUT_TRY(get_cached(adj, n_edges, nn, n_nn, n_rows, device, &cp));
+    if (!cp->field || cp->field_cols != n_cols) {
+        if (cp->field) field_destroy(cp->field);
+        cp->field = nullptr;
+        EUT_TRY(field_create(&cp->field, cp->plan, n_cols));
+        cp->field_cols = n_cols;
+    }
+    eut_field *f = cp->field;
+
+    // active columns (validated by field_diffuse's rules before any work is queued)
+    std::vector<int64_t> act;
+    std::vector<uint8_t> is_act(std::max<int64_t>(n_cols, 1), 0);
+    for (int64_t i = 0; i < n_indvar; i++) {
+        if (niter[i] <= 0) continue;
+        if (indvar[i] < 1 || indvar[i] > n_cols) {
+            set_error("index out of bounds: column %d of a %lld-column matrix", indvar[i], (long long)n_cols);
+            return EUT_ERR_INDEX;
+        }
+        if (is_act[indvar[i] - 1]) {
+            set_error("column %d listed twice in indvar", indvar[i]);
+            return EUT_ERR_ARG;
+        }
+        is_act[indvar[i] - 1] = 1;
+        act.push_back(i);
+    }
+    // Pipeline over chunks of active columns: H2D(g+1) | substeps(g) | D2H(g-1) on three streams.
+    const int64_t chunk = f->stage_cols;
+    std::vector<int32_t> cols, nit;
+    for (size_t a0 = 0; a0 < act.size(); a0 += chunk) {
+        const size_t a1 = std::min(act.size(), a0 + (size_t)chunk);
+        cols.clear(); nit.clear();
+        for (size_t a = a0; a < a1; a++) { cols.push_back(indvar[act[a]]); nit.push_back(niter[act[a]]); }
+        // host column j of this chunk is conc_in column cols[j]-1: upload one column at a time when
+        // they are not contiguous, as one 2-D copy when they are
+        bool contiguous = true;
+        for (size_t j = 1; j < cols.size(); j++) contiguous &= (cols[j] == cols[j - 1] + 1);
+        if (contiguous) {
+            EUT_TRY(field_upload(f, conc_in + (size_t)(cols[0] - 1) * n_rows, n_rows, cols.data(), (int64_t)cols.size()));
+        } else {
+            for (size_t j = 0; j < cols.size(); j++)
+                EUT_TRY(field_upload(f, conc_in + (size_t)(cols[j] - 1) * n_rows, n_rows, &cols[j], 1));
+        }
+        EUT_TRY(field_diffuse(f, nit.data(), cols.data(), (int64_t)cols.size()));
+        if (contiguous) {
+            EUT_TRY(field_download_async(f, conc_out + (size_t)(cols[0] - 1) * n_rows, n_rows, cols.data(), (int64_t)cols.size()));
+        } else {
+            for (size_t j = 0; j < cols.size(); j++)
+                EUT_TRY(field_download_async(f, conc_out + (size_t)(cols[j] - 1) * n_rows, n_rows, &cols[j], 1));
+        }
+    }
+    // columns the call does not touch are returned as they came (src/diffChange.cpp:34, :68)
+    for (int64_t c = 0; c < n_cols; c++)
+        if (!is_act[c] && n_rows > 0)
+            memcpy(conc_out + (size_t)c * n_rows, conc_in + (size_t)c * n_rows, (size_t)n_rows * sizeof(double));
+    EUT_CUDA(cudaStreamSynchronize(f->copy_stream));
+    EUT_CUDA(cudaStreamSynchronize(f->stream));
+    EUT_CUDA(cudaStreamSynchronize(f->down_stream));
+    return EUT_OK;
+}
+
+}  // namespace
+
+void eut_oneshot_reset(void)
+{
+    std::lock_guard<std::mutex> lock(g_mu);
+    for (auto &c : g_cache) drop(c);
+    g_cache.clear();
+}
+
+int eut_diffchange_par(const int32_t *adjmat, int64_t n_edges, const int32_t *nneighbors,
+                       int64_t n_nn, const double *conc_in, int64_t n_rows, int64_t n_cols,
+                       const int32_t *niter, const int32_t *indvar, int64_t n_indvar, int ncores,
+                       double *conc_out, int device)
+{
+    (void)ncores;
+    clear_error();
+    return oneshot_run(adjmat, n_edges, nneighbors, n_nn, conc_in, n_rows, n_cols, niter, indvar,
+                       n_indvar, conc_out, device);
+}
+
+int eut_diffchange(const double *adjmat, int64_t n_edges, const double *nneighbors, int64_t n_nn,
+                   const double *conc_in, int64_t n_rows, int64_t n_cols, const double *niter,
+                   int64_t n_niter, double *conc_out, int device)
+{
+    clear_error();
+    if (n_edges < 0 || n_nn < 0 || n_niter < 0 || (n_edges > 0 && !adjmat) ||
+        (n_nn > 0 && !nneighbors) || (n_niter > 0 && !niter)) {
+        set_error("eut_diffchange: NULL pointer or negative size");
+        return EUT_ERR_ARG;
+    }
+    // (int) casts of src/diffChange.cpp:20,26 -- out-of-range values are where the reference's
+    // bounds check fires; they are mapped to 0 here so that plan_build reports EUT_ERR_INDEX.
+    auto to_index = [](double v) -> int32_t {
+        if (!(v > -2147483648.0 && v < 2147483648.0)) return 0;
+        return (int32_t)v;
+    };
+    std::vector<int32_t> adj((size_t)n_edges * 2), nn((size_t)n_nn * 2);
+    for (int64_t j = 0; j < 2 * n_edges; j++) adj[j] = to_index(adjmat[j]);
+    for (int64_t j = 0; j < n_nn; j++) nn[j] = to_index(nneighbors[j]);
+    // n_neighbors stays a double in the reference ((double) nn - 1, :26): require it to be an
+    // integer that int32 holds, which is what mat.out always contains
+    for (int64_t j = 0; j < n_nn; j++) {
+        double v = nneighbors[n_nn + j];
+        if (!(v == std::floor(v)) || !(std::fabs(v) < 2147483648.0)) {
+            set_error("eut_diffchange: nneighbors[%lld,2] = %g is not an integer count", (long long)j + 1, v);
+            return EUT_ERR_UNSUPPORTED;
+        }
+        nn[n_nn + j] = (int32_t)v;
+    }
+    // `for (int k = 0; k < niter(i); k++)` with a double bound (:14)
+    std::vector<int32_t> nit, iv;
+    for (int64_t i = 0; i < n_niter; i++) {
+        double v = niter[i];
+        if (!(v > 0)) continue;  // also NaN
+        if (!(v < 2147483647.0)) { set_error("eut_diffchange: niter[%lld] is not finite", (long long)i + 1); return EUT_ERR_ARG; }
+        if (i >= n_cols) { set_error("index out of bounds: niter has an entry for column %lld of a %lld-column matrix", (long long)i + 1, (long long)n_cols); return EUT_ERR_INDEX; }
+        nit.push_back((int32_t)std::ceil(v));
+        iv.push_back((int32_t)(i + 1));
+    }
+    return oneshot_run(adj.data(), n_edges, nn.data(), n_nn, conc_in, n_rows, n_cols, nit.data(),
+                       iv.data(), (int64_t)iv.size(), conc_out, device);
+}
+
+}  // extern "C"

@@ -1,0 +1,751 @@
+// Cell <-> field exchange: cell->field lists (R/run_simulation.R:217-241, :591-624), gather
+// (R/run_simulation.R:249 + R/scavenge_compounds.R:17-22) and scatter + clamp
+// (R/run_simulation.R:689-740, :309-319), all on the device against the resident field.
+//
+// Determinism: the reference aggregates the per-cell contributions with a group-by sum in table
+// (= cell) order.  Instead of atomics the scatter walks, for every touched field point, the list of
+// (cell, entry) pairs that reference it in cell order (a transposed copy of the lists built once
+// per cell map), so every (field, compound) sum has a fixed order and the result is reproducible
+// bit for bit from run to run.
+//
+// R's `sum` / `colSums` accumulate in long double (x87 80-bit).  The device has no such type; sums
+// that R takes in long double are accumulated here as an unevaluated hi+lo pair (TwoSum), which is
+// at least as accurate, and rounded once at the end.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+#include "common.h"
+
+struct eut_cells {
+    eut_plan *plan = nullptr;
+    int64_t M = 0;          // cells
+    int64_t T = 0;          // entries (sum of list lengths)
+    int64_t cap_M = 0, cap_T = 0;
+    // per entry, cell-major (table order)
+    int64_t *d_cell_ptr = nullptr;  // [M+1]
+    int32_t *d_fid = nullptr;       // reference field id, 1-based
+    int32_t *d_fq = nullptr;        // internal position
+    double *d_dist = nullptr;
+    double *d_acc = nullptr;
+    int32_t *d_ecell = nullptr;     // cell of entry
+    // per cell
+    double *d_dmax = nullptr, *d_fsum = nullptr;
+    // transposed: entries grouped by field position, cell order inside a group
+    int32_t *d_t_entry = nullptr;   // [T] entry index
+    int32_t *d_t_key = nullptr;     // [T] sorted field positions
+    int32_t *d_seg_start = nullptr; // [n_seg+1] group boundaries in d_t_entry
+    int32_t *d_seg_fq = nullptr;    // [n_seg] field position of the group
+    int64_t n_seg = 0;
+    bool transposed = false;
+    // geometry index for eut_cells_build_lists: field points sorted by (z, x, y)
+    int64_t n_pts = 0;
+    double *d_gx = nullptr, *d_gy = nullptr;  // sorted coordinates
+    int32_t *d_gfield = nullptr;              // 1-based field id in sorted order
+    int32_t *d_col_start = nullptr;           // runs of equal (z, x): [n_cols_g+1]
+    double *d_col_x = nullptr;                // x of each run
+    int32_t *d_layer_col = nullptr;           // [n_layers+1] first run of each z
+    double *d_layer_z = nullptr;
+    int64_t n_cols_g = 0, n_layers = 0;
+    uint64_t pts_hash = 0;
+    // scratch
+    void *d_tmp = nullptr;
+    size_t tmp_bytes = 0;
+    double *d_fmol = nullptr;   // [M x C]
+    int64_t fmol_cap = 0;
+    int64_t *d_ex_ptr = nullptr;
+    int32_t *d_ex_cpd = nullptr;
+    double *d_ex_flx = nullptr, *d_ex_cs = nullptr;
+    int64_t ex_cap = 0, exptr_cap = 0;
+    uint8_t *d_const = nullptr;
+    int64_t const_cap = 0;
+    int64_t launches = 0;
+};
+
+namespace eut {
+
+// ---- hi+lo accumulation -----------------------------------------------------------------------
+struct dd { double hi, lo; };
+__device__ __forceinline__ void dd_add(dd &s, double x)
+{
+    const double t = __dadd_rn(s.hi, x);
+    const double bb = __dsub_rn(t, s.hi);
+    const double err = __dadd_rn(__dsub_rn(s.hi, __dsub_rn(t, bb)), __dsub_rn(x, bb));
+    s.hi = t;
+    s.lo = __dadd_rn(s.lo, err);
+}
+__device__ __forceinline__ double dd_value(const dd &s)
+{
+    // non-finite sums: TwoSum's error term is NaN there, the plain sum is what R would return
+    return (isfinite(s.hi) && isfinite(s.lo)) ? __dadd_rn(s.hi, s.lo) : s.hi;
+}
+__device__ __forceinline__ dd dd_warp_sum(dd s)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double h = __shfl_xor_sync(0xffffffffu, s.hi, o);
+        const double l = __shfl_xor_sync(0xffffffffu, s.lo, o);
+        dd_add(s, h);
+        s.lo = __dadd_rn(s.lo, l);
+    }
+    return s;
+}
+
+template <typename T>
+static int grow(T **p, int64_t *cap, int64_t need)
+{
+    if (need <= *cap && *p) return EUT_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    int64_t n = std::max<int64_t>(need + need / 8, 16);
+    EUT_CUDA(cudaMalloc((void **)p, (size_t)n * sizeof(T)));
+    *cap = n;
+    return EUT_OK;
+}
+
+static int ensure_tmp(eut_cells *c, size_t bytes)
+{
+    if (bytes <= c->tmp_bytes && c->d_tmp) return EUT_OK;
+    if (c->d_tmp) cudaFree(c->d_tmp);
+    c->d_tmp = nullptr;
+    EUT_CUDA(cudaMalloc(&c->d_tmp, bytes + bytes / 8 + 256));
+    c->tmp_bytes = bytes + bytes / 8 + 256;
+    return EUT_OK;
+}
+
+static int alloc_entries(eut_cells *c, int64_t M, int64_t T)
+{
+    if (M + 1 > c->cap_M || !c->d_cell_ptr) {
+        cudaFree(c->d_cell_ptr); cudaFree(c->d_dmax); cudaFree(c->d_fsum);
+        int64_t n = M + 1 + M / 8 + 16;
+        EUT_CUDA(cudaMalloc((void **)&c->d_cell_ptr, n * sizeof(int64_t)));
+        EUT_CUDA(cudaMalloc((void **)&c->d_dmax, n * sizeof(double)));
+        EUT_CUDA(cudaMalloc((void **)&c->d_fsum, n * sizeof(double)));
+        c->cap_M = n;
+    }
+    if (T > c->cap_T || !c->d_fid) {
+        cudaFree(c->d_fid); cudaFree(c->d_fq); cudaFree(c->d_dist); cudaFree(c->d_acc);
+        cudaFree(c->d_ecell); cudaFree(c->d_t_entry); cudaFree(c->d_t_key);
+        cudaFree(c->d_seg_start); cudaFree(c->d_seg_fq);
+        int64_t n = T + T / 8 + 16;
+        EUT_CUDA(cudaMalloc((void **)&c->d_fid, n * sizeof(int32_t)));
+        EUT_CUDA(cudaMalloc((void **)&c->d_fq, n * sizeof(int32_t)));
+        EUT_CUDA(cudaMalloc((void **)&c->d_dist, n * sizeof(double)));
+        EUT_CUDA(cudaMalloc((void **)&c->d_acc, n * sizeof(double)));
+        EUT_CUDA(cudaMalloc((void **)&c->d_ecell, n * sizeof(int32_t)));
+        EUT_CUDA(cudaMalloc((void **)&c->d_t_entry, n * sizeof(int32_t)));
+        EUT_CUDA(cudaMalloc((void **)&c->d_t_key, n * sizeof(int32_t)));
+        EUT_CUDA(cudaMalloc((void **)&c->d_seg_start, (n + 1) * sizeof(int32_t)));
+        EUT_CUDA(cudaMalloc((void **)&c->d_seg_fq, n * sizeof(int32_t)));
+        c->cap_T = n;
+    }
+    c->M = M;
+    c->T = T;
+    c->transposed = false;
+    return EUT_OK;
+}
+
+// ---- per-entry / per-cell derived data --------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_entry_cell(const int64_t *__restrict__ cell_ptr, int32_t *__restrict__ ecell, const int n_cells)
+{
+    // one warp per cell
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n_cells) return;
+    for (int64_t k = cell_ptr[w] + lane; k < cell_ptr[w + 1]; k += 32) ecell[k] = w;
+}
+
+__global__ void __launch_bounds__(256)
+k_entry_pos(const int32_t *__restrict__ fid, const int32_t *__restrict__ perm,
+            int32_t *__restrict__ fq, const int64_t n_entries, const int n_points, int *bad)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_entries) return;
+    const int f = fid[k];
+    if (f < 1 || f > n_points) { atomicExch(bad, 1); fq[k] = 0; return; }
+    fq[k] = perm[f - 1];
+}
+
+// field.frac ingredients per cell (R/run_simulation.R:729-730): max distance, sum(max - dist)
+__global__ void __launch_bounds__(256)
+k_cell_frac(const int64_t *__restrict__ cell_ptr, const double *__restrict__ dist,
+            double *__restrict__ dmax, double *__restrict__ fsum, const int n_cells)
+{
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n_cells) return;
+    const int64_t k0 = cell_ptr[w], k1 = cell_ptr[w + 1];
+    double m = -INFINITY;
+    bool nan = false;
+    for (int64_t k = k0 + lane; k < k1; k += 32) { double d = dist[k]; nan |= (d != d); m = fmax(m, d); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        nan |= (bool)__shfl_xor_sync(0xffffffffu, (int)nan, o);
+    }
+    dd s{0.0, 0.0};
+    for (int64_t k = k0 + lane; k < k1; k += 32) dd_add(s, __dsub_rn(m, dist[k]));
+    s = dd_warp_sum(s);
+    if (lane == 0) { dmax[w] = m; fsum[w] = dd_value(s); }
+    (void)nan;
+}
+
+// transposed list boundaries
+__global__ void __launch_bounds__(256)
+k_seg_flags(const int32_t *__restrict__ key, int32_t *__restrict__ flag, const int64_t n)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    flag[k] = (k == 0 || key[k] != key[k - 1]) ? 1 : 0;
+}
+__global__ void __launch_bounds__(256)
+k_seg_fill(const int32_t *__restrict__ key, const int32_t *__restrict__ flag,
+           const int32_t *__restrict__ rank, int32_t *__restrict__ seg_start,
+           int32_t *__restrict__ seg_fq, const int64_t n)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    if (flag[k]) { seg_start[rank[k] - 1] = (int32_t)k; seg_fq[rank[k] - 1] = key[k]; }
+}
+
+static int build_transposed(eut_cells *c, cudaStream_t s)
+{
+    if (c->transposed) return EUT_OK;
+    const int64_t T = c->T;
+    c->n_seg = 0;
+    if (T == 0) { c->transposed = true; return EUT_OK; }
+    // stable LSD radix sort of (field position, entry index): entries of one field keep cell order
+    size_t sort_bytes = 0;
+    int32_t *vals_in = nullptr;
+    int bits = 1;
+    while ((1ll << bits) < c->plan->Np) bits++;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, c->d_fq, c->d_t_key, vals_in, c->d_t_entry,
+                                    (int)T, 0, bits, s);
+    size_t scan_bytes = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, (int32_t *)nullptr, (int32_t *)nullptr, (int)T, s);
+    const size_t iota_off = ((sort_bytes + 255) / 256) * 256;
+    const size_t need = iota_off + std::max<size_t>((size_t)T * 4 * 2, scan_bytes + (size_t)T * 8 + 512);
+    EUT_TRY(ensure_tmp(c, need + (size_t)T * 8 + 1024));
+    char *base = (char *)c->d_tmp;
+    vals_in = (int32_t *)(base + iota_off);
+    {
+        std::vector<int32_t> iota(T);
+        std::iota(iota.begin(), iota.end(), 0);
+        EUT_CUDA(cudaMemcpyAsync(vals_in, iota.data(), T * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        EUT_CUDA(cudaStreamSynchronize(s));
+    }
+    EUT_CUDA(cub::DeviceRadixSort::SortPairs(base, sort_bytes, c->d_fq, c->d_t_key, vals_in, c->d_t_entry,
+                                             (int)T, 0, bits, s));
+    int32_t *flag = (int32_t *)(base + iota_off);
+    int32_t *rank = flag + T;
+    void *scan_tmp = (void *)(((uintptr_t)(rank + T) + 255) / 256 * 256);
+    const unsigned nb = (unsigned)((T + 255) / 256);
+    k_seg_flags<<<nb, 256, 0, s>>>(c->d_t_key, flag, T);
+    EUT_CUDA(cub::DeviceScan::InclusiveSum(scan_tmp, scan_bytes, flag, rank, (int)T, s));
+    k_seg_fill<<<nb, 256, 0, s>>>(c->d_t_key, flag, rank, c->d_seg_start, c->d_seg_fq, T);
+    int32_t n_seg = 0;
+    EUT_CUDA(cudaMemcpyAsync(&n_seg, rank + (T - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    EUT_CUDA(cudaStreamSynchronize(s));
+    c->n_seg = n_seg;
+    const int32_t t32 = (int32_t)T;
+    EUT_CUDA(cudaMemcpyAsync(c->d_seg_start + n_seg, &t32, sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    EUT_CUDA(cudaStreamSynchronize(s));
+    c->launches += 4;
+    c->transposed = true;
+    return EUT_OK;
+}
+
+static int finish_lists(eut_cells *c, cudaStream_t s)
+{
+    // internal positions, entry->cell, field.frac ingredients
+    const eut_plan *p = c->plan;
+    if (c->T > 0) {
+        int *bad = nullptr;
+        EUT_TRY(ensure_tmp(c, 256));
+        bad = (int *)c->d_tmp;
+        EUT_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), s));
+        k_entry_pos<<<(unsigned)((c->T + 255) / 256), 256, 0, s>>>(c->d_fid, p->d_perm, c->d_fq, c->T, (int)p->N, bad);
+        int h_bad = 0;
+        EUT_CUDA(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, s));
+        EUT_CUDA(cudaStreamSynchronize(s));
+        if (h_bad) { set_error("index out of bounds: a cell's field.id is outside 1..%lld", (long long)p->N); return EUT_ERR_INDEX; }
+    }
+    if (c->M > 0) {
+        const unsigned nb = (unsigned)((c->M * 32 + 255) / 256);
+        k_entry_cell<<<nb, 256, 0, s>>>(c->d_cell_ptr, c->d_ecell, (int)c->M);
+        k_cell_frac<<<nb, 256, 0, s>>>(c->d_cell_ptr, c->d_dist, c->d_dmax, c->d_fsum, (int)c->M);
+    }
+    c->launches += 3;
+    EUT_CUDA(cudaGetLastError());
+    return EUT_OK;
+}
+
+// ---- gather ------------------------------------------------------------------------------------
+// one warp per (cell, compound); lanes stride over the cell's entries
+__global__ void __launch_bounds__(256)
+k_gather(const double *__restrict__ buf, const int64_t col_stride, const int64_t buf_stride,
+         const int32_t *__restrict__ cur, const int64_t *__restrict__ cell_ptr,
+         const int32_t *__restrict__ fq, const double *__restrict__ acc, const double field_vol,
+         double *__restrict__ fmol, const int n_cells, const int n_cols)
+{
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= (int64_t)n_cells * n_cols) return;
+    const int i = (int)(w % n_cells), c = (int)(w / n_cells);
+    const double *__restrict__ col = buf + (int64_t)cur[c] * buf_stride + (int64_t)c * col_stride;
+    dd s{0.0, 0.0};
+    for (int64_t k = cell_ptr[i] + lane; k < cell_ptr[i + 1]; k += 32) {
+        // ((conc / 1000) * fieldVol) * acc.prop   (R/scavenge_compounds.R:17-18)
+        const double v = __dmul_rn(__dmul_rn(__ddiv_rn(col[fq[k]], 1000.0), field_vol), acc[k]);
+        dd_add(s, v);
+    }
+    s = dd_warp_sum(s);
+    if (lane == 0) fmol[(int64_t)c * n_cells + i] = dd_value(s);
+}
+
+// ---- scatter -----------------------------------------------------------------------------------
+// colSums(accmat) for every uptake exchange (R/run_simulation.R:696): one warp per exchange entry
+__global__ void __launch_bounds__(256)
+k_ex_colsum(const double *__restrict__ buf, const int64_t col_stride, const int64_t buf_stride,
+            const int32_t *__restrict__ cur, const int64_t *__restrict__ cell_ptr,
+            const int32_t *__restrict__ fq, const double *__restrict__ acc, const double field_vol,
+            const int64_t *__restrict__ ex_ptr, const int32_t *__restrict__ ex_cpd,
+            const double *__restrict__ ex_flx, double *__restrict__ ex_cs, const int n_cells)
+{
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= n_cells) return;
+    for (int64_t e = ex_ptr[i]; e < ex_ptr[i + 1]; e++) {
+        if (!(ex_flx[e] < 0)) continue;
+        const int c = ex_cpd[e] - 1;
+        const double *__restrict__ col = buf + (int64_t)cur[c] * buf_stride + (int64_t)c * col_stride;
+        dd s{0.0, 0.0};
+        for (int64_t k = cell_ptr[i] + lane; k < cell_ptr[i + 1]; k += 32)
+            dd_add(s, __dmul_rn(__dmul_rn(__ddiv_rn(col[fq[k]], 1000.0), field_vol), acc[k]));
+        s = dd_warp_sum(s);
+        if (lane == 0) ex_cs[e] = dd_value(s);
+    }
+}
+
+// One thread per touched field point; accumulators for a chunk of CH compounds live in shared
+// memory ([CH][threads], conflict free).  The thread walks the (cell, entry) pairs of its field in
+// cell order and, for every exchange of that cell inside the chunk, adds the contribution in the
+// reference's expression order; then applies sum, NaN->0, add, clamp (R/run_simulation.R:309-319).
+template <int CH, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_scatter(double *__restrict__ buf, const int64_t col_stride, const int64_t buf_stride,
+          const int32_t *__restrict__ cur, const int32_t *__restrict__ seg_start,
+          const int32_t *__restrict__ seg_fq, const int32_t *__restrict__ t_entry,
+          const int32_t *__restrict__ ecell, const double *__restrict__ dist,
+          const double *__restrict__ acc, const double *__restrict__ dmax,
+          const double *__restrict__ fsum, const double field_vol, const double vol_l,
+          const int64_t *__restrict__ ex_ptr, const int32_t *__restrict__ ex_cpd,
+          const double *__restrict__ ex_flx, const double *__restrict__ ex_cs,
+          const uint8_t *__restrict__ is_const, const int n_seg, const int c0, const int n_cols)
+{
+    __shared__ double s_acc[CH][THREADS];
+    const int t = blockIdx.x * THREADS + threadIdx.x;
+    if (t >= n_seg) return;
+#pragma unroll
+    for (int j = 0; j < CH; j++) s_acc[j][threadIdx.x] = 0.0;
+    unsigned touched = 0;
+    const int q = seg_fq[t];
+    for (int r = seg_start[t]; r < seg_start[t + 1]; r++) {
+        const int k = t_entry[r];
+        const int i = ecell[k];
+        const double dk = dist[k], ak = acc[k];
+        const double frac = __ddiv_rn(__dsub_rn(dmax[i], dk), fsum[i]);  // :729-730
+        for (int pass = 0; pass < 2; pass++) {                          // I.up rows, then I.pd rows
+            for (int64_t e = ex_ptr[i]; e < ex_ptr[i + 1]; e++) {
+                const int c = ex_cpd[e] - 1;
+                const int j = c - c0;
+                if (j < 0 || j >= CH) continue;
+                const double ex = ex_flx[e];
+                double d;
+                if (pass == 0) {
+                    if (!(ex < 0)) continue;
+                    const double cv = buf[(int64_t)cur[c] * buf_stride + (int64_t)c * col_stride + q];
+                    const double fpf = __dmul_rn(__dmul_rn(__ddiv_rn(cv, 1000.0), field_vol), ak);
+                    const double am = __ddiv_rn(fpf, ex_cs[e]);                           // :696
+                    d = __ddiv_rn(__ddiv_rn(__dmul_rn(am, ex), 1e12), vol_l);             // :707-708
+                } else {
+                    if (!(ex > 0)) continue;
+                    d = __dmul_rn(frac, __ddiv_rn(__ddiv_rn(ex, 1e12), vol_l));           // :732-734
+                }
+                s_acc[j][threadIdx.x] = __dadd_rn(s_acc[j][threadIdx.x], d);
+                touched |= 1u << j;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < CH; j++) {
+        const int c = c0 + j;
+        if (!((touched >> j) & 1u) || c >= n_cols) continue;
+        if (is_const && is_const[c]) continue;                          // :311-312
+        double d = s_acc[j][threadIdx.x];
+        if (d != d) d = 0.0;                                             // :315
+        double *pc = buf + (int64_t)cur[c] * buf_stride + (int64_t)c * col_stride + q;
+        double v = __dadd_rn(*pc, d);                                    // :318
+        if (v < 1e-12) v = 0.0;                                          // :319
+        *pc = v;
+    }
+}
+
+// ---- claim rescale (R/run_simulation.R:236-241) ------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_claim(const int32_t *__restrict__ seg_start, const int32_t *__restrict__ t_entry,
+        double *__restrict__ acc, const int n_seg)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_seg) return;
+    const int r0 = seg_start[t], r1 = seg_start[t + 1];
+    dd s{0.0, 0.0};
+    for (int r = r0; r < r1; r++) dd_add(s, acc[t_entry[r]]);
+    const double claim = dd_value(s);
+    if (!(claim > 1)) return;
+    const double e = 2.718281828459045;  // exp(1)
+    dd ts{0.0, 0.0};
+    for (int r = r0; r < r1; r++) dd_add(ts, pow(acc[t_entry[r]], e));
+    const double tsum = dd_value(ts);
+    for (int r = r0; r < r1; r++) {
+        const int k = t_entry[r];
+        double tmp = pow(acc[k], e);
+        tmp = __dmul_rn(__ddiv_rn(tmp, tsum), claim);
+        acc[k] = __ddiv_rn(tmp, claim);
+    }
+}
+
+// ---- lists from geometry (R/run_simulation.R:217-230 box prefilter, :591-624) -------------------
+// Field points are pre-sorted by (z, x, y) (the gridDT key, :168) and grouped into runs of equal
+// (z, x).  A thread handles one cell: for every layer whose z passes the box test, binary-search
+// the runs whose x passes, and inside each run the points whose y passes -- with the very same
+// floating-point predicates as the reference (|v - c| <= R is monotone in v) -- then apply the
+// distance test.  Pass 0 counts, pass 1 writes, so the output order is the key order.
+__device__ __forceinline__ bool in_box(double v, double c, double R) { return fabs(__dsub_rn(v, c)) <= R; }
+
+template <bool WRITE>
+__global__ void __launch_bounds__(128)
+k_cellmap(const double *__restrict__ gx, const double *__restrict__ gy,
+          const int32_t *__restrict__ gfield, const int32_t *__restrict__ col_start,
+          const double *__restrict__ col_x, const int32_t *__restrict__ layer_col,
+          const double *__restrict__ layer_z, const int n_layers,
+          const double *__restrict__ cx, const double *__restrict__ cy,
+          const double *__restrict__ csize, const double *__restrict__ cscv, const int n_cells,
+          const int dist_mode, int64_t *__restrict__ counts, const int64_t *__restrict__ cell_ptr,
+          int32_t *__restrict__ fid, double *__restrict__ fdist, double *__restrict__ facc)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cells) return;
+    const double x0 = cx[i], y0 = cy[i];
+    const double R = __dadd_rn(__ddiv_rn(csize[i], 2.0), cscv[i]);
+    const double inv = __ddiv_rn(-1.0, cscv[i]);
+    int64_t n = 0;
+    int64_t o = WRITE ? cell_ptr[i] : 0;
+    for (int l = 0; l < n_layers; l++) {
+        const double z = layer_z[l];
+        if (!in_box(z, 0.0, R)) continue;
+        // runs [a, b) of this layer with |x - x0| <= R
+        int lo = layer_col[l], hi = layer_col[l + 1];
+        int a = lo, b = hi;
+        {   // first run with x - x0 >= -R  (predicate monotone in x)
+            int l2 = lo, h2 = hi;
+            while (l2 < h2) { int m = (l2 + h2) >> 1; if (__dsub_rn(col_x[m], x0) < -R) l2 = m + 1; else h2 = m; }
+            a = l2;
+            l2 = a; h2 = hi;   // first run with x - x0 > R
+            while (l2 < h2) { int m = (l2 + h2) >> 1; if (__dsub_rn(col_x[m], x0) <= R) l2 = m + 1; else h2 = m; }
+            b = l2;
+        }
+        for (int r = a; r < b; r++) {
+            if (!in_box(col_x[r], x0, R)) continue;  // NaN safety; always true otherwise
+            int p0 = col_start[r], p1 = col_start[r + 1];
+            int l2 = p0, h2 = p1;
+            while (l2 < h2) { int m = (l2 + h2) >> 1; if (__dsub_rn(gy[m], y0) < -R) l2 = m + 1; else h2 = m; }
+            for (int pidx = l2; pidx < p1; pidx++) {
+                const double dy = __dsub_rn(gy[pidx], y0);
+                if (dy > R) break;
+                if (!(fabs(dy) <= R)) continue;
+                const double dx = __dsub_rn(gx[pidx], x0);
+                double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                if (dist_mode == 1) d2 = __dadd_rn(d2, __dmul_rn(z, z));
+                const double d = __dsqrt_rn(d2);
+                if (!(d <= R)) continue;                      // :612
+                if (WRITE) {
+                    double a2 = __dmul_rn(inv, __dsub_rn(d, R));  // :618
+                    if (a2 > 1) a2 = 1;                       // :619
+                    fid[o] = gfield[pidx]; fdist[o] = d; facc[o] = a2;
+                    o++;
+                }
+                n++;
+            }
+        }
+    }
+    if (!WRITE) counts[i] = n;
+}
+
+}  // namespace eut
+
+using namespace eut;
+
+extern "C" {
+
+int eut_cells_create(eut_cells **out, eut_plan *plan)
+{
+    clear_error();
+    if (!out || !plan) { set_error("eut_cells_create: NULL argument"); return EUT_ERR_ARG; }
+    *out = nullptr;
+    EUT_TRY(ensure_device(plan->device));
+    eut_cells *c = new eut_cells();
+    c->plan = plan;
+    *out = c;
+    return EUT_OK;
+}
+
+int eut_cells_destroy(eut_cells *c)
+{
+    if (!c) return EUT_OK;
+    cudaSetDevice(c->plan->device);
+    cudaDeviceSynchronize();
+    cudaFree(c->d_cell_ptr); cudaFree(c->d_fid); cudaFree(c->d_fq); cudaFree(c->d_dist);
+    cudaFree(c->d_acc); cudaFree(c->d_ecell); cudaFree(c->d_dmax); cudaFree(c->d_fsum);
+    cudaFree(c->d_t_entry); cudaFree(c->d_t_key); cudaFree(c->d_seg_start); cudaFree(c->d_seg_fq);
+    cudaFree(c->d_gx); cudaFree(c->d_gy); cudaFree(c->d_gfield); cudaFree(c->d_col_start);
+    cudaFree(c->d_col_x); cudaFree(c->d_layer_col); cudaFree(c->d_layer_z); cudaFree(c->d_tmp);
+    cudaFree(c->d_fmol); cudaFree(c->d_ex_ptr); cudaFree(c->d_ex_cpd); cudaFree(c->d_ex_flx);
+    cudaFree(c->d_ex_cs); cudaFree(c->d_const);
+    delete c;
+    return EUT_OK;
+}
+
+int eut_cells_set_lists(eut_cells *c, int64_t n_cells, const int64_t *cell_ptr, const int32_t *field_id,
+                        const double *field_dist, const double *acc_prop)
+{
+    clear_error();
+    if (!c || n_cells < 0 || !cell_ptr) { set_error("eut_cells_set_lists: bad argument"); return EUT_ERR_ARG; }
+    const int64_t T = cell_ptr[n_cells];
+    if (cell_ptr[0] != 0 || T < 0 || (T > 0 && (!field_id || !field_dist || !acc_prop)) || T >= INT32_MAX) {
+        set_error("eut_cells_set_lists: bad cell_ptr or NULL entry arrays");
+        return EUT_ERR_ARG;
+    }
+    for (int64_t i = 0; i < n_cells; i++)
+        if (cell_ptr[i + 1] < cell_ptr[i]) { set_error("eut_cells_set_lists: cell_ptr not monotone"); return EUT_ERR_ARG; }
+    EUT_TRY(ensure_device(c->plan->device));
+    EUT_TRY(alloc_entries(c, n_cells, T));
+    cudaStream_t s = 0;
+    EUT_CUDA(cudaMemcpyAsync(c->d_cell_ptr, cell_ptr, (n_cells + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    if (T > 0) {
+        EUT_CUDA(cudaMemcpyAsync(c->d_fid, field_id, T * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        EUT_CUDA(cudaMemcpyAsync(c->d_dist, field_dist, T * sizeof(double), cudaMemcpyHostToDevice, s));
+        EUT_CUDA(cudaMemcpyAsync(c->d_acc, acc_prop, T * sizeof(double), cudaMemcpyHostToDevice, s));
+    }
+    return finish_lists(c, s);
+}
+
+int eut_cells_build_lists(eut_cells *c, const double *pts, int64_t n_pts, const double *cx,
+                          const double *cy, const double *csize, const double *cscv,
+                          int64_t n_cells, int dist_mode)
+{
+    clear_error();
+    if (!c || !pts || n_pts != c->plan->N || n_cells < 0 || (n_cells > 0 && (!cx || !cy || !csize || !cscv))) {
+        set_error("eut_cells_build_lists: bad argument (pts must be N x 3 for the plan's N)");
+        return EUT_ERR_ARG;
+    }
+    EUT_TRY(ensure_device(c->plan->device));
+    cudaStream_t s = 0;
+    // (1) geometry index, rebuilt only when the points change (once per simulation)
+    const uint64_t h = hash_bytes(pts, (size_t)n_pts * 3 * sizeof(double), 0xabcdull);
+    if (h != c->pts_hash || c->n_pts != n_pts || !c->d_gx) {
+        std::vector<int32_t> ord(n_pts);
+        std::iota(ord.begin(), ord.end(), 0);
+        const double *X = pts, *Y = pts + n_pts, *Z = pts + 2 * n_pts;
+        std::stable_sort(ord.begin(), ord.end(), [&](int32_t a, int32_t b) {   // setkeyv(z, x, y), :168
+            if (Z[a] != Z[b]) return Z[a] < Z[b];
+            if (X[a] != X[b]) return X[a] < X[b];
+            return Y[a] < Y[b];
+        });
+        std::vector<double> gx(n_pts), gy(n_pts), col_x, layer_z;
+        std::vector<int32_t> gf(n_pts), col_start, layer_col;
+        for (int64_t k = 0; k < n_pts; k++) {
+            const int32_t i = ord[k];
+            gx[k] = X[i]; gy[k] = Y[i]; gf[k] = i + 1;
+            const bool new_layer = (k == 0) || Z[i] != Z[ord[k - 1]];
+            const bool new_col = new_layer || X[i] != X[ord[k - 1]];
+            if (new_layer) { layer_col.push_back((int32_t)col_start.size()); layer_z.push_back(Z[i]); }
+            if (new_col) { col_start.push_back((int32_t)k); col_x.push_back(X[i]); }
+        }
+        layer_col.push_back((int32_t)col_start.size());
+        col_start.push_back((int32_t)n_pts);
+        cudaFree(c->d_gx); cudaFree(c->d_gy); cudaFree(c->d_gfield); cudaFree(c->d_col_start);
+        cudaFree(c->d_col_x); cudaFree(c->d_layer_col); cudaFree(c->d_layer_z);
+        c->d_gx = c->d_gy = c->d_col_x = c->d_layer_z = nullptr;
+        c->d_gfield = c->d_col_start = c->d_layer_col = nullptr;
+        auto up = [&](auto **d, const auto &v) -> int {
+            using T = typename std::remove_reference<decltype(v)>::type::value_type;
+            EUT_CUDA(cudaMalloc((void **)d, std::max<size_t>(v.size(), 1) * sizeof(T)));
+            if (!v.empty()) EUT_CUDA(cudaMemcpy(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+            return EUT_OK;
+        };
+        EUT_TRY(up(&c->d_gx, gx)); EUT_TRY(up(&c->d_gy, gy)); EUT_TRY(up(&c->d_gfield, gf));
+        EUT_TRY(up(&c->d_col_start, col_start)); EUT_TRY(up(&c->d_col_x, col_x));
+        EUT_TRY(up(&c->d_layer_col, layer_col)); EUT_TRY(up(&c->d_layer_z, layer_z));
+        c->n_cols_g = (int64_t)col_x.size();
+        c->n_layers = (int64_t)layer_z.size();
+        c->n_pts = n_pts;
+        c->pts_hash = h;
+    }
+    // (2) count, scan, fill
+    const int64_t M = n_cells;
+    double *d_cell = nullptr;
+    EUT_TRY(ensure_tmp(c, (size_t)M * 4 * sizeof(double) + (size_t)(M + 1) * sizeof(int64_t) + 1024));
+    d_cell = (double *)c->d_tmp;
+    int64_t *d_counts = (int64_t *)(d_cell + 4 * M);
+    if (M > 0) {
+        EUT_CUDA(cudaMemcpyAsync(d_cell, cx, M * sizeof(double), cudaMemcpyHostToDevice, s));
+        EUT_CUDA(cudaMemcpyAsync(d_cell + M, cy, M * sizeof(double), cudaMemcpyHostToDevice, s));
+        EUT_CUDA(cudaMemcpyAsync(d_cell + 2 * M, csize, M * sizeof(double), cudaMemcpyHostToDevice, s));
+        EUT_CUDA(cudaMemcpyAsync(d_cell + 3 * M, cscv, M * sizeof(double), cudaMemcpyHostToDevice, s));
+    }
+    std::vector<int64_t> h_ptr(M + 1, 0);
+    if (M > 0) {
+        const unsigned nb = (unsigned)((M + 127) / 128);
+        k_cellmap<false><<<nb, 128, 0, s>>>(c->d_gx, c->d_gy, c->d_gfield, c->d_col_start, c->d_col_x,
+                                            c->d_layer_col, c->d_layer_z, (int)c->n_layers, d_cell,
+                                            d_cell + M, d_cell + 2 * M, d_cell + 3 * M, (int)M, dist_mode,
+                                            d_counts, nullptr, nullptr, nullptr, nullptr);
+        EUT_CUDA(cudaGetLastError());
+        std::vector<int64_t> h_cnt(M);
+        EUT_CUDA(cudaMemcpyAsync(h_cnt.data(), d_counts, M * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        EUT_CUDA(cudaStreamSynchronize(s));
+        for (int64_t i = 0; i < M; i++) h_ptr[i + 1] = h_ptr[i] + h_cnt[i];
+    }
+    const int64_t T = h_ptr[M];
+    if (T >= INT32_MAX) { set_error("eut_cells_build_lists: too many entries"); return EUT_ERR_UNSUPPORTED; }
+    // the cell arrays live in d_tmp: keep them alive across alloc_entries (which never touches d_tmp)
+    EUT_TRY(alloc_entries(c, M, T));
+    EUT_CUDA(cudaMemcpyAsync(c->d_cell_ptr, h_ptr.data(), (M + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    if (M > 0 && T > 0) {
+        const unsigned nb = (unsigned)((M + 127) / 128);
+        k_cellmap<true><<<nb, 128, 0, s>>>(c->d_gx, c->d_gy, c->d_gfield, c->d_col_start, c->d_col_x,
+                                           c->d_layer_col, c->d_layer_z, (int)c->n_layers, d_cell,
+                                           d_cell + M, d_cell + 2 * M, d_cell + 3 * M, (int)M, dist_mode,
+                                           nullptr, c->d_cell_ptr, c->d_fid, c->d_dist, c->d_acc);
+        EUT_CUDA(cudaGetLastError());
+    }
+    c->launches += 2;
+    EUT_CUDA(cudaStreamSynchronize(s));
+    return finish_lists(c, s);
+}
+
+int eut_cells_claim_rescale(eut_cells *c)
+{
+    clear_error();
+    if (!c) return EUT_ERR_ARG;
+    EUT_TRY(ensure_device(c->plan->device));
+    cudaStream_t s = 0;
+    EUT_TRY(build_transposed(c, s));
+    if (c->n_seg > 0) {
+        k_claim<<<(unsigned)((c->n_seg + 255) / 256), 256, 0, s>>>(c->d_seg_start, c->d_t_entry, c->d_acc, (int)c->n_seg);
+        c->launches++;
+        EUT_CUDA(cudaGetLastError());
+    }
+    EUT_CUDA(cudaStreamSynchronize(s));
+    return EUT_OK;
+}
+
+int64_t eut_cells_num_entries(const eut_cells *c) { return c ? c->T : 0; }
+
+int eut_cells_get_lists(const eut_cells *c, int64_t *cell_ptr, int32_t *field_id, double *field_dist,
+                        double *acc_prop)
+{
+    clear_error();
+    if (!c) return EUT_ERR_ARG;
+    EUT_TRY(ensure_device(c->plan->device));
+    EUT_CUDA(cudaDeviceSynchronize());
+    if (cell_ptr) {
+        if (c->d_cell_ptr) EUT_CUDA(cudaMemcpy(cell_ptr, c->d_cell_ptr, (c->M + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+        else cell_ptr[0] = 0;
+    }
+    if (c->T > 0) {
+        if (field_id) EUT_CUDA(cudaMemcpy(field_id, c->d_fid, c->T * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        if (field_dist) EUT_CUDA(cudaMemcpy(field_dist, c->d_dist, c->T * sizeof(double), cudaMemcpyDeviceToHost));
+        if (acc_prop) EUT_CUDA(cudaMemcpy(acc_prop, c->d_acc, c->T * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    return EUT_OK;
+}
+
+int eut_cells_gather(eut_cells *c, eut_field *f, double field_vol, double *fmol_host)
+{
+    clear_error();
+    if (!c || !f || f->plan != c->plan) { set_error("eut_cells_gather: cells and field must share a plan"); return EUT_ERR_ARG; }
+    EUT_TRY(ensure_device(c->plan->device));
+    const int64_t n = c->M * f->C;
+    if (n == 0) return EUT_OK;
+    EUT_TRY(grow(&c->d_fmol, &c->fmol_cap, n));
+    EUT_CUDA(cudaStreamSynchronize(0));  // list construction runs on the legacy stream
+    const unsigned nb = (unsigned)((n * 32 + 255) / 256);
+    k_gather<<<nb, 256, 0, f->stream>>>(f->d_buf, c->plan->Np, f->C * c->plan->Np, f->d_cur, c->d_cell_ptr,
+                                        c->d_fq, c->d_acc, field_vol, c->d_fmol, (int)c->M, (int)f->C);
+    f->launches++;
+    EUT_CUDA(cudaGetLastError());
+    if (fmol_host) {
+        EUT_CUDA(cudaMemcpyAsync(fmol_host, c->d_fmol, n * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+        EUT_CUDA(cudaStreamSynchronize(f->stream));
+    }
+    return EUT_OK;
+}
+
+int eut_cells_scatter(eut_cells *c, eut_field *f, double field_vol, const uint8_t *is_constant,
+                      const int64_t *ex_ptr, const int32_t *ex_cpd, const double *ex_flx)
+{
+    clear_error();
+    if (!c || !f || f->plan != c->plan || !ex_ptr) { set_error("eut_cells_scatter: bad argument"); return EUT_ERR_ARG; }
+    EUT_TRY(ensure_device(c->plan->device));
+    const int64_t M = c->M, X = ex_ptr[M];
+    if (M == 0 || X == 0 || c->T == 0) return EUT_OK;
+    if (!ex_cpd || !ex_flx) { set_error("eut_cells_scatter: NULL exchange arrays"); return EUT_ERR_ARG; }
+    for (int64_t e = 0; e < X; e++)
+        if (ex_cpd[e] < 1 || ex_cpd[e] > f->C) {
+            set_error("index out of bounds: exchange %lld refers to compound column %d of %lld", (long long)e + 1, ex_cpd[e], (long long)f->C);
+            return EUT_ERR_INDEX;
+        }
+    EUT_TRY(build_transposed(c, 0));
+    EUT_CUDA(cudaStreamSynchronize(0));
+    cudaStream_t s = f->stream;
+    EUT_TRY(grow(&c->d_ex_ptr, &c->exptr_cap, M + 1));
+    if (X > c->ex_cap || !c->d_ex_cpd) {
+        cudaFree(c->d_ex_cpd); cudaFree(c->d_ex_flx); cudaFree(c->d_ex_cs);
+        int64_t n = X + X / 8 + 16;
+        EUT_CUDA(cudaMalloc((void **)&c->d_ex_cpd, n * sizeof(int32_t)));
+        EUT_CUDA(cudaMalloc((void **)&c->d_ex_flx, n * sizeof(double)));
+        EUT_CUDA(cudaMalloc((void **)&c->d_ex_cs, n * sizeof(double)));
+        c->ex_cap = n;
+    }
+    EUT_CUDA(cudaMemcpyAsync(c->d_ex_ptr, ex_ptr, (M + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    EUT_CUDA(cudaMemcpyAsync(c->d_ex_cpd, ex_cpd, X * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    EUT_CUDA(cudaMemcpyAsync(c->d_ex_flx, ex_flx, X * sizeof(double), cudaMemcpyHostToDevice, s));
+    const uint8_t *d_const = nullptr;
+    if (is_constant) {
+        EUT_TRY(grow(&c->d_const, &c->const_cap, f->C));
+        EUT_CUDA(cudaMemcpyAsync(c->d_const, is_constant, f->C, cudaMemcpyHostToDevice, s));
+        d_const = c->d_const;
+    }
+    const int64_t bs = f->C * c->plan->Np;
+    k_ex_colsum<<<(unsigned)((M * 32 + 255) / 256), 256, 0, s>>>(f->d_buf, c->plan->Np, bs, f->d_cur, c->d_cell_ptr,
+                                                                c->d_fq, c->d_acc, field_vol, c->d_ex_ptr,
+                                                                c->d_ex_cpd, c->d_ex_flx, c->d_ex_cs, (int)M);
+    f->launches++;
+    constexpr int CH = 32, TH = 128;
+    const double vol_l = field_vol / 1e15;
+    for (int c0 = 0; c0 < f->C; c0 += CH) {
+        k_scatter<CH, TH><<<(unsigned)((c->n_seg + TH - 1) / TH), TH, 0, s>>>(
+            f->d_buf, c->plan->Np, bs, f->d_cur, c->d_seg_start, c->d_seg_fq, c->d_t_entry, c->d_ecell,
+            c->d_dist, c->d_acc, c->d_dmax, c->d_fsum, field_vol, vol_l, c->d_ex_ptr, c->d_ex_cpd,
+            c->d_ex_flx, c->d_ex_cs, d_const, (int)c->n_seg, c0, (int)f->C);
+        f->launches++;
+    }
+    EUT_CUDA(cudaGetLastError());
+    // ex_* host arrays may be pageable: the copies above were staged before returning
+    return EUT_OK;
+}
+
+}  // extern "C"

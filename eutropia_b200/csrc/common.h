@@ -1,0 +1,139 @@
+// Internal declarations shared by the translation units of libeutropia_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/eutropia_b200.h"
+
+namespace eut {
+
+void set_error(const char *fmt, ...);
+void clear_error();
+
+#define EUT_CUDA(call)                                                                      \
+    do {                                                                                    \
+        cudaError_t e__ = (call);                                                           \
+        if (e__ != cudaSuccess) {                                                           \
+            eut::set_error("%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__,      \
+                           __LINE__);                                                       \
+            return EUT_ERR_CUDA;                                                            \
+        }                                                                                   \
+    } while (0)
+
+#define EUT_TRY(call)                \
+    do {                             \
+        int rc__ = (call);           \
+        if (rc__ != EUT_OK) return rc__; \
+    } while (0)
+
+// 1/13: the share of a field's content that moves to each of its (at most 12) neighbours per
+// substep, src/diffChange.cpp:8.
+constexpr double kBDiv = 1.0 / 13;
+
+constexpr int kEllMax = 12;       // widest in-neighbour list the ELL fast path handles
+constexpr int kPadPoints = 64;    // column stride is a multiple of this many points (512 B)
+
+int ensure_device(int device);
+double now_ms();
+
+}  // namespace eut
+
+// ---------------------------------------------------------------------------------------------
+// plan: neighbour graph resident on one GPU
+// ---------------------------------------------------------------------------------------------
+struct eut_plan {
+    int device = 0;
+    int64_t N = 0, E = 0, Np = 0;
+    int max_in = 0, ell_w = 0, order = 0, regular_out = 0, n_tiles = 0;
+    int64_t device_bytes = 0;
+    double build_ms = 0;
+    uint64_t graph_hash = 0;
+
+    // host, reference ids, 0-based: in-neighbours per destination in mat.in row order
+    std::vector<int64_t> row_ptr;
+    std::vector<int32_t> col;
+    std::vector<int32_t> perm;   // reference id (0-based) -> internal position
+    std::vector<int32_t> iperm;  // internal position -> reference id (0-based), -1 for padding
+
+    // device, internal order
+    int32_t *d_nbr = nullptr;    // [ell_w][Np] internal ids of in-neighbours, mat.in order
+    uint8_t *d_deg = nullptr;    // [Np] in-degree
+    double *d_w = nullptr;       // [Np] (n_neighbors - 1) * (1/13)   (regular outflow only)
+    int32_t *d_perm = nullptr;   // [N]
+    int32_t *d_iperm = nullptr;  // [Np]
+    // generic path (any in-degree, any number of mat.out rows per point)
+    int64_t *d_row_ptr = nullptr;  // [N+1] internal order
+    int32_t *d_col = nullptr;      // [E] internal ids
+    int64_t *d_out_ptr = nullptr;  // [N+1]
+    double *d_out_w = nullptr;     // [n_nn]  (nn_j - 1) * (1/13), in mat.out row order per point
+};
+
+// ---------------------------------------------------------------------------------------------
+// field: N x C concentrations resident in HBM (two buffers, Jacobi ping-pong per column)
+// ---------------------------------------------------------------------------------------------
+struct eut_field {
+    eut_plan *plan = nullptr;
+    int64_t C = 0;
+    double *d_buf = nullptr;           // [2][C][Np]
+    std::vector<uint8_t> cur;          // which buffer holds column c now
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;
+    // staging for host <-> device column transfers (reference order)
+    double *d_stage = nullptr;
+    int64_t stage_cols = 0;
+    // active-column tables of the current diffuse call
+    int32_t *d_act = nullptr;          // [2][cap]: column, starting buffer
+    int64_t act_cap = 0;
+    std::vector<int32_t> h_act;        // host mirror (kept alive for async copies)
+    int32_t *d_cur = nullptr;          // [C] device mirror of cur
+    std::vector<int32_t> h_cur32;
+    int32_t *d_cols = nullptr;         // [2][C] scratch: column lists of transfers in flight
+    std::vector<int32_t> h_cols;
+    double *d_stage2 = nullptr;        // second staging buffer (download direction)
+    cudaEvent_t ev_stage_free[2] = {nullptr, nullptr};
+    cudaEvent_t ev_stage_ready[2] = {nullptr, nullptr};
+    cudaStream_t down_stream = nullptr;
+    cudaEvent_t ev_dstage_free[2] = {nullptr, nullptr};
+    cudaEvent_t ev_dstage_ready[2] = {nullptr, nullptr};
+    int64_t up_chunks = 0, down_chunks = 0;
+    double *d_stats = nullptr;         // [3][C]
+    int64_t launches = 0;
+    // options
+    int opt_cpt = 0;      // compounds per thread (0 = auto)
+    int opt_block = 256;
+    int opt_variant = 0;  // 0 auto, 1 ell, 2 generic
+    int opt_group_cols = 0;  // 0: substep-major over all active columns; >0: column groups
+};
+
+namespace eut {
+int plan_build(eut_plan *p, const int32_t *from, const int32_t *to, int64_t n_edges,
+               const int32_t *nn_id, const int32_t *nn_cnt, int64_t n_nn, int64_t n_points,
+               int device, uint32_t flags);
+void plan_free(eut_plan *p);
+uint64_t hash_bytes(const void *data, size_t n, uint64_t seed);
+
+// field.cu
+int field_create(eut_field **out, eut_plan *plan, int64_t n_cols);
+int field_destroy(eut_field *f);
+int field_upload(eut_field *f, const double *host, int64_t ld, const int32_t *cols, int64_t n_cols);
+int field_download_async(eut_field *f, double *host, int64_t ld, const int32_t *cols, int64_t n_cols);
+int field_sync_down(eut_field *f);
+int field_diffuse(eut_field *f, const int32_t *niter, const int32_t *indvar, int64_t n_indvar);
+
+// stencil.cu
+int launch_substep(eut_field *f, int n_act, int substep);
+int launch_permute_in(eut_field *f, const double *d_stage, int64_t ld, const int32_t *d_cols,
+                      const int32_t *d_cur, int64_t n_cols, cudaStream_t s);
+int launch_permute_out(eut_field *f, double *d_stage, int64_t ld, const int32_t *d_cols,
+                       const int32_t *d_cur, int64_t n_cols, cudaStream_t s);
+int launch_column_stats(eut_field *f, const int32_t *d_cur);
+const char *last_error_cstr();
+int launch_fill_column(eut_field *f, int32_t col0, double value);
+}  // namespace eut

@@ -1,0 +1,239 @@
+// Field residency: allocation, host<->device column transfers (chunked, double-buffered, on their
+// own copy streams) and the substep schedule of a diffuse call.
+#include <algorithm>
+#include <numeric>
+
+#include "common.h"
+
+namespace eut {
+
+static constexpr int64_t kStageBytes = 64ll << 20;  // per staging slot
+
+static int field_alloc(eut_field *f)
+{
+    const eut_plan *p = f->plan;
+    const int64_t C = std::max<int64_t>(f->C, 1);
+    const size_t buf_bytes = (size_t)2 * C * p->Np * sizeof(double);
+    EUT_CUDA(cudaMalloc((void **)&f->d_buf, buf_bytes));
+    EUT_CUDA(cudaMemset(f->d_buf, 0, buf_bytes));
+    f->cur.assign(C, 0);
+    f->h_cur32.assign(C, 0);
+    EUT_CUDA(cudaMalloc((void **)&f->d_cur, C * sizeof(int32_t)));
+    EUT_CUDA(cudaMemset(f->d_cur, 0, C * sizeof(int32_t)));
+    f->act_cap = C;
+    EUT_CUDA(cudaMalloc((void **)&f->d_act, 2 * C * sizeof(int32_t)));
+    f->h_act.assign(2 * C, 0);
+    EUT_CUDA(cudaMalloc((void **)&f->d_cols, 4 * C * sizeof(int32_t)));
+    f->h_cols.assign(4 * C, 0);
+    EUT_CUDA(cudaMalloc((void **)&f->d_stats, 3 * C * sizeof(double)));
+    const int64_t n = std::max<int64_t>(p->N, 1);
+    f->stage_cols = std::max<int64_t>(1, std::min<int64_t>(C, kStageBytes / (8 * n)));
+    const size_t stage_bytes = (size_t)f->stage_cols * n * sizeof(double);
+    EUT_CUDA(cudaMalloc((void **)&f->d_stage, 2 * stage_bytes));
+    EUT_CUDA(cudaMalloc((void **)&f->d_stage2, 2 * stage_bytes));
+    EUT_CUDA(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
+    f->own_stream = true;
+    EUT_CUDA(cudaStreamCreateWithFlags(&f->copy_stream, cudaStreamNonBlocking));
+    EUT_CUDA(cudaStreamCreateWithFlags(&f->down_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        EUT_CUDA(cudaEventCreateWithFlags(&f->ev_stage_free[i], cudaEventDisableTiming));
+        EUT_CUDA(cudaEventCreateWithFlags(&f->ev_stage_ready[i], cudaEventDisableTiming));
+        EUT_CUDA(cudaEventCreateWithFlags(&f->ev_dstage_free[i], cudaEventDisableTiming));
+        EUT_CUDA(cudaEventCreateWithFlags(&f->ev_dstage_ready[i], cudaEventDisableTiming));
+    }
+    return EUT_OK;
+}
+
+int field_create(eut_field **out, eut_plan *plan, int64_t n_cols)
+{
+    if (!out || !plan || n_cols < 0) {
+        set_error("eut_field_create: bad argument");
+        return EUT_ERR_ARG;
+    }
+    EUT_TRY(ensure_device(plan->device));
+    eut_field *f = new eut_field();
+    f->plan = plan;
+    f->C = n_cols;
+    int rc = field_alloc(f);
+    if (rc != EUT_OK) {
+        field_destroy(f);
+        return rc;
+    }
+    *out = f;
+    return EUT_OK;
+}
+
+int field_destroy(eut_field *f)
+{
+    if (!f) return EUT_OK;
+    cudaSetDevice(f->plan->device);
+    if (f->stream) cudaStreamSynchronize(f->stream);
+    if (f->copy_stream) cudaStreamSynchronize(f->copy_stream);
+    if (f->down_stream) cudaStreamSynchronize(f->down_stream);
+    cudaFree(f->d_buf); cudaFree(f->d_cur); cudaFree(f->d_act); cudaFree(f->d_cols);
+    cudaFree(f->d_stats); cudaFree(f->d_stage); cudaFree(f->d_stage2);
+    for (int i = 0; i < 2; i++) {
+        if (f->ev_stage_free[i]) cudaEventDestroy(f->ev_stage_free[i]);
+        if (f->ev_stage_ready[i]) cudaEventDestroy(f->ev_stage_ready[i]);
+        if (f->ev_dstage_free[i]) cudaEventDestroy(f->ev_dstage_free[i]);
+        if (f->ev_dstage_ready[i]) cudaEventDestroy(f->ev_dstage_ready[i]);
+    }
+    if (f->own_stream && f->stream) cudaStreamDestroy(f->stream);
+    if (f->copy_stream) cudaStreamDestroy(f->copy_stream);
+    if (f->down_stream) cudaStreamDestroy(f->down_stream);
+    delete f;
+    return EUT_OK;
+}
+
+static int check_cols(const eut_field *f, const int32_t *cols, int64_t n_cols, const char *who)
+{
+    if (n_cols < 0 || (!cols && n_cols > f->C)) {
+        set_error("%s: %lld columns requested, field has %lld", who, (long long)n_cols,
+                  (long long)f->C);
+        return EUT_ERR_INDEX;
+    }
+    if (cols)
+        for (int64_t j = 0; j < n_cols; j++)
+            if (cols[j] < 1 || cols[j] > f->C) {
+                set_error("%s: column %d out of bounds (field has %lld columns)", who, cols[j],
+                          (long long)f->C);
+                return EUT_ERR_INDEX;
+            }
+    return EUT_OK;
+}
+
+// host -> device.  Chunk g uses staging slot g&1: copy_stream moves the columns (reference order),
+// the compute stream permutes them into the field; events hand the slot back and forth.
+int field_upload(eut_field *f, const double *host, int64_t ld, const int32_t *cols, int64_t n_cols)
+{
+    const eut_plan *p = f->plan;
+    EUT_TRY(check_cols(f, cols, n_cols, "eut_field_upload"));
+    if (n_cols == 0 || p->N == 0) return EUT_OK;
+    if (!host || ld < p->N) {
+        set_error("eut_field_upload: NULL host pointer or ld < N");
+        return EUT_ERR_ARG;
+    }
+    EUT_TRY(ensure_device(p->device));
+    const int64_t N = p->N;
+    for (int64_t j0 = 0, g = f->up_chunks; j0 < n_cols; j0 += f->stage_cols, g++) {
+        const int slot = (int)(g & 1);
+        const int64_t nc = std::min(f->stage_cols, n_cols - j0);
+        double *stage = f->d_stage + (size_t)slot * f->stage_cols * N;
+        int32_t *hc = f->h_cols.data() + (size_t)slot * f->C;
+        for (int64_t j = 0; j < nc; j++) hc[j] = cols ? cols[j0 + j] - 1 : (int32_t)(j0 + j);
+        if (g >= 2) EUT_CUDA(cudaStreamWaitEvent(f->copy_stream, f->ev_stage_free[slot], 0));
+        EUT_CUDA(cudaMemcpy2DAsync(stage, N * sizeof(double), host + (size_t)j0 * ld,
+                                   ld * sizeof(double), N * sizeof(double), nc,
+                                   cudaMemcpyHostToDevice, f->copy_stream));
+        EUT_CUDA(cudaEventRecord(f->ev_stage_ready[slot], f->copy_stream));
+        EUT_CUDA(cudaStreamWaitEvent(f->stream, f->ev_stage_ready[slot], 0));
+        int32_t *dc = f->d_cols + (size_t)slot * f->C;
+        EUT_CUDA(cudaMemcpyAsync(dc, hc, nc * sizeof(int32_t), cudaMemcpyHostToDevice, f->stream));
+        EUT_TRY(launch_permute_in(f, stage, N, dc, f->d_cur, nc, f->stream));
+        EUT_CUDA(cudaEventRecord(f->ev_stage_free[slot], f->stream));
+        f->up_chunks = g + 1;
+    }
+    return EUT_OK;
+}
+
+// device -> host, asynchronous: the caller must field_sync_down() before reading `host`.
+int field_download_async(eut_field *f, double *host, int64_t ld, const int32_t *cols, int64_t n_cols)
+{
+    const eut_plan *p = f->plan;
+    EUT_TRY(check_cols(f, cols, n_cols, "eut_field_download"));
+    if (n_cols == 0 || p->N == 0) return EUT_OK;
+    if (!host || ld < p->N) {
+        set_error("eut_field_download: NULL host pointer or ld < N");
+        return EUT_ERR_ARG;
+    }
+    EUT_TRY(ensure_device(p->device));
+    const int64_t N = p->N;
+    for (int64_t j0 = 0, g = f->down_chunks; j0 < n_cols; j0 += f->stage_cols, g++) {
+        const int slot = (int)(g & 1);
+        const int64_t nc = std::min(f->stage_cols, n_cols - j0);
+        double *stage = f->d_stage2 + (size_t)slot * f->stage_cols * N;
+        int32_t *hc = f->h_cols.data() + (size_t)(2 + slot) * f->C;
+        for (int64_t j = 0; j < nc; j++) hc[j] = cols ? cols[j0 + j] - 1 : (int32_t)(j0 + j);
+        int32_t *dc = f->d_cols + (size_t)(2 + slot) * f->C;
+        if (g >= 2) EUT_CUDA(cudaStreamWaitEvent(f->stream, f->ev_dstage_free[slot], 0));
+        EUT_CUDA(cudaMemcpyAsync(dc, hc, nc * sizeof(int32_t), cudaMemcpyHostToDevice, f->stream));
+        EUT_TRY(launch_permute_out(f, stage, N, dc, f->d_cur, nc, f->stream));
+        EUT_CUDA(cudaEventRecord(f->ev_dstage_ready[slot], f->stream));
+        EUT_CUDA(cudaStreamWaitEvent(f->down_stream, f->ev_dstage_ready[slot], 0));
+        EUT_CUDA(cudaMemcpy2DAsync(host + (size_t)j0 * ld, ld * sizeof(double), stage,
+                                   N * sizeof(double), N * sizeof(double), nc,
+                                   cudaMemcpyDeviceToHost, f->down_stream));
+        EUT_CUDA(cudaEventRecord(f->ev_dstage_free[slot], f->down_stream));
+        f->down_chunks = g + 1;
+    }
+    return EUT_OK;
+}
+
+int field_sync_down(eut_field *f)
+{
+    EUT_CUDA(cudaStreamSynchronize(f->down_stream));
+    return EUT_OK;
+}
+
+// diffChangePar contract: niter[i] substeps on column indvar[i] (src/diffChange.cpp:45-64).
+// Columns are sorted by substep count (descending) so that the set still active at substep s is a
+// prefix of the table; every substep is one launch over that prefix.
+int field_diffuse(eut_field *f, const int32_t *niter, const int32_t *indvar, int64_t n_indvar)
+{
+    const eut_plan *p = f->plan;
+    if (n_indvar < 0 || (n_indvar > 0 && (!niter || !indvar))) {
+        set_error("eut_field_diffuse: bad argument");
+        return EUT_ERR_ARG;
+    }
+    if (n_indvar == 0) return EUT_OK;
+    EUT_TRY(ensure_device(p->device));
+    std::vector<uint8_t> seen(f->C, 0);
+    for (int64_t i = 0; i < n_indvar; i++) {
+        // the reference only touches conc(., indvar-1) inside the substep loop: a bad column with
+        // zero substeps is never dereferenced there (src/diffChange.cpp:48-54)
+        if (niter[i] <= 0) continue;
+        if (indvar[i] < 1 || indvar[i] > f->C) {
+            set_error("index out of bounds: indvar[%lld] = %d, field has %lld columns",
+                      (long long)i + 1, indvar[i], (long long)f->C);
+            return EUT_ERR_INDEX;
+        }
+        if (seen[indvar[i] - 1]) {
+            set_error("eut_field_diffuse: column %d listed twice in indvar (data race in the "
+                      "reference's OpenMP loop, src/diffChange.cpp:44-63)", indvar[i]);
+            return EUT_ERR_ARG;
+        }
+        seen[indvar[i] - 1] = 1;
+    }
+    std::vector<int64_t> order;
+    for (int64_t i = 0; i < n_indvar; i++)
+        if (niter[i] > 0) order.push_back(i);
+    if (order.empty()) return EUT_OK;
+    std::stable_sort(order.begin(), order.end(),
+                     [&](int64_t a, int64_t b) { return niter[a] > niter[b]; });
+    const int n_tot = (int)order.size();
+    for (int a = 0; a < n_tot; a++) {
+        const int c = indvar[order[a]] - 1;
+        f->h_act[a] = c;
+        f->h_act[f->act_cap + a] = f->cur[c];
+    }
+    EUT_CUDA(cudaMemcpyAsync(f->d_act, f->h_act.data(), n_tot * sizeof(int32_t),
+                             cudaMemcpyHostToDevice, f->stream));
+    EUT_CUDA(cudaMemcpyAsync(f->d_act + f->act_cap, f->h_act.data() + f->act_cap,
+                             n_tot * sizeof(int32_t), cudaMemcpyHostToDevice, f->stream));
+    const int max_it = niter[order[0]];
+    int n_act = n_tot;
+    for (int s = 0; s < max_it; s++) {
+        while (n_act > 0 && niter[order[n_act - 1]] <= s) n_act--;
+        EUT_TRY(launch_substep(f, n_act, s));
+    }
+    for (int a = 0; a < n_tot; a++) {
+        const int c = indvar[order[a]] - 1;
+        f->cur[c] = (uint8_t)((f->cur[c] + niter[order[a]]) & 1);
+        f->h_cur32[c] = f->cur[c];
+    }
+    EUT_CUDA(cudaMemcpyAsync(f->d_cur, f->h_cur32.data(), f->C * sizeof(int32_t),
+                             cudaMemcpyHostToDevice, f->stream));
+    return EUT_OK;
+}
+
+}  // namespace eut

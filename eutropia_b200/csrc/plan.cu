@@ -1,0 +1,281 @@
+// Plan construction: host-side analysis of mat.in / mat.out and upload of the device-resident
+// neighbour tables.  The graph is consumed exactly as given (R/growthEnvironment.R:138-149 builds
+// it once per simulation); nothing is regenerated from geometry.
+#include <algorithm>
+#include <chrono>
+#include <numeric>
+
+#include "common.h"
+
+namespace eut {
+
+static thread_local std::string g_err;
+
+void set_error(const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+void clear_error() { g_err.clear(); }
+const char *last_error_cstr() { return g_err.c_str(); }
+
+double now_ms()
+{
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+int ensure_device(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        set_error("no CUDA device available (%s); eutropia_b200 has no CPU path",
+                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return EUT_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) {
+        set_error("device ordinal %d out of range (have %d)", device, n);
+        return EUT_ERR_ARG;
+    }
+    EUT_CUDA(cudaSetDevice(device));
+    return EUT_OK;
+}
+
+uint64_t hash_bytes(const void *data, size_t n, uint64_t seed)
+{
+    // 64-bit multiply-rotate over 8-byte words; only used to recognise "same graph as last call".
+    const uint8_t *p = static_cast<const uint8_t *>(data);
+    uint64_t h = seed ^ (n * 0x9E3779B97F4A7C15ull);
+    size_t nw = n / 8;
+    for (size_t i = 0; i < nw; i++) {
+        uint64_t w;
+        memcpy(&w, p + 8 * i, 8);
+        h ^= w * 0xC2B2AE3D27D4EB4Full;
+        h = (h << 31) | (h >> 33);
+        h *= 0x9E3779B97F4A7C15ull;
+    }
+    uint64_t tail = 0;
+    memcpy(&tail, p + 8 * nw, n - 8 * nw);
+    h ^= tail * 0x165667B19E3779F9ull;
+    h ^= h >> 29;
+    h *= 0xBF58476D1CE4E5B9ull;
+    h ^= h >> 32;
+    return h;
+}
+
+template <typename T>
+static int upload(T **dptr, const std::vector<T> &h, int64_t *bytes)
+{
+    size_t n = h.size() ? h.size() : 1;
+    EUT_CUDA(cudaMalloc(reinterpret_cast<void **>(dptr), n * sizeof(T)));
+    if (!h.empty())
+        EUT_CUDA(cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *bytes += (int64_t)(n * sizeof(T));
+    return EUT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Internal point ordering.  Any permutation is arithmetically neutral: the per-destination
+// summation order is the mat.in row order stored in the neighbour tables, not the memory order.
+// ---------------------------------------------------------------------------------------------
+static void order_identity(eut_plan *p)
+{
+    p->perm.resize(p->N);
+    std::iota(p->perm.begin(), p->perm.end(), 0);
+}
+
+// ROWBLOCK: derive "rows" (maximal chains i, i+1, ... joined by edges in both directions -- in the
+// reference's numbering these are the raster rows of one layer, R/growthEnvironment.R:86-88) and
+// order whole rows by a breadth-first sweep over the row adjacency graph, so that the rows a row
+// exchanges with (same layer y+-1, adjacent layers) sit next to it in memory instead of a whole
+// layer away.  Points keep their order inside a row, so warps still read runs of consecutive ids.
+static void order_rowblock(eut_plan *p)
+{
+    const int64_t N = p->N;
+    std::vector<uint8_t> linked(N, 0);  // linked[i]: edge (i+1 -> i) and (i -> i+1) both exist
+    auto has_in = [&](int64_t dst, int32_t src) {
+        for (int64_t k = p->row_ptr[dst]; k < p->row_ptr[dst + 1]; k++)
+            if (p->col[k] == src) return true;
+        return false;
+    };
+    for (int64_t i = 0; i + 1 < N; i++)
+        linked[i] = has_in(i, (int32_t)(i + 1)) && has_in(i + 1, (int32_t)i);
+    std::vector<int32_t> row_of(N);
+    std::vector<int64_t> row_start;
+    for (int64_t i = 0; i < N; i++) {
+        if (i == 0 || !linked[i - 1]) row_start.push_back(i);
+        row_of[i] = (int32_t)row_start.size() - 1;
+    }
+    const int64_t R = (int64_t)row_start.size();
+    row_start.push_back(N);
+
+    // BFS over rows, visiting the neighbours of a row in ascending row id; restart at the lowest
+    // unvisited row for disconnected pieces.
+    std::vector<uint8_t> seen(R, 0);
+    std::vector<int32_t> row_order;
+    row_order.reserve(R);
+    std::vector<int32_t> nb;
+    for (int64_t seed = 0; seed < R; seed++) {
+        if (seen[seed]) continue;
+        seen[seed] = 1;
+        size_t head = row_order.size();
+        row_order.push_back((int32_t)seed);
+        while (head < row_order.size()) {
+            int32_t r = row_order[head++];
+            nb.clear();
+            for (int64_t i = row_start[r]; i < row_start[r + 1]; i++)
+                for (int64_t k = p->row_ptr[i]; k < p->row_ptr[i + 1]; k++) {
+                    int32_t rr = row_of[p->col[k]];
+                    if (!seen[rr]) { seen[rr] = 1; nb.push_back(rr); }
+                }
+            std::sort(nb.begin(), nb.end());
+            for (int32_t rr : nb) row_order.push_back(rr);
+        }
+    }
+    p->perm.resize(N);
+    int64_t pos = 0;
+    for (int32_t r : row_order)
+        for (int64_t i = row_start[r]; i < row_start[r + 1]; i++) p->perm[i] = (int32_t)pos++;
+    p->n_tiles = (int)R;
+}
+
+int plan_build(eut_plan *p, const int32_t *from, const int32_t *to, int64_t n_edges,
+               const int32_t *nn_id, const int32_t *nn_cnt, int64_t n_nn, int64_t n_points,
+               int device, uint32_t flags)
+{
+    const double t0 = now_ms();
+    if (n_edges < 0 || n_nn < 0 || n_points < 0 || (n_edges > 0 && (!from || !to)) ||
+        (n_nn > 0 && (!nn_id || !nn_cnt))) {
+        set_error("eut_plan_create: NULL pointer or negative size");
+        return EUT_ERR_ARG;
+    }
+    if (n_points >= (int64_t)INT32_MAX - 2 * kPadPoints) {
+        set_error("eut_plan_create: %lld points exceed the int32 index range of the reference",
+                  (long long)n_points);
+        return EUT_ERR_UNSUPPORTED;
+    }
+    EUT_TRY(ensure_device(device));
+    p->device = device;
+    p->N = n_points;
+    p->E = n_edges;
+    const int64_t N = n_points;
+
+    // -- bounds: where the reference's Armadillo accessors would throw ------------------------
+    for (int64_t j = 0; j < n_edges; j++) {
+        if (from[j] < 1 || from[j] > N || to[j] < 1 || to[j] > N) {
+            set_error("index out of bounds: mat.in row %lld = (%d, %d), field has %lld points",
+                      (long long)j + 1, from[j], to[j], (long long)N);
+            return EUT_ERR_INDEX;
+        }
+    }
+    for (int64_t j = 0; j < n_nn; j++) {
+        if (nn_id[j] < 1 || nn_id[j] > N) {
+            set_error("index out of bounds: mat.out row %lld id = %d, field has %lld points",
+                      (long long)j + 1, nn_id[j], (long long)N);
+            return EUT_ERR_INDEX;
+        }
+    }
+
+    // -- in-neighbour CSR: stable counting sort by `to`, keeps mat.in row order per destination
+    p->row_ptr.assign(N + 1, 0);
+    for (int64_t j = 0; j < n_edges; j++) p->row_ptr[to[j]]++;  // to is 1-based -> slot to[j]
+    for (int64_t i = 0; i < N; i++) p->row_ptr[i + 1] += p->row_ptr[i];
+    p->col.resize(n_edges);
+    {
+        std::vector<int64_t> fill(p->row_ptr.begin(), p->row_ptr.end() - 1);
+        for (int64_t j = 0; j < n_edges; j++) p->col[fill[to[j] - 1]++] = from[j] - 1;
+    }
+    p->max_in = 0;
+    for (int64_t i = 0; i < N; i++)
+        p->max_in = std::max<int>(p->max_in, (int)(p->row_ptr[i + 1] - p->row_ptr[i]));
+
+    // -- outflow rows per point, mat.out row order -------------------------------------------
+    std::vector<int64_t> out_ptr(N + 1, 0);
+    for (int64_t j = 0; j < n_nn; j++) out_ptr[nn_id[j]]++;
+    bool regular = (n_nn == N);
+    for (int64_t i = 0; i < N; i++) {
+        if (out_ptr[i + 1] != 1) regular = false;
+        out_ptr[i + 1] += out_ptr[i];
+    }
+    p->regular_out = regular ? 1 : 0;
+    std::vector<double> out_w(n_nn);
+    {
+        std::vector<int64_t> fill(out_ptr.begin(), out_ptr.end() - 1);
+        for (int64_t j = 0; j < n_nn; j++)
+            out_w[fill[nn_id[j] - 1]++] = (((double)nn_cnt[j]) - 1) * kBDiv;  // src/diffChange.cpp:60
+    }
+
+    // -- ordering -----------------------------------------------------------------------------
+    uint32_t order = flags & EUT_ORDER_MASK;
+    if (order == EUT_ORDER_AUTO) order = EUT_ORDER_ROWBLOCK;
+    if (order == EUT_ORDER_ROWBLOCK && N > 0) order_rowblock(p);
+    else { order = EUT_ORDER_IDENTITY; order_identity(p); }
+    p->order = (int)order;
+    p->Np = ((N + kPadPoints - 1) / kPadPoints) * kPadPoints;
+    if (p->Np == 0) p->Np = kPadPoints;
+    p->iperm.assign(p->Np, -1);
+    for (int64_t i = 0; i < N; i++) p->iperm[p->perm[i]] = (int32_t)i;
+
+    // -- device tables ------------------------------------------------------------------------
+    const bool ell_ok = regular && p->max_in <= kEllMax && !(flags & EUT_PLAN_FORCE_GENERIC);
+    p->device_bytes = 0;
+    EUT_TRY(upload(&p->d_perm, p->perm, &p->device_bytes));
+    EUT_TRY(upload(&p->d_iperm, p->iperm, &p->device_bytes));
+    if (ell_ok) {
+        p->ell_w = std::max(p->max_in, 1);
+        std::vector<int32_t> nbr((size_t)p->ell_w * p->Np);
+        std::vector<uint8_t> deg(p->Np, 0);
+        std::vector<double> w(p->Np, 0.0);
+        for (int64_t q = 0; q < p->Np; q++) {
+            int32_t i = p->iperm[q];
+            int d = 0;
+            if (i >= 0) {
+                d = (int)(p->row_ptr[i + 1] - p->row_ptr[i]);
+                deg[q] = (uint8_t)d;
+                w[q] = out_w[out_ptr[i]];
+                for (int k = 0; k < d; k++)
+                    nbr[(size_t)k * p->Np + q] = p->perm[p->col[p->row_ptr[i] + k]];
+            }
+            for (int k = d; k < p->ell_w; k++) nbr[(size_t)k * p->Np + q] = (int32_t)q;
+        }
+        EUT_TRY(upload(&p->d_nbr, nbr, &p->device_bytes));
+        EUT_TRY(upload(&p->d_deg, deg, &p->device_bytes));
+        EUT_TRY(upload(&p->d_w, w, &p->device_bytes));
+    } else {
+        p->ell_w = 0;
+        std::vector<int64_t> rp(N + 1, 0), op(N + 1, 0);
+        std::vector<int32_t> cl(n_edges);
+        std::vector<double> ow(n_nn);
+        for (int64_t q = 0; q < N; q++) {
+            int32_t i = p->iperm[q];
+            rp[q + 1] = rp[q] + (p->row_ptr[i + 1] - p->row_ptr[i]);
+            op[q + 1] = op[q] + (out_ptr[i + 1] - out_ptr[i]);
+            for (int64_t k = p->row_ptr[i], o = rp[q]; k < p->row_ptr[i + 1]; k++, o++)
+                cl[o] = p->perm[p->col[k]];
+            for (int64_t k = out_ptr[i], o = op[q]; k < out_ptr[i + 1]; k++, o++) ow[o] = out_w[k];
+        }
+        EUT_TRY(upload(&p->d_row_ptr, rp, &p->device_bytes));
+        EUT_TRY(upload(&p->d_col, cl, &p->device_bytes));
+        EUT_TRY(upload(&p->d_out_ptr, op, &p->device_bytes));
+        EUT_TRY(upload(&p->d_out_w, ow, &p->device_bytes));
+    }
+    p->build_ms = now_ms() - t0;
+    return EUT_OK;
+}
+
+void plan_free(eut_plan *p)
+{
+    if (!p) return;
+    cudaSetDevice(p->device);
+    cudaFree(p->d_nbr); cudaFree(p->d_deg); cudaFree(p->d_w); cudaFree(p->d_perm);
+    cudaFree(p->d_iperm); cudaFree(p->d_row_ptr); cudaFree(p->d_col); cudaFree(p->d_out_ptr);
+    cudaFree(p->d_out_w);
+}
+
+}  // namespace eut

@@ -1,0 +1,214 @@
+"""Session tier: graph, field and cell lists resident on one B200 (thin wrappers over the C ABI).
+
+`Plan` <- `mat.in` / `mat.out` (R/growthEnvironment.R:50-51), `Field` <- `concentrations` /
+`exoenzymes.conc` (:44, :56), `Cells` <- the per-cell lists of `get_cellFieldEnv_ex`
+(R/run_simulation.R:591-624).  All compute happens in libeutropia_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, ptr
+
+__all__ = ["Plan", "Field", "Cells"]
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _f64c(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _colmajor(a):
+    a = np.asarray(a)
+    if a.ndim == 1:
+        a = a.reshape(-1, 1)
+    return np.require(a, dtype=np.float64, requirements=["F", "A"])
+
+
+class Plan:
+    """The neighbour graph resident on a GPU, consumed exactly as given."""
+
+    def __init__(self, mat_in, mat_out, n_points=None, device=0, order=_lib.ORDER_AUTO,
+                 force_generic=False):
+        mat_in = np.asarray(mat_in).reshape(-1, 2)
+        mat_out = np.asarray(mat_out).reshape(-1, 2)
+        self._from, self._to = _i32(mat_in[:, 0]), _i32(mat_in[:, 1])
+        self._id, self._cnt = _i32(mat_out[:, 0]), _i32(mat_out[:, 1])
+        if n_points is None:
+            n_points = int(mat_out.shape[0])
+        flags = int(order) | (_lib.PLAN_FORCE_GENERIC if force_generic else 0)
+        h = C.c_void_p()
+        check(_lib.lib().eut_plan_create(C.byref(h), ptr(self._from), ptr(self._to),
+                                         self._from.shape[0], ptr(self._id), ptr(self._cnt),
+                                         self._id.shape[0], int(n_points), int(device), flags))
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().eut_plan_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @property
+    def info(self) -> _lib.PlanInfo:
+        inf = _lib.PlanInfo()
+        check(_lib.lib().eut_plan_get_info(self._h, C.byref(inf)))
+        return inf
+
+    @property
+    def n_points(self) -> int:
+        return int(self.info.n_points)
+
+    def csr(self):
+        """(row_ptr int64[N+1], col int32[E]) as the device tables hold them, in reference ids."""
+        inf = self.info
+        rp = np.zeros(inf.n_points + 1, dtype=np.int64)
+        col = np.zeros(max(inf.n_edges, 1), dtype=np.int32)
+        check(_lib.lib().eut_plan_get_csr(self._h, ptr(rp), ptr(col)))
+        return rp, col[:inf.n_edges]
+
+    def perm(self):
+        p = np.zeros(max(self.n_points, 1), dtype=np.int32)
+        check(_lib.lib().eut_plan_get_perm(self._h, ptr(p)))
+        return p[:self.n_points]
+
+
+class Field:
+    """N x C concentrations resident in HBM across rounds."""
+
+    def __init__(self, plan: Plan, n_cols: int):
+        self.plan = plan
+        self.n_cols = int(n_cols)
+        h = C.c_void_p()
+        check(_lib.lib().eut_field_create(C.byref(h), plan._h, self.n_cols))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().eut_field_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def upload(self, conc, cols=None):
+        """`conc`: N x len(cols) (or N x C) column-major host matrix; `cols` 1-based."""
+        a = _colmajor(conc)
+        c = None if cols is None else _i32(cols)
+        n = a.shape[1] if c is None else c.shape[0]
+        ld = a.strides[1] // 8 if a.shape[1] > 1 else max(a.shape[0], 1)
+        check(_lib.lib().eut_field_upload(self._h, ptr(a), ld, ptr(c), n))
+
+    def upload_ptr(self, host_ptr: int, ld: int, cols=None, n_cols=None):
+        c = None if cols is None else _i32(cols)
+        n = int(n_cols) if c is None else c.shape[0]
+        check(_lib.lib().eut_field_upload(self._h, C.c_void_p(host_ptr), int(ld), ptr(c), n))
+
+    def download(self, cols=None, out=None):
+        c = None if cols is None else _i32(cols)
+        n = self.n_cols if c is None else c.shape[0]
+        npts = self.plan.n_points
+        if out is None:
+            out = np.empty((npts, n), dtype=np.float64, order="F")
+        check(_lib.lib().eut_field_download(self._h, ptr(out), max(npts, 1), ptr(c), n))
+        return out
+
+    def download_ptr(self, host_ptr: int, ld: int, cols=None, n_cols=None):
+        c = None if cols is None else _i32(cols)
+        n = int(n_cols) if c is None else c.shape[0]
+        check(_lib.lib().eut_field_download(self._h, C.c_void_p(host_ptr), int(ld), ptr(c), n))
+
+    def diffuse(self, niter, indvar):
+        """`niter[i]` substeps on column `indvar[i]` (1-based): the diffChangePar contract."""
+        ni = _i32(np.trunc(np.asarray(niter, dtype=np.float64)))
+        iv = _i32(np.trunc(np.asarray(indvar, dtype=np.float64)))
+        if ni.shape[0] < iv.shape[0]:
+            raise _lib.EutropiaIndexError(_lib.ERR_INDEX, "niter is shorter than indvar")
+        check(_lib.lib().eut_field_diffuse(self._h, ptr(ni), ptr(iv), iv.shape[0]))
+
+    def sync(self):
+        check(_lib.lib().eut_field_sync(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(_lib.lib().eut_field_stream(self._h) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(_lib.lib().eut_field_launch_count(self._h))
+
+    def set_option(self, name: str, value: int):
+        check(_lib.lib().eut_field_set_option(self._h, name.encode(), int(value)))
+
+    def column_stats(self):
+        mn = np.zeros(max(self.n_cols, 1)); mx = np.zeros_like(mn); me = np.zeros_like(mn)
+        check(_lib.lib().eut_field_column_stats(self._h, ptr(mn), ptr(mx), ptr(me)))
+        return mn[:self.n_cols], mx[:self.n_cols], me[:self.n_cols]
+
+    def fill_column(self, col: int, value: float):
+        check(_lib.lib().eut_field_fill_column(self._h, int(col), float(value)))
+
+
+class Cells:
+    """Ragged cell -> field lists on the device, with gather and scatter against a `Field`."""
+
+    def __init__(self, plan: Plan):
+        self.plan = plan
+        h = C.c_void_p()
+        check(_lib.lib().eut_cells_create(C.byref(h), plan._h))
+        self._h = h
+        self.n_cells = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().eut_cells_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def set_lists(self, cell_ptr, field_id, field_dist, acc_prop):
+        cp = np.ascontiguousarray(cell_ptr, dtype=np.int64)
+        fid, fd, acc = _i32(field_id), _f64c(field_dist), _f64c(acc_prop)
+        self.n_cells = cp.shape[0] - 1
+        check(_lib.lib().eut_cells_set_lists(self._h, self.n_cells, ptr(cp), ptr(fid), ptr(fd), ptr(acc)))
+
+    def build_lists(self, pts, cx, cy, csize, cscv, dist_mode=0):
+        p = _colmajor(pts)
+        cx, cy, csize, cscv = (_f64c(a) for a in (cx, cy, csize, cscv))
+        self.n_cells = cx.shape[0]
+        check(_lib.lib().eut_cells_build_lists(self._h, ptr(p), p.shape[0], ptr(cx), ptr(cy), ptr(csize),
+                                               ptr(cscv), self.n_cells, int(dist_mode)))
+
+    def claim_rescale(self):
+        check(_lib.lib().eut_cells_claim_rescale(self._h))
+
+    @property
+    def n_entries(self) -> int:
+        return int(_lib.lib().eut_cells_num_entries(self._h))
+
+    def get_lists(self):
+        t = self.n_entries
+        cp = np.zeros(self.n_cells + 1, dtype=np.int64)
+        fid = np.zeros(max(t, 1), dtype=np.int32)
+        fd = np.zeros(max(t, 1)); acc = np.zeros(max(t, 1))
+        check(_lib.lib().eut_cells_get_lists(self._h, ptr(cp), ptr(fid), ptr(fd), ptr(acc)))
+        return cp, fid[:t], fd[:t], acc[:t]
+
+    def gather(self, field: Field, field_vol: float, want_host=True):
+        out = np.zeros((self.n_cells, field.n_cols), dtype=np.float64, order="F") if want_host else None
+        check(_lib.lib().eut_cells_gather(self._h, field._h, float(field_vol), ptr(out)))
+        return out
+
+    def scatter(self, field: Field, field_vol: float, is_constant, ex_ptr, ex_cpd, ex_flx):
+        isc = None if is_constant is None else np.ascontiguousarray(is_constant, dtype=np.uint8)
+        ep = np.ascontiguousarray(ex_ptr, dtype=np.int64)
+        ec, ef = _i32(ex_cpd), _f64c(ex_flx)
+        check(_lib.lib().eut_cells_scatter(self._h, field._h, float(field_vol), ptr(isc), ptr(ep),
+                                           ptr(ec), ptr(ef)))

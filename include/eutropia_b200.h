@@ -1,0 +1,210 @@
+/*
+ * eutropia_b200 -- C ABI of the B200 (sm_100a) implementation of Eutropia's per-timestep compound
+ * diffusion + cell<->field exchange path.
+ *
+ * This header is the drop-in boundary.  Every entry point takes plain pointers and sizes (no R,
+ * Rcpp, Armadillo or torch types) and cites the reference interface it replaces; paths are relative
+ * to the reference tree (Waschina/Eutropia 0.1.7).  The Rcpp glue a maintainer adds on the R side
+ * is shown in INTEGRATION.md and shipped under rcpp/.
+ *
+ * Conventions (identical to the reference):
+ *   - matrices are column-major, field / compound indices are 1-based;
+ *   - concentrations are IEEE binary64; all arithmetic on the device is binary64 with
+ *     round-to-nearest and NO fused multiply-add, in the reference's operation order.
+ *
+ * Two tiers:
+ *   one-shot : eut_diffchange / eut_diffchange_par -- exact `diffChange` / `diffChangePar`
+ *              semantics, host buffers in, host buffer out (H2D + substeps + D2H per call);
+ *   session  : eut_plan_* (graph resident on a GPU), eut_field_* (field resident across rounds),
+ *              eut_cells_* (cell lists, gather, scatter) -- nothing crosses PCIe per round except
+ *              what the caller asks for.
+ *
+ * There is NO CPU fallback: without a usable CUDA device every compute entry point fails with
+ * EUT_ERR_CUDA / EUT_ERR_NO_DEVICE and says so in eut_last_error().
+ */
+#ifndef EUTROPIA_B200_H
+#define EUTROPIA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EUT_API __attribute__((visibility("default")))
+
+/* ---- status codes -------------------------------------------------------------------------- */
+enum {
+    EUT_OK             = 0,
+    EUT_ERR_INDEX      = 1,  /* an index is outside 1..N / 1..C: where Armadillo's bounds check
+                                (no ARMA_NO_DEBUG in src/Makevars) makes the reference raise an R
+                                error instead of reading out of range */
+    EUT_ERR_ARG        = 2,  /* NULL pointer, negative size, shape mismatch */
+    EUT_ERR_ALLOC      = 3,  /* host or device allocation failed */
+    EUT_ERR_CUDA       = 4,  /* a CUDA runtime call failed; text in eut_last_error() */
+    EUT_ERR_NO_DEVICE  = 5,  /* no CUDA device: this library has no CPU path */
+    EUT_ERR_UNSUPPORTED= 6,
+    EUT_ERR_NCCL       = 7
+};
+
+/* Message describing the last failure on the calling thread ("" if none). */
+EUT_API const char *eut_last_error(void);
+/* ABI version of this header (major*1000 + minor). */
+EUT_API int eut_abi_version(void);
+/* Number of usable CUDA devices (0 when there is no driver / no GPU). */
+EUT_API int eut_device_count(void);
+
+/* ---- one-shot tier: the two Rcpp entry points ------------------------------------------------
+ *
+ * eut_diffchange  replaces  diffChange(adjmat, nneighbors, conc, niter)
+ *     R closure            R/RcppExports.R:4-6
+ *     .Call symbol         _Eutropia_diffChange, src/RcppExports.cpp:16-27
+ *     implementation       src/diffChange.cpp:6-35
+ *   adjmat      n_edges x 2 doubles (from | to), cast with (int) like src/diffChange.cpp:20
+ *   nneighbors  n_nn x 2 doubles (id | n_neighbors), src/diffChange.cpp:26
+ *   conc_in     n_rows x n_cols; never written (R value semantics, SURVEY 8b "Ownership")
+ *   niter       n_niter doubles; column i runs while (int)k < niter[i] (src/diffChange.cpp:12-14);
+ *               columns >= n_niter are returned unchanged; n_niter > n_cols with a positive entry
+ *               beyond n_cols -> EUT_ERR_INDEX
+ *   conc_out    n_rows x n_cols, distinct from conc_in; receives the whole matrix (:34)
+ *   device      CUDA ordinal
+ */
+EUT_API int eut_diffchange(const double *adjmat, int64_t n_edges,
+                           const double *nneighbors, int64_t n_nn,
+                           const double *conc_in, int64_t n_rows, int64_t n_cols,
+                           const double *niter, int64_t n_niter,
+                           double *conc_out, int device);
+
+/* eut_diffchange_par  replaces  diffChangePar(adjmat, nneighbors, conc, niter, indvar, ncores)
+ *     R closure            R/RcppExports.R:8-10
+ *     .Call symbol         _Eutropia_diffChangePar, src/RcppExports.cpp:30-43
+ *     implementation       src/diffChange.cpp:38-69
+ *     live caller          diffuse_compoundsPar, R/growthEnvironment.R:385-390 and :417-422
+ *   adjmat / nneighbors    int32, column-major, 1-based
+ *   niter[i]               substeps of column indvar[i] (by position, src/diffChange.cpp:48)
+ *   indvar                 1-based column numbers, unique (the reference's OpenMP loop races
+ *                          otherwise, :44-45/:63); duplicates -> EUT_ERR_ARG here
+ *   ncores                 accepted for signature compatibility; the GPU path ignores it
+ */
+EUT_API int eut_diffchange_par(const int32_t *adjmat, int64_t n_edges,
+                               const int32_t *nneighbors, int64_t n_nn,
+                               const double *conc_in, int64_t n_rows, int64_t n_cols,
+                               const int32_t *niter, const int32_t *indvar, int64_t n_indvar,
+                               int ncores, double *conc_out, int device);
+
+/* Drop the cached plans / staging buffers the one-shot tier keeps between calls. */
+EUT_API void eut_oneshot_reset(void);
+
+/* ---- session tier: plan = neighbour graph resident on one GPU --------------------------------
+ *
+ * Consumes the `mat.in` / `mat.out` slots of growthEnvironment as given
+ * (R/growthEnvironment.R:50-51, built at :138-149): `from`/`to` are the two columns of mat.in,
+ * `nn_id`/`nn_cnt` the two columns of mat.out.  The graph is never regenerated from geometry.
+ * Per destination the inflow is summed in mat.in row order (stable sort by `to`).
+ */
+typedef struct eut_plan eut_plan;
+
+enum {                       /* eut_plan_create flags */
+    EUT_ORDER_AUTO      = 0, /* library picks the internal point ordering */
+    EUT_ORDER_IDENTITY  = 1, /* keep the reference's (layer-major) order */
+    EUT_ORDER_ROWBLOCK  = 2, /* locality ordering derived from the graph */
+    EUT_ORDER_MASK      = 0xf,
+    EUT_PLAN_FORCE_GENERIC = 0x10 /* use the generic CSR kernel even when the fast path applies */
+};
+
+typedef struct eut_plan_info {
+    int64_t n_points;        /* N */
+    int64_t n_edges;         /* E */
+    int64_t n_padded;        /* internal column stride (points) */
+    int32_t max_in_degree;
+    int32_t ell_width;       /* 0 when the generic CSR kernel is used */
+    int32_t order;           /* EUT_ORDER_* actually used */
+    int32_t regular_outflow; /* 1: exactly one mat.out row per point (the fast path) */
+    int32_t device;
+    int32_t n_tiles;
+    int64_t device_bytes;    /* graph bytes resident in HBM */
+    double  build_ms;        /* host analysis + upload time */
+} eut_plan_info;
+
+EUT_API int eut_plan_create(eut_plan **out,
+                            const int32_t *from, const int32_t *to, int64_t n_edges,
+                            const int32_t *nn_id, const int32_t *nn_cnt, int64_t n_nn,
+                            int64_t n_points, int device, uint32_t flags);
+EUT_API int eut_plan_destroy(eut_plan *plan);
+EUT_API int eut_plan_get_info(const eut_plan *plan, eut_plan_info *info);
+/* The in-neighbour index map the device uses, translated back to reference ids (1-based), for
+ * bit-exact comparison with the CSR derived from mat.in: row_ptr[N+1], col[E]. */
+EUT_API int eut_plan_get_csr(const eut_plan *plan, int64_t *row_ptr, int32_t *col);
+/* Internal position (0-based) of every reference point id: perm[N]. */
+EUT_API int eut_plan_get_perm(const eut_plan *plan, int32_t *perm);
+
+/* ---- session tier: field = N x C concentrations resident in HBM -------------------------------
+ * Mirrors growthEnvironment@concentrations (R/growthEnvironment.R:44) / @exoenzymes.conc (:56). */
+typedef struct eut_field eut_field;
+
+EUT_API int eut_field_create(eut_field **out, eut_plan *plan, int64_t n_cols);
+EUT_API int eut_field_destroy(eut_field *field);
+/* host -> device; `host` is column-major with leading dimension ld (>= N).  cols = NULL copies
+ * columns 1..n_cols of the field from host columns 0..n_cols-1; otherwise cols[i] (1-based field
+ * column) receives host column i. */
+EUT_API int eut_field_upload(eut_field *field, const double *host, int64_t ld,
+                             const int32_t *cols, int64_t n_cols);
+EUT_API int eut_field_download(eut_field *field, double *host, int64_t ld,
+                               const int32_t *cols, int64_t n_cols);
+/* `niter[i]` Jacobi substeps on column `indvar[i]` (the diffChangePar contract), asynchronous on
+ * the field's stream. */
+EUT_API int eut_field_diffuse(eut_field *field, const int32_t *niter, const int32_t *indvar,
+                              int64_t n_indvar);
+EUT_API int eut_field_sync(eut_field *field);
+/* cudaStream_t the field's work is enqueued on (for CUDA-event timing by the caller), and a
+ * setter to make the field use a caller-owned stream. */
+EUT_API void *eut_field_stream(eut_field *field);
+EUT_API int eut_field_set_stream(eut_field *field, void *cuda_stream);
+/* Number of kernels this field has launched since creation (bench.py's gpu_launches). */
+EUT_API int64_t eut_field_launch_count(const eut_field *field);
+/* Kernel variant selection for experiments: see DESIGN.md ("kernel variants"). */
+EUT_API int eut_field_set_option(eut_field *field, const char *name, int64_t value);
+/* Per-column reductions on the device (diffuse_compoundsPar's column selection and D = Inf rule,
+ * R/growthEnvironment.R:372, :393-401): writes min, max, mean of every column (arrays of n_cols). */
+EUT_API int eut_field_column_stats(eut_field *field, double *col_min, double *col_max,
+                                   double *col_mean);
+/* Overwrite a column with one value (D = Inf -> column mean, R/growthEnvironment.R:393-401). */
+EUT_API int eut_field_fill_column(eut_field *field, int32_t col, double value);
+
+/* ---- session tier: cells = ragged cell -> field lists + gather / scatter ----------------------
+ * Lists follow get_cellFieldEnv_ex's output (R/run_simulation.R:591-624): per cell the field ids
+ * (1-based), the cell-field distances and the accessible proportions, in CSR form. */
+typedef struct eut_cells eut_cells;
+
+EUT_API int eut_cells_create(eut_cells **out, eut_plan *plan);
+EUT_API int eut_cells_destroy(eut_cells *cells);
+/* Install lists computed elsewhere (e.g. by R): cell_ptr[n_cells+1] 0-based offsets. */
+EUT_API int eut_cells_set_lists(eut_cells *cells, int64_t n_cells, const int64_t *cell_ptr,
+                                const int32_t *field_id, const double *field_dist,
+                                const double *acc_prop);
+/* Build the lists on the device from geometry: replaces the per-cell box prefilter +
+ * get_cellFieldEnv_ex (R/run_simulation.R:217-232, :591-624).  pts is N x 3 column-major.
+ * dist_mode 0: planar xy distance (sf/GEOS), 1: xyz. */
+EUT_API int eut_cells_build_lists(eut_cells *cells, const double *pts, int64_t n_pts,
+                                  const double *cx, const double *cy, const double *csize,
+                                  const double *cscv, int64_t n_cells, int dist_mode);
+/* Oversubscribed-field rescale of acc_prop (R/run_simulation.R:236-241). */
+EUT_API int eut_cells_claim_rescale(eut_cells *cells);
+EUT_API int64_t eut_cells_num_entries(const eut_cells *cells);
+EUT_API int eut_cells_get_lists(const eut_cells *cells, int64_t *cell_ptr, int32_t *field_id,
+                                double *field_dist, double *acc_prop);
+/* Gather (R/run_simulation.R:249, R/scavenge_compounds.R:17-22): fmol[n_cells x n_cols]
+ * column-major = accessible fmol per cell and compound. */
+EUT_API int eut_cells_gather(eut_cells *cells, eut_field *field, double field_vol, double *fmol_host);
+/* Scatter + clamp (R/run_simulation.R:689-740, :309-319).  Per cell i the exchanges
+ * ex_ptr[i]..ex_ptr[i+1]: ex_cpd (1-based field column), ex_flx (fmol; <0 uptake, >0 production).
+ * is_constant[n_cols] (may be NULL) marks buffered compounds, which are left untouched. */
+EUT_API int eut_cells_scatter(eut_cells *cells, eut_field *field, double field_vol,
+                              const uint8_t *is_constant, const int64_t *ex_ptr,
+                              const int32_t *ex_cpd, const double *ex_flx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EUTROPIA_B200_H */

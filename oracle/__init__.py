@@ -1,0 +1,167 @@
+"""ctypes front-end of the CPU oracle (TEST INFRASTRUCTURE ONLY).
+
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s `cpu_baseline` / `--impl reference` legs
+may import this package.  The product package `eutropia_b200` never does (tests/test_boundary.py
+greps for it).  PARITY UNPINNED -- see the header of `diffchange_oracle.c`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle_eutropia.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with gcc (see oracle/Makefile)."""
+    srcs = [os.path.join(_HERE, f) for f in ("diffchange_oracle.c", "cellfield_oracle.c", "Makefile")]
+    stale = (not os.path.exists(_LIB_PATH)) or any(
+        os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True,
+                       stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        sz, dp, ip, lp = C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p
+        L.eut_oracle_diffchange.argtypes = [dp, sz, dp, sz, dp, sz, sz, dp, sz]
+        L.eut_oracle_diffchange.restype = C.c_int
+        L.eut_oracle_diffchange_par.argtypes = [ip, sz, ip, sz, dp, sz, sz, ip, ip, sz, C.c_int]
+        L.eut_oracle_diffchange_par.restype = C.c_int
+        L.eut_oracle_max_threads.restype = C.c_int
+        L.eut_oracle_cellmap.argtypes = [dp, sz, dp, dp, dp, dp, sz, C.c_int, lp, ip, dp, dp, C.c_long]
+        L.eut_oracle_cellmap.restype = C.c_long
+        L.eut_oracle_claim.argtypes = [ip, dp, C.c_long, sz]
+        L.eut_oracle_claim.restype = C.c_int
+        L.eut_oracle_gather.argtypes = [dp, sz, sz, lp, ip, dp, sz, C.c_double, dp, dp]
+        L.eut_oracle_gather.restype = C.c_int
+        L.eut_oracle_scatter.argtypes = [dp, sz, sz, C.c_void_p, lp, ip, dp, dp, sz, C.c_double,
+                                         lp, ip, dp]
+        L.eut_oracle_scatter.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a, order="F"):
+    return np.require(a, dtype=np.float64, requirements=[order, "A"])
+
+
+class OracleIndexError(IndexError):
+    """Mirrors the R error Armadillo's bounds check raises (`Mat::operator(): index out of bounds`)."""
+
+
+def _check(rc):
+    if rc == 1:
+        raise OracleIndexError("Mat::operator(): index out of bounds")
+    if rc:
+        raise MemoryError("oracle allocation failed")
+
+
+def max_threads() -> int:
+    return int(lib().eut_oracle_max_threads())
+
+
+def diffChange(adjmat, nneighbors, conc, niter):
+    """`diffChange(adjmat, nneighbors, conc, niter)` (src/diffChange.cpp:6-35): every argument is
+    converted to double like `arma::mat` / `arma::vec` do; returns a new matrix."""
+    adj = _f64(np.asarray(adjmat).reshape(-1, 2) if np.size(adjmat) else np.zeros((0, 2)))
+    nn = _f64(np.asarray(nneighbors).reshape(-1, 2) if np.size(nneighbors) else np.zeros((0, 2)))
+    out = np.array(conc, dtype=np.float64, order="F", copy=True)
+    if out.ndim == 1:
+        out = out.reshape(-1, 1, order="F")
+    nit = np.ascontiguousarray(np.asarray(niter, dtype=np.float64).ravel())
+    rc = lib().eut_oracle_diffchange(_p(adj), adj.shape[0], _p(nn), nn.shape[0], _p(out),
+                                     out.shape[0], out.shape[1], _p(nit), nit.shape[0])
+    _check(rc)
+    return out
+
+
+def diffChangePar(adjmat, nneighbors, conc, niter, indvar, ncores=1):
+    """`diffChangePar(...)` (src/diffChange.cpp:38-69): int32 indices (doubles are truncated like
+    Rcpp's conversion to `arma::Col<int>`), OpenMP over `indvar`; returns a new matrix."""
+    adj = np.require(np.asarray(adjmat).reshape(-1, 2), dtype=np.int32, requirements=["F", "A"])
+    nn = np.require(np.asarray(nneighbors).reshape(-1, 2), dtype=np.int32, requirements=["F", "A"])
+    out = np.array(conc, dtype=np.float64, order="F", copy=True)
+    if out.ndim == 1:
+        out = out.reshape(-1, 1, order="F")
+    nit = np.ascontiguousarray(np.trunc(np.asarray(niter, dtype=np.float64)).astype(np.int32).ravel())
+    iv = np.ascontiguousarray(np.trunc(np.asarray(indvar, dtype=np.float64)).astype(np.int32).ravel())
+    if nit.shape[0] < iv.shape[0]:
+        raise OracleIndexError("Mat::operator(): index out of bounds")  # niter(i), :48
+    rc = lib().eut_oracle_diffchange_par(_p(adj), adj.shape[0], _p(nn), nn.shape[0], _p(out),
+                                         out.shape[0], out.shape[1], _p(nit), _p(iv), iv.shape[0],
+                                         int(ncores))
+    _check(rc)
+    return out
+
+
+def cellmap(pts, cx, cy, csize, cscv, dist_mode=0):
+    """Cell -> field lists; returns (cell_ptr int64[M+1], field_id int32, field_dist, acc_prop)."""
+    pts = _f64(pts)
+    cx, cy, csize, cscv = (np.ascontiguousarray(a, dtype=np.float64) for a in (cx, cy, csize, cscv))
+    m = cx.shape[0]
+    ptr = np.zeros(m + 1, dtype=np.int64)
+    cap = max(1, 256 * m)
+    while True:
+        fid = np.zeros(cap, dtype=np.int32)
+        fd = np.zeros(cap, dtype=np.float64)
+        acc = np.zeros(cap, dtype=np.float64)
+        tot = lib().eut_oracle_cellmap(_p(pts), pts.shape[0], _p(cx), _p(cy), _p(csize), _p(cscv), m,
+                                       int(dist_mode), _p(ptr), _p(fid), _p(fd), _p(acc), cap)
+        if tot < 0:
+            raise MemoryError
+        if tot <= cap:
+            return ptr, fid[:tot].copy(), fd[:tot].copy(), acc[:tot].copy()
+        cap = int(tot)
+
+
+def claim(field_id, acc_prop, n_pts):
+    """Oversubscription rescale; returns the new acc_prop."""
+    fid = np.ascontiguousarray(field_id, dtype=np.int32)
+    acc = np.array(acc_prop, dtype=np.float64, copy=True)
+    _check(lib().eut_oracle_claim(_p(fid), _p(acc), fid.shape[0], int(n_pts)))
+    return acc
+
+
+def gather(conc, cell_ptr, field_id, acc_prop, field_vol, want_fpf=False):
+    conc = _f64(conc)
+    ptr = np.ascontiguousarray(cell_ptr, dtype=np.int64)
+    fid = np.ascontiguousarray(field_id, dtype=np.int32)
+    acc = np.ascontiguousarray(acc_prop, dtype=np.float64)
+    m = ptr.shape[0] - 1
+    fmol = np.zeros((m, conc.shape[1]), dtype=np.float64, order="F")
+    fpf = np.zeros((fid.shape[0], conc.shape[1]), dtype=np.float64, order="F") if want_fpf else None
+    _check(lib().eut_oracle_gather(_p(conc), conc.shape[0], conc.shape[1], _p(ptr), _p(fid), _p(acc),
+                                   m, float(field_vol), _p(fmol), _p(fpf)))
+    return (fmol, fpf) if want_fpf else fmol
+
+
+def scatter(conc, is_constant, cell_ptr, field_id, field_dist, acc_prop, field_vol,
+            ex_ptr, ex_cpd, ex_flx):
+    out = np.array(conc, dtype=np.float64, order="F", copy=True)
+    isc = None if is_constant is None else np.ascontiguousarray(is_constant, dtype=np.uint8)
+    ptr = np.ascontiguousarray(cell_ptr, dtype=np.int64)
+    fid = np.ascontiguousarray(field_id, dtype=np.int32)
+    fd = np.ascontiguousarray(field_dist, dtype=np.float64)
+    acc = np.ascontiguousarray(acc_prop, dtype=np.float64)
+    exp_ = np.ascontiguousarray(ex_ptr, dtype=np.int64)
+    exc = np.ascontiguousarray(ex_cpd, dtype=np.int32)
+    exf = np.ascontiguousarray(ex_flx, dtype=np.float64)
+    _check(lib().eut_oracle_scatter(_p(out), out.shape[0], out.shape[1], _p(isc), _p(ptr), _p(fid),
+                                    _p(fd), _p(acc), ptr.shape[0] - 1, float(field_vol),
+                                    _p(exp_), _p(exc), _p(exf)))
+    return out
