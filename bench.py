@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: field-point x compound diffusion updates/s on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A "step" is one simulated round of the hot path on a resident field: scatter of the cells' exchange
+fluxes (+clamp) -> S diffusion substeps on every compound -> gather of the accessible amounts
+(R/run_simulation.R:309-319, :380-383, :243-258).  Workload at N=1: BASELINE.json configs[2]
+(non-convex polygon, ~1M points x 64 compounds, 60 substeps, 50k cells); at N GPUs the same mesh with
+64*N compounds sharded by compound (configs[3] at N=8), no data-path collective -> weak scaling.
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the definition of every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "field-point*compound diffusion updates/s"
+UNIT = "updates/s"
+BYTES_PER_UPDATE = 16  # one fp64 read + one fp64 write per point, compound and substep
+
+WORKLOADS = {
+    # name: (mesh, compounds per GPU, substeps, cells, exchanges per cell)
+    "harbor1m": ("harbor1m", 64, 60, 50_000, 10),
+    "square100k": ("square100k", 16, 1000, 0, 0),
+    "harbor250k": ("harbor:250000", 64, 60, 12_500, 10),
+    "tiny": ("harbor:20000", 8, 10, 500, 4),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_inputs(workload: str, n_cols: int, seed: int, want_conc=True):
+    from eutropia_b200 import synth
+    mesh_name, _, substeps, n_cells, per_cell = WORKLOADS[workload]
+    mesh = synth.config_mesh(mesh_name)
+    conc = synth.synthetic_concentrations(mesh.field_pts, n_cols, seed=seed) if want_conc else None
+    cells = synth.place_cells(mesh, n_cells, seed=seed + 1) if n_cells else None
+    ex = synth.synthetic_exchanges(n_cells, n_cols, per_cell, seed=seed + 2) if n_cells else None
+    if ex is not None:
+        ex = (ex[0], ex[1], ex[2] * 1e-3)   # fmol per round, well below the accessible amounts
+    return mesh, conc, cells, ex, substeps
+
+
+def cpu_sample(mesh, substeps_full, n_cols_full, threads, target_s=12.0):
+    """Time the CPU oracle (restatement of diffChangePar, OpenMP over compounds like the reference)
+    on a bounded sample of the workload: same mesh, `threads` columns (one per thread, at most the
+    workload's columns), as many substeps as fit in about target_s."""
+    import oracle
+    from eutropia_b200 import synth
+    n = mesh.nfields
+    cols = int(max(1, min(n_cols_full, threads)))
+    conc = synth.synthetic_concentrations(mesh.field_pts, cols, seed=99)
+    iv = np.arange(1, cols + 1, dtype=np.int32)
+    t0 = time.perf_counter()
+    oracle.diffChangePar(mesh.mat_in, mesh.mat_out, conc, np.ones(cols, np.int32), iv, threads)
+    t1 = time.perf_counter() - t0
+    s = int(max(1, min(substeps_full, target_s / max(t1, 1e-6))))
+    t0 = time.perf_counter()
+    oracle.diffChangePar(mesh.mat_in, mesh.mat_out, conc, np.full(cols, s, np.int32), iv, threads)
+    dt = time.perf_counter() - t0
+    return {"value": n * cols * s / dt, "unit": UNIT, "cores": int(threads), "kind": "port",
+            "sample": f"{n} points x {cols} compounds x {s} substeps in {dt:.2f} s "
+                      f"(oracle/diffchange_oracle.c, OpenMP over compounds, {threads} threads)"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the Rcpp original cannot be
+    built here) on this box's host cores, same config and metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    oracle.build()
+    threads = oracle.max_threads()
+    mesh_name, cpg, substeps, n_cells, per_cell = WORKLOADS[args.workload]
+    mesh, _, _, _, _ = build_inputs(args.workload, 1, seed=1, want_conc=False)
+    per_step_target = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
+    vals = []
+    sample = None
+    for it in range(args.warmup + args.steps):
+        r = cpu_sample(mesh, substeps, cpg * args.gpus, threads, target_s=per_step_target)
+        if it >= args.warmup:
+            vals.append(r["value"])
+        sample = r
+    v = float(np.mean(vals))
+    n_total = mesh.nfields * cpg * args.gpus * substeps
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": n_total / v * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {mesh.nfields} points x {cpg * args.gpus} compounds x "
+                                   f"{substeps} substeps (CPU arm times a bounded sample per step; ms_per_step is "
+                                   f"the full step extrapolated from it)"},
+            "cpu_baseline": dict(sample, value=v),
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import eutropia_b200 as eb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: eutropia_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    dev = local
+
+    mesh_name, cpg, substeps, n_cells, per_cell = WORKLOADS[args.workload]
+    # compound sharding: rank r owns columns [r*cpg, (r+1)*cpg) of the global N x (cpg*world) field
+    mesh, conc, cellgeo, ex, substeps = build_inputs(args.workload, cpg, seed=1000 + rank)
+    n = mesh.nfields
+    plan = eb.Plan(mesh.mat_in, mesh.mat_out, device=dev)
+    field = eb.Field(plan, cpg)
+    for k, v in (args.opt or []):
+        field.set_option(k, v)
+    field.upload(conc)
+    cells = None
+    if n_cells:
+        cells = eb.Cells(plan)
+        cells.build_lists(mesh.field_pts, *cellgeo)
+        cells.claim_rescale()
+    niter = np.full(cpg, substeps, dtype=np.int32)
+    indvar = np.arange(1, cpg + 1, dtype=np.int32)
+    stream = torch.cuda.ExternalStream(field.stream, device=dev)
+
+    def step():
+        if cells is not None:
+            cells.scatter(field, mesh.field_vol, None, *ex)
+        field.diffuse(niter, indvar)
+        if cells is not None:
+            cells.gather(field, mesh.field_vol, want_host=False)
+
+    def barrier():
+        field.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---- device-resident timing ------------------------------------------------------------
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(dev)
+    sampler.start()
+    l0 = field.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dev_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with torch.cuda.stream(stream):
+        ev0.record()
+    for k in range(args.steps):
+        if cells is not None:
+            cells.scatter(field, mesh.field_vol, None, *ex)
+        with torch.cuda.stream(stream):
+            dev_ev[k][0].record()
+        field.diffuse(niter, indvar)
+        with torch.cuda.stream(stream):
+            dev_ev[k][1].record()
+        if cells is not None:
+            cells.gather(field, mesh.field_vol, want_host=False)
+    with torch.cuda.stream(stream):
+        ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = field.launch_count - l0
+    ms = ev0.elapsed_time(ev1)
+    diff_ms = sum(a.elapsed_time(b) for a, b in dev_ev)
+    t = torch.tensor([ms, diff_ms], dtype=torch.float64, device=f"cuda:{dev}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, diff_ms = float(t[0]), float(t[1])
+    updates_per_step = n * cpg * world * substeps
+    value = updates_per_step * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers (one-shot diffChangePar) ------------
+    pin_in = torch.from_numpy(conc.T).contiguous().pin_memory()      # [cpg, n] == column-major n x cpg
+    pin_out = torch.empty_like(pin_in).pin_memory()
+    adj = np.require(mesh.mat_in, dtype=np.int32, requirements=["F", "A"])
+    nn = np.require(mesh.mat_out, dtype=np.int32, requirements=["F", "A"])
+    L = eb._lib.lib()
+
+    def e2e_call():
+        eb._lib.check(L.eut_diffchange_par(eb._lib.ptr(adj), adj.shape[0], eb._lib.ptr(nn), nn.shape[0],
+                                           pin_in.data_ptr(), n, cpg, eb._lib.ptr(niter), eb._lib.ptr(indvar),
+                                           cpg, 1, pin_out.data_ptr(), dev))
+
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(2):
+        e2e_call()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_call()
+        pin_in, pin_out = pin_out, pin_in       # next round starts from this round's result
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{dev}")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = updates_per_step * e2e_steps / float(te[0])
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        n_sub = substeps * args.steps
+        launch_ms = diff_ms / n_sub
+        achieved = BYTES_PER_UPDATE * n * cpg / (launch_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(args.workload)
+            except Exception:
+                traffic = None
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            import oracle
+            oracle.build()
+            cpu = cpu_sample(mesh, substeps, cpg, oracle.max_threads())
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: non-convex polygon mesh, {n} points x {cpg * world} compounds "
+                                   f"({cpg}/GPU, sharded by compound), {substeps} substeps/step, {n_cells} cells x "
+                                   f"{per_cell} exchanges; step = scatter+clamp -> substeps -> gather on the resident field",
+                       "l2": f"inputs larger than L2 ({2 * n * cpg * 8 / 2**20:.0f} MiB ping-pong field per GPU)",
+                       "plan": {"order": int(plan.info.order), "ell_width": int(plan.info.ell_width)}},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "k_substep_ell", "launch_ms": launch_ms,
+                         "algorithmic_bytes_per_launch": BYTES_PER_UPDATE * n * cpg},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * cpg * 8,
+                    "d2h_bytes_per_step": n * cpg * 8, "steps": e2e_steps,
+                    "api": "eut_diffchange_par (one-shot C ABI, pinned host buffers, graph cached by hash)",
+                    "timer": "host wall clock around the blocking calls, max over ranks"},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="harbor1m", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--opt", action="append", type=lambda s: (s.split("=")[0], int(s.split("=")[1])),
+                    help="field option, e.g. --opt cpt=4")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

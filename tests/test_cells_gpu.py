@@ -1,0 +1,164 @@
+"""GPU parity tests of the cell<->field exchange (cell map, claim rescale, gather, scatter+clamp)
+through the C ABI against the CPU oracle.  Index maps (field ids per cell, in key order) must be
+bit-exact; values must agree within 1e-12 relative (sums that R takes in long double are taken as
+hi+lo pairs on the device), and the scatter must be reproducible bit for bit run to run."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+import eutropia_b200 as eb
+from eutropia_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+REL = 1e-12
+
+
+def close(a, b, rel=REL, absol=0.0):
+    return np.all(np.abs(a - b) <= rel * np.maximum(np.abs(b), 1e-300) + absol)
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(GOLD, "cells_small.npz"))
+
+
+def test_cellmap_bit_exact_indices(gold):
+    g = gold
+    plan = eb.Plan(g["mat_in"], g["mat_out"])
+    cells = eb.Cells(plan)
+    cells.build_lists(g["field_pts"], g["cx"], g["cy"], g["size"], g["scv"])
+    ptr, fid, fd, acc = cells.get_lists()
+    assert np.array_equal(ptr, g["cell_ptr"])
+    assert np.array_equal(fid, g["field_id"])            # index map: bit-exact, key order (z,x,y)
+    assert np.array_equal(fd, g["field_dist"])           # IEEE sqrt / mul / add: bit-exact too
+    assert np.array_equal(acc, g["acc_raw"])
+    cells.claim_rescale()
+    _, _, _, acc2 = cells.get_lists()
+    assert close(acc2, g["acc_prop"])
+    assert np.array_equal(acc2[g["acc_prop"] == g["acc_raw"]], g["acc_raw"][g["acc_prop"] == g["acc_raw"]])
+
+
+def test_cellmap_xyz_mode_and_no_cells(gold):
+    g = gold
+    plan = eb.Plan(g["mat_in"], g["mat_out"])
+    cells = eb.Cells(plan)
+    cells.build_lists(g["field_pts"], g["cx"], g["cy"], g["size"], g["scv"], dist_mode=1)
+    ptr, fid, fd, acc = cells.get_lists()
+    rp, rf, rd, ra = oracle.cellmap(g["field_pts"], g["cx"], g["cy"], g["size"], g["scv"], dist_mode=1)
+    assert np.array_equal(ptr, rp) and np.array_equal(fid, rf) and np.array_equal(fd, rd) and np.array_equal(acc, ra)
+    cells.build_lists(g["field_pts"], [], [], [], [])
+    assert cells.n_entries == 0
+    # a cell far outside the mesh has an empty list
+    cells.build_lists(g["field_pts"], [1e6, float(g["cx"][0])], [1e6, float(g["cy"][0])], [1.2, 1.2], [3.1, 3.1])
+    ptr, fid, _, _ = cells.get_lists()
+    assert ptr[1] == 0 and ptr[2] == fid.size > 0
+
+
+def test_gather_scatter_match_oracle(gold):
+    g = gold
+    vol = float(g["field_vol"])
+    plan = eb.Plan(g["mat_in"], g["mat_out"])
+    field = eb.Field(plan, g["conc"].shape[1])
+    field.upload(g["conc"])
+    cells = eb.Cells(plan)
+    cells.set_lists(g["cell_ptr"], g["field_id"], g["field_dist"], g["acc_prop"])
+    fmol = cells.gather(field, vol)
+    assert close(fmol, g["fmol"])
+    cells.scatter(field, vol, g["is_const"], g["ex_ptr"], g["ex_cpd"], g["ex_flx"])
+    after = field.download()
+    ref = g["after"]
+    # tolerance relative to the field magnitude: uptake and production cancel inside one sum
+    assert close(after, ref, rel=REL, absol=REL * np.abs(g["conc"]).max())
+    assert np.array_equal(after == 0.0, ref == 0.0)                 # the < 1e-12 clamp hits the same entries
+    assert np.array_equal(after[:, 4], g["conc"][:, 4])             # constant compound untouched
+    untouched = np.ones(g["conc"].shape[0], bool); untouched[g["field_id"] - 1] = False
+    assert np.array_equal(after[untouched], g["conc"][untouched])
+    # run-to-run reproducibility (deterministic order, no atomics)
+    field.upload(g["conc"])
+    cells.scatter(field, vol, g["is_const"], g["ex_ptr"], g["ex_cpd"], g["ex_flx"])
+    assert np.array_equal(field.download(), after)
+
+
+def test_round_scatter_diffuse_gather(gold):
+    # one simulated round on the resident field == the oracle's round
+    g = gold
+    vol = float(g["field_vol"])
+    plan = eb.Plan(g["mat_in"], g["mat_out"])
+    field = eb.Field(plan, 6)
+    field.upload(g["conc"])
+    cells = eb.Cells(plan)
+    cells.build_lists(g["field_pts"], g["cx"], g["cy"], g["size"], g["scv"])
+    cells.claim_rescale()
+    cells.scatter(field, vol, g["is_const"], g["ex_ptr"], g["ex_cpd"], g["ex_flx"])
+    field.diffuse([60, 22, 60, 60], [1, 2, 3, 6])
+    fmol = cells.gather(field, vol)
+    ref = oracle.diffChangePar(g["mat_in"], g["mat_out"], g["after"], [60, 22, 60, 60], [1, 2, 3, 6], 2)
+    rfmol = oracle.gather(ref, g["cell_ptr"], g["field_id"], g["acc_prop"], vol)
+    scale = np.abs(g["conc"]).max()
+    assert close(field.download(), ref, absol=REL * scale)
+    assert close(fmol, rfmol, rel=1e-11, absol=1e-12 * np.abs(rfmol).max())
+
+
+def test_scatter_nan_and_clamp_rules(small_mesh):
+    m = small_mesh
+    plan = eb.Plan(m.mat_in, m.mat_out)
+    conc = np.full((m.nfields, 3), 2.0)
+    conc[:, 1] = 0.0                        # nothing accessible: colSum 0 -> 0/0 -> NaN -> dropped
+    cx, cy = np.array([0.0, 0.4]), np.array([0.0, 0.2])
+    size, scv = np.full(2, 1.24), np.full(2, 3.1)
+    cells = eb.Cells(plan)
+    cells.build_lists(m.field_pts, cx, cy, size, scv)
+    ptr, fid, fd, acc = cells.get_lists()
+    ex_ptr = np.array([0, 3, 4]); ex_cpd = np.array([2, 1, 3, 2]); ex_flx = np.array([-1e-3, -1e-3, 2e-3, 5e-3])
+    ref = oracle.scatter(conc, None, ptr, fid, fd, acc, m.field_vol, ex_ptr, ex_cpd, ex_flx)
+    field = eb.Field(plan, 3)
+    field.upload(conc)
+    cells.scatter(field, m.field_vol, None, ex_ptr, ex_cpd, ex_flx)
+    got = field.download()
+    assert close(got, ref, absol=1e-12 * 2.0)
+    assert not np.isnan(got).any()
+    # fields shared by both cells lose cell 1's production of compound 2 as well (NaN swallows the group sum)
+    both = np.intersect1d(fid[ptr[0]:ptr[1]], fid[ptr[1]:ptr[2]]) - 1
+    assert both.size > 0 and np.all(got[both, 1] == 0.0)
+
+
+def test_properties_at_scale():
+    m = synth.config_mesh("harbor:200000")
+    n_cells, C = 5000, 16
+    conc = synth.synthetic_concentrations(m.field_pts, C, seed=51)
+    cx, cy, size, scv = synth.place_cells(m, n_cells, seed=52)
+    plan = eb.Plan(m.mat_in, m.mat_out)
+    field = eb.Field(plan, C)
+    field.upload(conc)
+    cells = eb.Cells(plan)
+    cells.build_lists(m.field_pts, cx, cy, size, scv)
+    ptr, fid, fd, acc = cells.get_lists()
+    # sample of cells against the oracle (index map exact)
+    pick = np.array([0, 1, 77, 4999])
+    rp, rf, rd, ra = oracle.cellmap(m.field_pts, cx[pick], cy[pick], size[pick], scv[pick])
+    for j, i in enumerate(pick):
+        assert np.array_equal(fid[ptr[i]:ptr[i + 1]], rf[rp[j]:rp[j + 1]])
+        assert np.array_equal(fd[ptr[i]:ptr[i + 1]], rd[rp[j]:rp[j + 1]])
+    per_cell = np.diff(ptr)
+    assert 100 < per_cell.mean() < 160                      # ~133 fields per cell at 3 layers
+    cells.claim_rescale()
+    _, _, _, acc2 = cells.get_lists()
+    claim = np.bincount(fid, weights=acc2, minlength=m.nfields + 1)
+    assert claim.max() <= 1 + 1e-9
+    assert close(acc2, oracle.claim(fid, acc, m.nfields), rel=1e-11)
+    # gather vs oracle at full size
+    fmol = cells.gather(field, m.field_vol)
+    assert close(fmol, oracle.gather(conc, ptr, fid, acc2, m.field_vol))
+    # scatter: total fmol moved per compound equals the sum of the cells' fluxes (small fluxes: no clamp)
+    ex_ptr, ex_cpd, ex_flx = synth.synthetic_exchanges(n_cells, C, 4, seed=53)
+    ex_flx *= 1e-4
+    cells.scatter(field, m.field_vol, None, ex_ptr, ex_cpd, ex_flx)
+    after = field.download()
+    moved = (after - conc).sum(0) * 1e12 * (m.field_vol / 1e15)
+    want = np.bincount(ex_cpd - 1, weights=ex_flx, minlength=C)
+    assert np.allclose(moved, want, rtol=1e-6, atol=1e-9)
+    ref = oracle.scatter(conc, None, ptr, fid, fd, acc2, m.field_vol, ex_ptr, ex_cpd, ex_flx)
+    assert close(after, ref, absol=1e-12 * np.abs(conc).max())
