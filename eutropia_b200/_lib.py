@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libeutropia_b200.so")
 
 OK, ERR_INDEX, ERR_ARG, ERR_ALLOC, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED, ERR_NCCL = range(8)
 
-ORDER_AUTO, ORDER_IDENTITY, ORDER_ROWBLOCK = 0, 1, 2
+ORDER_AUTO, ORDER_IDENTITY, ORDER_ROWBLOCK, ORDER_TILED = 0, 1, 2, 3
 PLAN_FORCE_GENERIC = 0x10
 
 
@@ -33,6 +33,8 @@ class PlanInfo(C.Structure):
         ("max_in_degree", C.c_int32), ("ell_width", C.c_int32), ("order", C.c_int32),
         ("regular_outflow", C.c_int32), ("device", C.c_int32), ("n_tiles", C.c_int32),
         ("device_bytes", C.c_int64), ("build_ms", C.c_double),
+        ("tiled", C.c_int32), ("img_points", C.c_int32), ("max_tile_points", C.c_int32),
+        ("max_copies", C.c_int32), ("halo_ratio", C.c_double),
     ]
 
 

@@ -58,6 +58,9 @@ int eut_plan_get_info(const eut_plan *p, eut_plan_info *info)
     info->max_in_degree = p->max_in; info->ell_width = p->ell_w; info->order = p->order;
     info->regular_outflow = p->regular_out; info->device = p->device; info->n_tiles = p->n_tiles;
     info->device_bytes = p->device_bytes; info->build_ms = p->build_ms;
+    info->tiled = p->tiled ? 1 : 0; info->img_points = p->tiles.img_points;
+    info->max_tile_points = p->tiles.max_tile_points; info->max_copies = p->tiles.max_copies;
+    info->halo_ratio = p->tiles.halo_ratio;
     return EUT_OK;
 }
 

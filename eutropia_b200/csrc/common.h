@@ -45,9 +45,37 @@ double now_ms();
 }  // namespace eut
 
 // ---------------------------------------------------------------------------------------------
+// tiled path (tiles.cu): host-side result of the tile planner
+// ---------------------------------------------------------------------------------------------
+namespace eut {
+struct TileParams {
+    int tile_cols = 64;          // columns of the pseudo x coordinate per tile
+    double target_rows = 24;     // rows (all layers) per band the planner aims for
+    int levels_per_band = 0;     // 0: derive from target_rows
+    int max_tile_points = 1536;  // = threads per CTA x points per thread of the kernel
+    int max_img_points = 4096;   // shared-memory image limit (points) per buffer
+    int max_copies = 1536;       // copy granules per tile the kernel can hold in registers
+};
+struct TilePlanHost {
+    std::vector<int32_t> tile_start;  // [n_tiles+1] internal ids
+    std::vector<int32_t> copy_ptr;    // [n_tiles+1]
+    std::vector<int2> copies;         // x: internal id of the first point, y: image offset | n_points << 16
+    std::vector<uint16_t> loc;        // [W][Np] byte offset of every in-neighbour inside the image
+    int img_points = 0, max_tile_points = 0, max_copies = 0;
+    double halo_ratio = 0;
+};
+}  // namespace eut
+
+// ---------------------------------------------------------------------------------------------
 // plan: neighbour graph resident on one GPU
 // ---------------------------------------------------------------------------------------------
 struct eut_plan {
+    eut::TilePlanHost tiles;
+    bool tiled = false;
+    int32_t *d_tile_start = nullptr;
+    int32_t *d_copy_ptr = nullptr;
+    int2 *d_copies = nullptr;
+    uint16_t *d_loc16 = nullptr;
     int device = 0;
     int64_t N = 0, E = 0, Np = 0;
     int max_in = 0, ell_w = 0, order = 0, regular_out = 0, n_tiles = 0;
@@ -118,6 +146,7 @@ int plan_build(eut_plan *p, const int32_t *from, const int32_t *to, int64_t n_ed
                int device, uint32_t flags);
 void plan_free(eut_plan *p);
 uint64_t hash_bytes(const void *data, size_t n, uint64_t seed);
+int build_tiles(eut_plan *p, const TileParams &tp);
 
 // field.cu
 int field_create(eut_field **out, eut_plan *plan, int64_t n_cols);

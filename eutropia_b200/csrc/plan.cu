@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <chrono>
 #include <numeric>
+#include <cstdlib>
 
 #include "common.h"
 
@@ -212,18 +213,28 @@ int plan_build(eut_plan *p, const int32_t *from, const int32_t *to, int64_t n_ed
     }
 
     // -- ordering -----------------------------------------------------------------------------
+    const bool ell_ok = regular && p->max_in <= kEllMax && !(flags & EUT_PLAN_FORCE_GENERIC);
     uint32_t order = flags & EUT_ORDER_MASK;
-    if (order == EUT_ORDER_AUTO) order = EUT_ORDER_ROWBLOCK;
-    if (order == EUT_ORDER_ROWBLOCK && N > 0) order_rowblock(p);
-    else { order = EUT_ORDER_IDENTITY; order_identity(p); }
+    if (order == EUT_ORDER_AUTO) order = ell_ok ? EUT_ORDER_TILED : EUT_ORDER_ROWBLOCK;
+    p->tiled = false;
+    if (order == EUT_ORDER_TILED && N > 0 && ell_ok) {
+        TileParams tp;
+        if (const char *e = getenv("EUT_TILE_COLS")) tp.tile_cols = atoi(e);
+        if (const char *e = getenv("EUT_TILE_ROWS")) tp.target_rows = atof(e);
+        if (build_tiles(p, tp) == EUT_OK) p->tiled = true;
+        else order = EUT_ORDER_ROWBLOCK;   // graph not lattice-like enough: ELL kernel
+    } else if (order == EUT_ORDER_TILED) order = EUT_ORDER_ROWBLOCK;
+    if (!p->tiled) {
+        if (order == EUT_ORDER_ROWBLOCK && N > 0) order_rowblock(p);
+        else { order = EUT_ORDER_IDENTITY; order_identity(p); }
+        p->Np = ((N + kPadPoints - 1) / kPadPoints) * kPadPoints;
+        if (p->Np == 0) p->Np = kPadPoints;
+        p->iperm.assign(p->Np, -1);
+        for (int64_t i = 0; i < N; i++) p->iperm[p->perm[i]] = (int32_t)i;
+    }
     p->order = (int)order;
-    p->Np = ((N + kPadPoints - 1) / kPadPoints) * kPadPoints;
-    if (p->Np == 0) p->Np = kPadPoints;
-    p->iperm.assign(p->Np, -1);
-    for (int64_t i = 0; i < N; i++) p->iperm[p->perm[i]] = (int32_t)i;
 
     // -- device tables ------------------------------------------------------------------------
-    const bool ell_ok = regular && p->max_in <= kEllMax && !(flags & EUT_PLAN_FORCE_GENERIC);
     p->device_bytes = 0;
     EUT_TRY(upload(&p->d_perm, p->perm, &p->device_bytes));
     EUT_TRY(upload(&p->d_iperm, p->iperm, &p->device_bytes));
@@ -247,6 +258,14 @@ int plan_build(eut_plan *p, const int32_t *from, const int32_t *to, int64_t n_ed
         EUT_TRY(upload(&p->d_nbr, nbr, &p->device_bytes));
         EUT_TRY(upload(&p->d_deg, deg, &p->device_bytes));
         EUT_TRY(upload(&p->d_w, w, &p->device_bytes));
+        if (p->tiled) {
+            EUT_TRY(upload(&p->d_tile_start, p->tiles.tile_start, &p->device_bytes));
+            EUT_TRY(upload(&p->d_copy_ptr, p->tiles.copy_ptr, &p->device_bytes));
+            EUT_TRY(upload(&p->d_copies, p->tiles.copies, &p->device_bytes));
+            EUT_TRY(upload(&p->d_loc16, p->tiles.loc, &p->device_bytes));
+            p->tiles.loc.clear(); p->tiles.loc.shrink_to_fit();
+            p->tiles.copies.clear(); p->tiles.copies.shrink_to_fit();
+        }
     } else {
         p->ell_w = 0;
         std::vector<int64_t> rp(N + 1, 0), op(N + 1, 0);
@@ -276,6 +295,7 @@ void plan_free(eut_plan *p)
     cudaFree(p->d_nbr); cudaFree(p->d_deg); cudaFree(p->d_w); cudaFree(p->d_perm);
     cudaFree(p->d_iperm); cudaFree(p->d_row_ptr); cudaFree(p->d_col); cudaFree(p->d_out_ptr);
     cudaFree(p->d_out_w);
+    cudaFree(p->d_tile_start); cudaFree(p->d_copy_ptr); cudaFree(p->d_copies); cudaFree(p->d_loc16);
 }
 
 }  // namespace eut

@@ -83,6 +83,167 @@ k_substep_csr(double *__restrict__ buf, const int64_t col_stride, const int64_t 
     dst[q] = __dadd_rn(cq, y);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tiled path (tiles.cu builds the tables): one CTA = one compact tile of <= 256*PPT points and a
+// slice of the active compound columns.  For every column the tile's image -- own points plus halo
+// runs -- is staged into shared memory with cp.async (16-byte granules on the contiguous runs,
+// 8-byte granules on odd ends / lone halo points), NBUF columns deep, so HBM/L2 latency is hidden
+// by the copies of the next columns instead of by occupancy.  The per-thread state (copy granules,
+// 16-bit image offsets of the 12 neighbour slots of PPT points, outflow weights) is loaded once
+// per tile and reused for all columns.  The arithmetic is the same DADD/DMUL sequence as above.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async_8(uint32_t saddr, const void *g)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(uint32_t saddr, const void *g)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ double lds_f64(uint32_t saddr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(saddr));
+    return v;
+}
+
+template <int W, int PPT, int MAXCE, int NBUF>
+__global__ void __launch_bounds__(256, 2)
+k_substep_tile(double *__restrict__ buf, const int64_t col_stride, const int64_t buf_stride,
+               const int32_t *__restrict__ tile_start, const int32_t *__restrict__ copy_ptr,
+               const int2 *__restrict__ copies, const uint16_t *__restrict__ loc16,
+               const uint8_t *__restrict__ deg, const double *__restrict__ wout,
+               const int32_t *__restrict__ act_col, const int32_t *__restrict__ act_par,
+               const int n_act, const int substep, const int img_bytes, const int cols_per_cta)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x;
+    const int t0 = __ldg(tile_start + tile);
+    const int cnt = __ldg(tile_start + tile + 1) - t0;
+    const int a_begin = blockIdx.y * cols_per_cta;
+    const int n_cols = min(n_act, a_begin + cols_per_cta) - a_begin;
+    if (n_cols <= 0) return;
+    const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
+
+    // copy granules of this thread
+    int cg[MAXCE];
+    uint32_t cs[MAXCE];
+    {
+        const int c0 = __ldg(copy_ptr + tile);
+        const int nc = __ldg(copy_ptr + tile + 1) - c0;
+#pragma unroll
+        for (int e = 0; e < MAXCE; e++) {
+            const int i = tid + e * 256;
+            int2 d = make_int2(0, 0);
+            if (i < nc) d = __ldg(copies + c0 + i);
+            cg[e] = d.x;
+            cs[e] = (uint32_t)d.y;
+        }
+    }
+    // neighbour offsets (bytes inside the image), two per register
+    uint32_t lo[PPT][W / 2];
+    int dg[PPT];
+    double wq[PPT];
+#pragma unroll
+    for (int p = 0; p < PPT; p++) {
+        const int lp = tid + p * 256;
+        const bool on = lp < cnt;
+        const int64_t q = t0 + (on ? lp : 0);
+        dg[p] = on ? (int)__ldg(deg + q) : -1;
+        wq[p] = __ldg(wout + q);
+#pragma unroll
+        for (int k = 0; k < W / 2; k++) {
+            const uint32_t a = __ldg(loc16 + (int64_t)(2 * k) * col_stride + q);
+            const uint32_t b = __ldg(loc16 + (int64_t)(2 * k + 1) * col_stride + q);
+            lo[p][k] = a | (b << 16);
+        }
+    }
+    // zero cells 0,1 of every buffer (never overwritten by copies)
+    if (tid < NBUF) {
+        double *z = reinterpret_cast<double *>(smem_raw + (size_t)tid * img_bytes);
+        z[0] = 0.0; z[1] = 0.0;
+    }
+    const uint32_t own_off = (uint32_t)(2 + (t0 & 1)) * 8u;
+
+    auto issue = [&](int j) {
+        if (j < n_cols) {
+            const int a = a_begin + j;
+            const int c = __ldg(act_col + a);
+            const int b = (__ldg(act_par + a) + substep) & 1;
+            const double *__restrict__ src = buf + (int64_t)b * buf_stride + (int64_t)c * col_stride;
+            const uint32_t sb = s_base + (uint32_t)(j % NBUF) * (uint32_t)img_bytes;
+#pragma unroll
+            for (int e = 0; e < MAXCE; e++) {
+                const uint32_t n = cs[e] >> 16;
+                const uint32_t so = sb + (cs[e] & 0xffffu) * 8u;
+                if (n == 2) cp_async_16(so, src + cg[e]);
+                else if (n == 1) cp_async_8(so, src + cg[e]);
+            }
+        }
+        cp_async_commit();
+    };
+
+#pragma unroll
+    for (int s = 0; s < NBUF - 1; s++) issue(s);
+    for (int j = 0; j < n_cols; j++) {
+        issue(j + NBUF - 1);
+        cp_async_wait<NBUF - 1>();
+        __syncthreads();
+        const int a = a_begin + j;
+        const int c = __ldg(act_col + a);
+        const int b = (__ldg(act_par + a) + substep) & 1;
+        double *__restrict__ dst = buf + (int64_t)(b ^ 1) * buf_stride + (int64_t)c * col_stride + t0;
+        const uint32_t sb = s_base + (uint32_t)(j % NBUF) * (uint32_t)img_bytes;
+#pragma unroll
+        for (int p = 0; p < PPT; p++) {
+            const int lp = tid + p * 256;
+            if (dg[p] >= 0) {
+                const double cq = lds_f64(sb + own_off + (uint32_t)lp * 8u);
+                double acc = 0.0;
+#pragma unroll
+                for (int k = 0; k < W; k++) {
+                    const uint32_t off = (k & 1) ? (lo[p][k >> 1] >> 16) : (lo[p][k >> 1] & 0xffffu);
+                    if (k < dg[p]) acc = __dadd_rn(acc, lds_f64(sb + off));
+                }
+                double y = __dmul_rn(acc, kBDiv);
+                y = __dsub_rn(y, __dmul_rn(cq, wq[p]));
+                dst[lp] = __dadd_rn(cq, y);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+static int launch_tile(eut_field *f, int n_act, int substep)
+{
+    const eut_plan *p = f->plan;
+    constexpr int PPT = 6, MAXCE = 6, NBUF = 3;
+    const int img_bytes = ((p->tiles.img_points * 8 + 15) / 16) * 16;
+    const size_t smem = (size_t)NBUF * img_bytes;
+    // enough CTAs to fill the machine twice, as few column slices as possible (the per-tile
+    // tables are re-read once per slice)
+    int slices = 1;
+    const int64_t want = 2ll * 148 * 2;
+    while ((int64_t)p->n_tiles * slices < want && slices < n_act) slices++;
+    if (f->opt_cpt > 0) slices = (n_act + f->opt_cpt - 1) / f->opt_cpt;
+    const int cols_per_cta = (n_act + slices - 1) / slices;
+    dim3 grid((unsigned)p->n_tiles, (unsigned)((n_act + cols_per_cta - 1) / cols_per_cta), 1);
+    auto kern = k_substep_tile<12, PPT, MAXCE, NBUF>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        EUT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    kern<<<grid, 256, smem, f->stream>>>(f->d_buf, p->Np, f->C * p->Np, p->d_tile_start, p->d_copy_ptr,
+                                         p->d_copies, p->d_loc16, p->d_deg, p->d_w, f->d_act,
+                                         f->d_act + f->act_cap, n_act, substep, img_bytes, cols_per_cta);
+    return EUT_OK;
+}
+
 template <int W>
 static int launch_ell_w(eut_field *f, int n_act, int substep)
 {
@@ -110,7 +271,9 @@ int launch_substep(eut_field *f, int n_act, int substep)
     const eut_plan *p = f->plan;
     if (n_act <= 0 || p->N == 0) return EUT_OK;
     const int64_t bs = f->C * p->Np;
-    if (p->ell_w > 0) {
+    if (p->tiled && f->opt_variant != 1) {
+        EUT_TRY(launch_tile(f, n_act, substep));
+    } else if (p->ell_w > 0) {
         if (p->ell_w <= 4) EUT_TRY(launch_ell_w<4>(f, n_act, substep));
         else if (p->ell_w <= 8) EUT_TRY(launch_ell_w<8>(f, n_act, substep));
         else EUT_TRY(launch_ell_w<12>(f, n_act, substep));

@@ -108,7 +108,8 @@ typedef struct eut_plan eut_plan;
 enum {                       /* eut_plan_create flags */
     EUT_ORDER_AUTO      = 0, /* library picks the internal point ordering */
     EUT_ORDER_IDENTITY  = 1, /* keep the reference's (layer-major) order */
-    EUT_ORDER_ROWBLOCK  = 2, /* locality ordering derived from the graph */
+    EUT_ORDER_ROWBLOCK  = 2, /* whole raster rows reordered breadth-first over the row graph */
+    EUT_ORDER_TILED     = 3, /* compact 3-D tiles derived from the graph + shared-memory kernel */
     EUT_ORDER_MASK      = 0xf,
     EUT_PLAN_FORCE_GENERIC = 0x10 /* use the generic CSR kernel even when the fast path applies */
 };
@@ -125,6 +126,11 @@ typedef struct eut_plan_info {
     int32_t n_tiles;
     int64_t device_bytes;    /* graph bytes resident in HBM */
     double  build_ms;        /* host analysis + upload time */
+    int32_t tiled;           /* 1: the tiled shared-memory kernel is available */
+    int32_t img_points;      /* points per shared-memory image (tiled) */
+    int32_t max_tile_points;
+    int32_t max_copies;
+    double  halo_ratio;      /* halo points / own points, summed over tiles (tiled) */
 } eut_plan_info;
 
 EUT_API int eut_plan_create(eut_plan **out,

@@ -30,7 +30,7 @@ def test_golden_fixture_one_shot():
     assert_parity(out, g["expected"])
 
 
-@pytest.mark.parametrize("order", [_lib.ORDER_IDENTITY, _lib.ORDER_ROWBLOCK])
+@pytest.mark.parametrize("order", [_lib.ORDER_IDENTITY, _lib.ORDER_ROWBLOCK, _lib.ORDER_TILED])
 @pytest.mark.parametrize("generic", [False, True])
 def test_session_matches_oracle_all_variants(harbor_mesh, order, generic):
     m = harbor_mesh
@@ -40,6 +40,7 @@ def test_session_matches_oracle_all_variants(harbor_mesh, order, generic):
     ref = oracle.diffChangePar(m.mat_in, m.mat_out, conc, niter, indvar, 4)
     plan = eb.Plan(m.mat_in, m.mat_out, order=order, force_generic=generic)
     assert (plan.info.ell_width == 0) == generic
+    assert bool(plan.info.tiled) == (order == _lib.ORDER_TILED and not generic)
     f = eb.Field(plan, 9)
     f.upload(conc)
     f.diffuse(niter, indvar)
@@ -56,7 +57,7 @@ def test_index_map_bit_exact(harbor_mesh):
     to, frm = m.mat_in[:, 1].astype(np.int64), m.mat_in[:, 0]
     order = np.argsort(to, kind="stable")
     row_ptr = np.concatenate([[0], np.cumsum(np.bincount(to, minlength=n + 1)[1:])])
-    for o in (_lib.ORDER_IDENTITY, _lib.ORDER_ROWBLOCK):
+    for o in (_lib.ORDER_IDENTITY, _lib.ORDER_ROWBLOCK, _lib.ORDER_TILED):
         for generic in (False, True):
             plan = eb.Plan(m.mat_in, m.mat_out, order=o, force_generic=generic)
             rp, col = plan.csr()
