@@ -15,6 +15,7 @@ OK, ERR_INDEX, ERR_ARG, ERR_ALLOC, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED, ERR
 
 ORDER_AUTO, ORDER_IDENTITY, ORDER_ROWBLOCK, ORDER_TILED = 0, 1, 2, 3
 PLAN_FORCE_GENERIC = 0x10
+PLAN_HOST_ONLY = 0x20
 
 
 class EutropiaError(RuntimeError):
@@ -34,7 +35,8 @@ class PlanInfo(C.Structure):
         ("regular_outflow", C.c_int32), ("device", C.c_int32), ("n_tiles", C.c_int32),
         ("device_bytes", C.c_int64), ("build_ms", C.c_double),
         ("tiled", C.c_int32), ("img_points", C.c_int32), ("max_tile_points", C.c_int32),
-        ("max_copies", C.c_int32), ("halo_ratio", C.c_double),
+        ("max_bulk", C.c_int32), ("max_single", C.c_int32), ("n_copies", C.c_int32),
+        ("halo_ratio", C.c_double),
     ]
 
 
@@ -64,6 +66,7 @@ def lib() -> C.CDLL:
         "eut_plan_get_info": (C.c_int, [vp, C.POINTER(PlanInfo)]),
         "eut_plan_get_csr": (C.c_int, [vp, vp, vp]),
         "eut_plan_get_perm": (C.c_int, [vp, vp]),
+        "eut_plan_get_tiles": (C.c_int, [vp, vp, vp, vp]),
         "eut_field_create": (C.c_int, [C.POINTER(vp), vp, i64]),
         "eut_field_destroy": (C.c_int, [vp]),
         "eut_field_upload": (C.c_int, [vp, vp, i64, vp, i64]),
@@ -97,7 +100,7 @@ def lib() -> C.CDLL:
 EXPORTS = (
     "eut_last_error eut_abi_version eut_device_count eut_diffchange eut_diffchange_par "
     "eut_oneshot_reset eut_plan_create eut_plan_destroy eut_plan_get_info eut_plan_get_csr "
-    "eut_plan_get_perm eut_field_create eut_field_destroy eut_field_upload eut_field_download "
+    "eut_plan_get_perm eut_plan_get_tiles eut_field_create eut_field_destroy eut_field_upload eut_field_download "
     "eut_field_diffuse eut_field_sync eut_field_stream eut_field_set_stream "
     "eut_field_launch_count eut_field_set_option eut_field_column_stats eut_field_fill_column "
     "eut_cells_create eut_cells_destroy eut_cells_set_lists eut_cells_build_lists "

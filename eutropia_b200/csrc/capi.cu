@@ -59,7 +59,8 @@ int eut_plan_get_info(const eut_plan *p, eut_plan_info *info)
     info->regular_outflow = p->regular_out; info->device = p->device; info->n_tiles = p->n_tiles;
     info->device_bytes = p->device_bytes; info->build_ms = p->build_ms;
     info->tiled = p->tiled ? 1 : 0; info->img_points = p->tiles.img_points;
-    info->max_tile_points = p->tiles.max_tile_points; info->max_copies = p->tiles.max_copies;
+    info->max_tile_points = p->tiles.max_tile_points; info->max_bulk = p->tiles.max_bulk;
+    info->max_single = p->tiles.max_single; info->n_copies = (int32_t)p->tiles.n_copies;
     info->halo_ratio = p->tiles.halo_ratio;
     return EUT_OK;
 }
@@ -70,6 +71,7 @@ int eut_plan_get_csr(const eut_plan *p, int64_t *row_ptr, int32_t *col)
 {
     clear_error();
     if (!p || !row_ptr || (!col && p->E > 0)) { set_error("eut_plan_get_csr: NULL argument"); return EUT_ERR_ARG; }
+    if (p->host_only) { set_error("eut_plan_get_csr: host-only plan has no device tables"); return EUT_ERR_UNSUPPORTED; }
     EUT_TRY(ensure_device(p->device));
     const int64_t N = p->N;
     if (p->ell_w > 0) {
@@ -99,6 +101,17 @@ int eut_plan_get_csr(const eut_plan *p, int64_t *row_ptr, int32_t *col)
             for (int64_t k = rp[q], o = row_ptr[i]; k < rp[q + 1]; k++, o++) col[o] = p->iperm[cl[k]] + 1;
         }
     }
+    return EUT_OK;
+}
+
+int eut_plan_get_tiles(const eut_plan *p, int32_t *tile_meta, int32_t *copies, uint16_t *loc)
+{
+    if (!p || !p->tiled) { set_error("eut_plan_get_tiles: plan has no tile tables"); return EUT_ERR_ARG; }
+    if (!p->host_only) { set_error("eut_plan_get_tiles: only for EUT_PLAN_HOST_ONLY plans"); return EUT_ERR_UNSUPPORTED; }
+    const auto &T = p->tiles;
+    if (tile_meta) std::copy(T.meta.begin(), T.meta.end(), tile_meta);
+    if (copies) memcpy(copies, T.copies.data(), T.copies.size() * sizeof(int2));
+    if (loc) std::copy(T.loc.begin(), T.loc.end(), loc);
     return EUT_OK;
 }
 

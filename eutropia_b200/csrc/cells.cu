@@ -492,7 +492,7 @@ extern "C" {
 int eut_cells_create(eut_cells **out, eut_plan *plan)
 {
     clear_error();
-    if (!out || !plan) { set_error("eut_cells_create: NULL argument"); return EUT_ERR_ARG; }
+    if (!out || !plan || plan->host_only) { set_error("eut_cells_create: NULL argument or host-only plan"); return EUT_ERR_ARG; }
     *out = nullptr;
     EUT_TRY(ensure_device(plan->device));
     eut_cells *c = new eut_cells();

@@ -50,18 +50,23 @@ double now_ms();
 namespace eut {
 struct TileParams {
     int tile_cols = 64;          // columns of the pseudo x coordinate per tile
-    double target_rows = 24;     // rows (all layers) per band the planner aims for
-    int levels_per_band = 0;     // 0: derive from target_rows
+    int band_levels = 16;        // tiles are ordered by coarse level band, then by u column
     int max_tile_points = 1536;  // = threads per CTA x points per thread of the kernel
     int max_img_points = 4096;   // shared-memory image limit (points) per buffer
-    int max_copies = 1536;       // copy granules per tile the kernel can hold in registers
+    int max_bulk = 64;           // bulk copies per tile the kernel can hold (2 per lane of warp 0)
+    int max_single = 512;        // single 8-byte copies per tile (2 per thread)
 };
 struct TilePlanHost {
     std::vector<int32_t> tile_start;  // [n_tiles+1] internal ids
-    std::vector<int32_t> copy_ptr;    // [n_tiles+1]
-    std::vector<int2> copies;         // x: internal id of the first point, y: image offset | n_points << 16
-    std::vector<uint16_t> loc;        // [W][Np] byte offset of every in-neighbour inside the image
-    int img_points = 0, max_tile_points = 0, max_copies = 0;
+    // per tile 8 ints: first id, points, first bulk copy, #bulk, first single copy, #single,
+    // bytes moved by the bulk copies, image points
+    std::vector<int32_t> meta;
+    // bulk:   x = first internal id (even), y = image offset (even) | n_points (even) << 16
+    // single: x = internal id,              y = image offset
+    std::vector<int2> copies;
+    std::vector<uint16_t> loc;        // [12][Np] byte offset of every in-neighbour inside the image
+    int img_points = 0, max_tile_points = 0, max_bulk = 0, max_single = 0;
+    int64_t n_copies = 0;
     double halo_ratio = 0;
 };
 }  // namespace eut
@@ -72,8 +77,8 @@ struct TilePlanHost {
 struct eut_plan {
     eut::TilePlanHost tiles;
     bool tiled = false;
-    int32_t *d_tile_start = nullptr;
-    int32_t *d_copy_ptr = nullptr;
+    bool host_only = false;
+    int32_t *d_tile_meta = nullptr;
     int2 *d_copies = nullptr;
     uint16_t *d_loc16 = nullptr;
     int device = 0;

@@ -46,8 +46,8 @@ static int field_alloc(eut_field *f)
 
 int field_create(eut_field **out, eut_plan *plan, int64_t n_cols)
 {
-    if (!out || !plan || n_cols < 0) {
-        set_error("eut_field_create: bad argument");
+    if (!out || !plan || n_cols < 0 || plan->host_only) {
+        set_error("eut_field_create: bad argument (NULL, negative size or host-only plan)");
         return EUT_ERR_ARG;
     }
     EUT_TRY(ensure_device(plan->device));

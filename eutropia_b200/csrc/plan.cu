@@ -161,7 +161,9 @@ int plan_build(eut_plan *p, const int32_t *from, const int32_t *to, int64_t n_ed
                   (long long)n_points);
         return EUT_ERR_UNSUPPORTED;
     }
-    EUT_TRY(ensure_device(device));
+    const bool host_only = (flags & EUT_PLAN_HOST_ONLY) != 0;
+    if (!host_only) EUT_TRY(ensure_device(device));
+    p->host_only = host_only;
     p->device = device;
     p->N = n_points;
     p->E = n_edges;
@@ -220,7 +222,8 @@ int plan_build(eut_plan *p, const int32_t *from, const int32_t *to, int64_t n_ed
     if (order == EUT_ORDER_TILED && N > 0 && ell_ok) {
         TileParams tp;
         if (const char *e = getenv("EUT_TILE_COLS")) tp.tile_cols = atoi(e);
-        if (const char *e = getenv("EUT_TILE_ROWS")) tp.target_rows = atof(e);
+        if (const char *e = getenv("EUT_TILE_POINTS")) tp.max_tile_points = std::min(1536, std::max(64, atoi(e)));
+        if (const char *e = getenv("EUT_TILE_BAND")) tp.band_levels = atoi(e);
         if (build_tiles(p, tp) == EUT_OK) p->tiled = true;
         else order = EUT_ORDER_ROWBLOCK;   // graph not lattice-like enough: ELL kernel
     } else if (order == EUT_ORDER_TILED) order = EUT_ORDER_ROWBLOCK;
@@ -233,6 +236,11 @@ int plan_build(eut_plan *p, const int32_t *from, const int32_t *to, int64_t n_ed
         for (int64_t i = 0; i < N; i++) p->iperm[p->perm[i]] = (int32_t)i;
     }
     p->order = (int)order;
+    if (host_only) {   // analysis only (CPU tests of the planner): no device tables
+        p->ell_w = ell_ok ? std::max(p->max_in, 1) : 0;
+        p->build_ms = now_ms() - t0;
+        return EUT_OK;
+    }
 
     // -- device tables ------------------------------------------------------------------------
     p->device_bytes = 0;
@@ -259,8 +267,7 @@ int plan_build(eut_plan *p, const int32_t *from, const int32_t *to, int64_t n_ed
         EUT_TRY(upload(&p->d_deg, deg, &p->device_bytes));
         EUT_TRY(upload(&p->d_w, w, &p->device_bytes));
         if (p->tiled) {
-            EUT_TRY(upload(&p->d_tile_start, p->tiles.tile_start, &p->device_bytes));
-            EUT_TRY(upload(&p->d_copy_ptr, p->tiles.copy_ptr, &p->device_bytes));
+            EUT_TRY(upload(&p->d_tile_meta, p->tiles.meta, &p->device_bytes));
             EUT_TRY(upload(&p->d_copies, p->tiles.copies, &p->device_bytes));
             EUT_TRY(upload(&p->d_loc16, p->tiles.loc, &p->device_bytes));
             p->tiles.loc.clear(); p->tiles.loc.shrink_to_fit();
@@ -290,12 +297,12 @@ int plan_build(eut_plan *p, const int32_t *from, const int32_t *to, int64_t n_ed
 
 void plan_free(eut_plan *p)
 {
-    if (!p) return;
+    if (!p || p->host_only) return;
     cudaSetDevice(p->device);
     cudaFree(p->d_nbr); cudaFree(p->d_deg); cudaFree(p->d_w); cudaFree(p->d_perm);
     cudaFree(p->d_iperm); cudaFree(p->d_row_ptr); cudaFree(p->d_col); cudaFree(p->d_out_ptr);
     cudaFree(p->d_out_w);
-    cudaFree(p->d_tile_start); cudaFree(p->d_copy_ptr); cudaFree(p->d_copies); cudaFree(p->d_loc16);
+    cudaFree(p->d_tile_meta); cudaFree(p->d_copies); cudaFree(p->d_loc16);
 }
 
 }  // namespace eut

@@ -9,15 +9,17 @@
 // Only __dadd_rn/__dmul_rn/__dsub_rn are used so that nvcc can never contract to FMA.
 // The reference zeroes its scratch vector with `ychg = ychg * 0`; on finite inputs the result of
 // the substep is the same as starting from +0.0 ("signed zeros"), which is what the
-// Jacobi gather form does here.
+// Jacobi gather form does here.  Adding +0.0 for an unused neighbour slot is exact as well: the
+// running sum starts at +0.0 and x + (+0.0) == x for every x except -0.0, which a sum that started
+// at +0.0 can never be.
 #include "common.h"
 
 namespace eut {
 
 // ---------------------------------------------------------------------------------------------
-// ELL fast path: thread = one point, CPT compound columns per thread (neighbour indices are
-// loaded once and reused for all CPT columns); warp = 32 consecutive internal positions, so every
-// neighbour slot is a run of (mostly) consecutive addresses -> coalesced 256-byte requests.
+// ELL path: thread = one point, CPT compound columns per thread (neighbour indices are loaded
+// once and reused for all CPT columns); warp = 32 consecutive internal positions.  Used when the
+// graph does not tile (tiles.cu) and as a cross-check of the tiled kernel.
 // ---------------------------------------------------------------------------------------------
 template <int W, int CPT>
 __global__ void __launch_bounds__(256)
@@ -86,74 +88,114 @@ k_substep_csr(double *__restrict__ buf, const int64_t col_stride, const int64_t 
 // ---------------------------------------------------------------------------------------------
 // Tiled path (tiles.cu builds the tables): one CTA = one compact tile of <= 256*PPT points and a
 // slice of the active compound columns.  For every column the tile's image -- own points plus halo
-// runs -- is staged into shared memory with cp.async (16-byte granules on the contiguous runs,
-// 8-byte granules on odd ends / lone halo points), NBUF columns deep, so HBM/L2 latency is hidden
-// by the copies of the next columns instead of by occupancy.  The per-thread state (copy granules,
-// 16-bit image offsets of the 12 neighbour slots of PPT points, outflow weights) is loaded once
-// per tile and reused for all columns.  The arithmetic is the same DADD/DMUL sequence as above.
+// runs -- is staged into shared memory NBUF columns deep:
+//   * the 16-byte aligned runs by cp.async.bulk (TMA engine, SASS UBLKCP), issued by the lanes of
+//     warp 0 and completing on an mbarrier with a transaction count;
+//   * odd run ends and lone halo points by 8-byte cp.async (LDGSTS) from the threads that own them.
+// HBM/L2 latency is hidden by the copies of the next columns, not by occupancy.  The per-thread
+// state (copy descriptors, 16-bit image offsets of the 12 neighbour slots of PPT points, outflow
+// weights) is loaded once per tile and reused for all columns of the slice.  The compute step
+// issues all 13 shared-memory loads of two points before their two DADD chains start, so that the
+// chains (fixed summation order, hence serial) overlap each other and the loads.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async_8(uint32_t saddr, const void *g)
+__device__ __forceinline__ void cp_async_8_if(bool on, uint32_t saddr, const void *g)
 {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(saddr), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async_16(uint32_t saddr, const void *g)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(g) : "memory");
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %0, 0;\n"
+                 " @p cp.async.ca.shared.global [%1], [%2], 8;\n}\n" ::"r"((int)on), "r"(saddr), "l"(g) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_arrive(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile("{\n .reg .pred p;\n"
+                 "WAIT_%=:\n"
+                 " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 " @p bra DONE_%=;\n"
+                 " bra WAIT_%=;\n"
+                 "DONE_%=:\n}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t saddr, const void *g, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(saddr), "l"(g), "r"(bytes), "r"(bar) : "memory");
+}
 __device__ __forceinline__ double lds_f64(uint32_t saddr)
 {
     double v;
     asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(saddr));
     return v;
 }
+__device__ __forceinline__ double lds_f64_if(bool on, uint32_t saddr)
+{
+    double v;
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %1, 0;\n mov.f64 %0, 0d0000000000000000;\n"
+                 " @p ld.shared.f64 %0, [%2];\n}\n" : "=d"(v) : "r"((int)on), "r"(saddr));
+    return v;
+}
 
-template <int W, int PPT, int MAXCE, int NBUF>
+template <int PPT, int NBUF>
 __global__ void __launch_bounds__(256, 2)
 k_substep_tile(double *__restrict__ buf, const int64_t col_stride, const int64_t buf_stride,
-               const int32_t *__restrict__ tile_start, const int32_t *__restrict__ copy_ptr,
-               const int2 *__restrict__ copies, const uint16_t *__restrict__ loc16,
-               const uint8_t *__restrict__ deg, const double *__restrict__ wout,
-               const int32_t *__restrict__ act_col, const int32_t *__restrict__ act_par,
-               const int n_act, const int substep, const int img_bytes, const int cols_per_cta)
+               const int32_t *__restrict__ tile_meta, const int2 *__restrict__ copies,
+               const uint16_t *__restrict__ loc16, const uint8_t *__restrict__ deg,
+               const double *__restrict__ wout, const int32_t *__restrict__ act_col,
+               const int32_t *__restrict__ act_par, const int n_act, const int substep,
+               const int img_bytes, const int cols_per_cta)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int W = 12;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long s_bar[NBUF];
     const int tid = threadIdx.x;
     const int tile = blockIdx.x;
-    const int t0 = __ldg(tile_start + tile);
-    const int cnt = __ldg(tile_start + tile + 1) - t0;
     const int a_begin = blockIdx.y * cols_per_cta;
     const int n_cols = min(n_act, a_begin + cols_per_cta) - a_begin;
     if (n_cols <= 0) return;
+    const int4 m0 = __ldg(reinterpret_cast<const int4 *>(tile_meta) + 2 * tile);
+    const int4 m1 = __ldg(reinterpret_cast<const int4 *>(tile_meta) + 2 * tile + 1);
+    const int t0 = m0.x, cnt = m0.y;
     const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t bar_base = (uint32_t)__cvta_generic_to_shared(s_bar);
 
-    // copy granules of this thread
-    int cg[MAXCE];
-    uint32_t cs[MAXCE];
-    {
-        const int c0 = __ldg(copy_ptr + tile);
-        const int nc = __ldg(copy_ptr + tile + 1) - c0;
+    // bulk copies: lanes of warp 0 hold up to two each; single copies: every thread up to two
+    int bg[2] = {0, 0};
+    uint32_t bs[2] = {0, 0};
+    if (tid < 32) {
 #pragma unroll
-        for (int e = 0; e < MAXCE; e++) {
-            const int i = tid + e * 256;
-            int2 d = make_int2(0, 0);
-            if (i < nc) d = __ldg(copies + c0 + i);
-            cg[e] = d.x;
-            cs[e] = (uint32_t)d.y;
+        for (int e = 0; e < 2; e++) {
+            const int i = tid + e * 32;
+            if (i < m0.w) { const int2 d = __ldg(copies + m0.z + i); bg[e] = d.x; bs[e] = (uint32_t)d.y; }
         }
     }
-    // neighbour offsets (bytes inside the image), two per register
+    int sg[2] = {0, 0};
+    uint32_t ss[2] = {0, 0};
+    bool son[2];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+        const int i = tid + e * 256;
+        son[e] = i < m1.y;
+        if (son[e]) { const int2 d = __ldg(copies + m1.x + i); sg[e] = d.x; ss[e] = (uint32_t)d.y * 8u; }
+    }
+    // neighbour offsets (bytes inside the image), two per register; degree class; outflow weight
     uint32_t lo[PPT][W / 2];
-    int dg[PPT];
     double wq[PPT];
+    uint32_t act_mask = 0, hi_mask = 0;
 #pragma unroll
     for (int p = 0; p < PPT; p++) {
         const int lp = tid + p * 256;
         const bool on = lp < cnt;
         const int64_t q = t0 + (on ? lp : 0);
-        dg[p] = on ? (int)__ldg(deg + q) : -1;
+        const int d = (int)__ldg(deg + q);
+        act_mask |= (on ? 1u : 0u) << p;
+        hi_mask |= ((on && d > 8) ? 1u : 0u) << p;
         wq[p] = __ldg(wout + q);
 #pragma unroll
         for (int k = 0; k < W / 2; k++) {
@@ -162,11 +204,14 @@ k_substep_tile(double *__restrict__ buf, const int64_t col_stride, const int64_t
             lo[p][k] = a | (b << 16);
         }
     }
-    // zero cells 0,1 of every buffer (never overwritten by copies)
     if (tid < NBUF) {
+        // image cells 0,1 of every buffer stay zero: the target of unused neighbour slots
         double *z = reinterpret_cast<double *>(smem_raw + (size_t)tid * img_bytes);
         z[0] = 0.0; z[1] = 0.0;
+        mbar_init(bar_base + 8u * tid, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
+    __syncthreads();
     const uint32_t own_off = (uint32_t)(2 + (t0 & 1)) * 8u;
 
     auto issue = [&](int j) {
@@ -175,14 +220,20 @@ k_substep_tile(double *__restrict__ buf, const int64_t col_stride, const int64_t
             const int c = __ldg(act_col + a);
             const int b = (__ldg(act_par + a) + substep) & 1;
             const double *__restrict__ src = buf + (int64_t)b * buf_stride + (int64_t)c * col_stride;
-            const uint32_t sb = s_base + (uint32_t)(j % NBUF) * (uint32_t)img_bytes;
+            const int slot = j % NBUF;
+            const uint32_t sb = s_base + (uint32_t)slot * (uint32_t)img_bytes;
+            const uint32_t bar = bar_base + 8u * slot;
+            if (tid < 32) {
+                if (tid == 0) mbar_expect_tx_arrive(bar, (uint32_t)m1.z);
+                __syncwarp();
 #pragma unroll
-            for (int e = 0; e < MAXCE; e++) {
-                const uint32_t n = cs[e] >> 16;
-                const uint32_t so = sb + (cs[e] & 0xffffu) * 8u;
-                if (n == 2) cp_async_16(so, src + cg[e]);
-                else if (n == 1) cp_async_8(so, src + cg[e]);
+                for (int e = 0; e < 2; e++) {
+                    const uint32_t n = bs[e] >> 16;
+                    if (n) bulk_g2s(sb + (bs[e] & 0xffffu) * 8u, src + bg[e], n * 8u, bar);
+                }
             }
+#pragma unroll
+            for (int e = 0; e < 2; e++) cp_async_8_if(son[e], sb + ss[e], src + sg[e]);
         }
         cp_async_commit();
     };
@@ -192,55 +243,71 @@ k_substep_tile(double *__restrict__ buf, const int64_t col_stride, const int64_t
     for (int j = 0; j < n_cols; j++) {
         issue(j + NBUF - 1);
         cp_async_wait<NBUF - 1>();
+        const int slot = j % NBUF;
+        mbar_wait(bar_base + 8u * slot, (uint32_t)((j / NBUF) & 1));
         __syncthreads();
         const int a = a_begin + j;
         const int c = __ldg(act_col + a);
         const int b = (__ldg(act_par + a) + substep) & 1;
         double *__restrict__ dst = buf + (int64_t)(b ^ 1) * buf_stride + (int64_t)c * col_stride + t0;
-        const uint32_t sb = s_base + (uint32_t)(j % NBUF) * (uint32_t)img_bytes;
+        const uint32_t sb = s_base + (uint32_t)slot * (uint32_t)img_bytes;
 #pragma unroll
-        for (int p = 0; p < PPT; p++) {
-            const int lp = tid + p * 256;
-            if (dg[p] >= 0) {
-                const double cq = lds_f64(sb + own_off + (uint32_t)lp * 8u);
-                double acc = 0.0;
+        for (int pp = 0; pp < PPT; pp += 2) {
+            // loads of two points first ...
+            double v[2][W], cq[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int p = pp + h;
+                const bool on = (act_mask >> p) & 1u, hi = (hi_mask >> p) & 1u;
+                cq[h] = lds_f64_if(on, sb + own_off + (uint32_t)(tid + p * 256) * 8u);
 #pragma unroll
                 for (int k = 0; k < W; k++) {
                     const uint32_t off = (k & 1) ? (lo[p][k >> 1] >> 16) : (lo[p][k >> 1] & 0xffffu);
-                    if (k < dg[p]) acc = __dadd_rn(acc, lds_f64(sb + off));
+                    v[h][k] = (k < 8) ? lds_f64_if(on, sb + off) : lds_f64_if(hi, sb + off);
                 }
-                double y = __dmul_rn(acc, kBDiv);
-                y = __dsub_rn(y, __dmul_rn(cq, wq[p]));
-                dst[lp] = __dadd_rn(cq, y);
+            }
+            // ... then the two summation chains, in mat.in order
+            double acc[2] = {0.0, 0.0};
+#pragma unroll
+            for (int k = 0; k < W; k++) {
+                acc[0] = __dadd_rn(acc[0], v[0][k]);
+                acc[1] = __dadd_rn(acc[1], v[1][k]);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int p = pp + h;
+                double y = __dmul_rn(acc[h], kBDiv);
+                y = __dsub_rn(y, __dmul_rn(cq[h], wq[p]));
+                if ((act_mask >> p) & 1u) dst[tid + p * 256] = __dadd_rn(cq[h], y);
             }
         }
         __syncthreads();
     }
 }
 
-static int launch_tile(eut_field *f, int n_act, int substep)
+int launch_tile(eut_field *f, int n_act, int substep)
 {
     const eut_plan *p = f->plan;
-    constexpr int PPT = 6, MAXCE = 6, NBUF = 3;
-    const int img_bytes = ((p->tiles.img_points * 8 + 15) / 16) * 16;
+    constexpr int PPT = 6, NBUF = 3;
+    const int img_bytes = ((p->tiles.img_points * 8 + 127) / 128) * 128;
     const size_t smem = (size_t)NBUF * img_bytes;
-    // enough CTAs to fill the machine twice, as few column slices as possible (the per-tile
-    // tables are re-read once per slice)
+    // enough CTAs to fill the machine a few times over, as few column slices as possible (the
+    // per-tile tables are re-read once per slice)
     int slices = 1;
-    const int64_t want = 2ll * 148 * 2;
+    const int64_t want = 4ll * 148 * 2;
     while ((int64_t)p->n_tiles * slices < want && slices < n_act) slices++;
     if (f->opt_cpt > 0) slices = (n_act + f->opt_cpt - 1) / f->opt_cpt;
     const int cols_per_cta = (n_act + slices - 1) / slices;
     dim3 grid((unsigned)p->n_tiles, (unsigned)((n_act + cols_per_cta - 1) / cols_per_cta), 1);
-    auto kern = k_substep_tile<12, PPT, MAXCE, NBUF>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    auto kern = k_substep_tile<PPT, NBUF>;
+    static bool attr_set[64] = {false};
+    if (!attr_set[p->device & 63]) {
         EUT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
+        attr_set[p->device & 63] = true;
     }
-    kern<<<grid, 256, smem, f->stream>>>(f->d_buf, p->Np, f->C * p->Np, p->d_tile_start, p->d_copy_ptr,
-                                         p->d_copies, p->d_loc16, p->d_deg, p->d_w, f->d_act,
-                                         f->d_act + f->act_cap, n_act, substep, img_bytes, cols_per_cta);
+    kern<<<grid, 256, smem, f->stream>>>(f->d_buf, p->Np, f->C * p->Np, p->d_tile_meta, p->d_copies,
+                                         p->d_loc16, p->d_deg, p->d_w, f->d_act, f->d_act + f->act_cap,
+                                         n_act, substep, img_bytes, cols_per_cta);
     return EUT_OK;
 }
 

@@ -13,11 +13,14 @@
 //   2. every pair of adjacent rows gets an alignment offset (position of a point's neighbour in the
 //      other row minus its own position); a breadth-first sweep over the row graph turns these
 //      into a column coordinate u for every point and a level for every row;
-//   3. tile  = (band of `levels_per_band` consecutive levels) x (block of `tile_cols` columns);
-//      points are renumbered tile by tile, row by row inside a tile;
-//   4. per tile: halo = in-neighbours outside the tile, grouped into runs of consecutive internal
-//      ids; the shared-memory image is [own points | halo runs | zero cell]; a copy list (16-byte
-//      and 8-byte cp.async granules) and 16-bit local neighbour offsets are emitted.
+//   3. rows are cut into pieces at multiples of `tile_cols` in u; pieces of one u-column that touch
+//      each other form a strip (one per arm of a non-convex domain); every strip is cut along the
+//      level axis into tiles of at most `max_tile_points` points;
+//   4. points are renumbered tile by tile, level by level and row by row inside a tile;
+//   5. per tile: halo = in-neighbours outside the tile, grouped into runs of consecutive internal
+//      ids; the shared-memory image is [2 zero cells | own points | halo runs]; emitted are a list
+//      of bulk copies (16-byte aligned runs, for cp.async.bulk), a list of single 8-byte copies
+//      (odd run ends, lone halo points) and 16-bit image offsets of every neighbour slot.
 #include <algorithm>
 #include <numeric>
 
@@ -26,10 +29,18 @@
 namespace eut {
 
 namespace {
-struct Piece {           // a run of one row inside one tile column
-    int32_t band, ucol, level, row;
+struct Piece {           // a run of one row inside one u-column
+    int32_t ucol, level;
     int32_t first;       // reference id of the first point
     int32_t count;
+    int32_t strip;
+};
+
+struct Dsu {
+    std::vector<int32_t> p;
+    explicit Dsu(size_t n) : p(n) { std::iota(p.begin(), p.end(), 0); }
+    int32_t find(int32_t x) { while (p[x] != x) { p[x] = p[p[x]]; x = p[x]; } return x; }
+    void unite(int32_t a, int32_t b) { a = find(a); b = find(b); if (a != b) p[std::max(a, b)] = std::min(a, b); }
 };
 }  // namespace
 
@@ -57,7 +68,6 @@ int build_tiles(eut_plan *p, const TileParams &tp)
     row_start.push_back((int32_t)N);
 
     // ---- 2. row adjacency with alignment offsets, BFS -> level, column origin ------------------
-    // adjacency in CSR form: for each row the distinct neighbour rows and min(k_other - k_own)
     std::vector<int64_t> adj_ptr(R + 1, 0);
     std::vector<int32_t> adj_row, adj_delta;
     {
@@ -82,116 +92,136 @@ int build_tiles(eut_plan *p, const TileParams &tp)
             adj_ptr[r + 1] = (int64_t)adj_row.size();
         }
     }
-    std::vector<int32_t> level(R, -1), xs(R, 0), comp(R, -1);
-    std::vector<int32_t> comp_rows, comp_maxlevel;
+    std::vector<int32_t> level(R, -1), xs(R, 0);
+    int32_t xmin = 0;
     {
         std::vector<int32_t> queue;
         queue.reserve(R);
+        int32_t level_base = 0;   // components are stacked along the level axis
         for (int32_t seed = 0; seed < R; seed++) {
             if (level[seed] >= 0) continue;
-            const int32_t cid = (int32_t)comp_rows.size();
-            comp_rows.push_back(0);
-            comp_maxlevel.push_back(0);
             size_t head = queue.size();
-            level[seed] = 0; xs[seed] = 0; comp[seed] = cid;
+            level[seed] = level_base; xs[seed] = 0;
             queue.push_back(seed);
+            int32_t maxl = level_base;
             while (head < queue.size()) {
                 const int32_t r = queue[head++];
-                comp_rows[cid]++;
-                comp_maxlevel[cid] = std::max(comp_maxlevel[cid], level[r]);
+                maxl = std::max(maxl, level[r]);
+                xmin = std::min(xmin, xs[r]);
                 for (int64_t a = adj_ptr[r]; a < adj_ptr[r + 1]; a++) {
                     const int32_t rr = adj_row[a];
                     if (level[rr] >= 0) continue;
                     level[rr] = level[r] + 1;
                     xs[rr] = xs[r] - adj_delta[a];   // neighbour at k_other = k_own + delta shares u
-                    comp[rr] = cid;
                     queue.push_back(rr);
                 }
             }
-        }
-    }
-    // normalise u >= 0 per component; bands per component, stacked
-    const int n_comp = (int)comp_rows.size();
-    std::vector<int32_t> comp_xmin(n_comp, INT32_MAX), comp_band0(n_comp, 0), comp_lpb(n_comp, 1);
-    for (int32_t r = 0; r < R; r++) comp_xmin[comp[r]] = std::min(comp_xmin[comp[r]], xs[r]);
-    {
-        int32_t band_base = 0;
-        for (int c = 0; c < n_comp; c++) {
-            const double rows_per_level = (double)comp_rows[c] / (comp_maxlevel[c] + 1);
-            int lpb = tp.levels_per_band > 0
-                          ? tp.levels_per_band
-                          : (int)std::max(1.0, std::floor(tp.target_rows / std::max(1.0, rows_per_level) + 0.5));
-            comp_lpb[c] = lpb;
-            comp_band0[c] = band_base;
-            band_base += comp_maxlevel[c] / lpb + 1;
+            level_base = maxl + 2;
         }
     }
 
-    // ---- 3. pieces -> tiles -> permutation ------------------------------------------------------
-    const int X = tp.tile_cols;
+    // ---- 3. pieces, strips, tiles -------------------------------------------------------------
+    const int X = std::max(2, tp.tile_cols);
     std::vector<Piece> pieces;
     pieces.reserve((size_t)(N / std::max(1, X / 2)) + R);
+    std::vector<int32_t> piece_of(N);
     for (int32_t r = 0; r < R; r++) {
-        const int c = comp[r];
-        const int32_t u0 = xs[r] - comp_xmin[c];
+        const int32_t u0 = xs[r] - xmin;
         const int32_t len = row_start[r + 1] - row_start[r];
-        const int32_t band = comp_band0[c] + level[r] / comp_lpb[c];
         int32_t k = 0;
         while (k < len) {
             const int32_t ucol = (u0 + k) / X;
             const int32_t kend = std::min<int32_t>(len, (ucol + 1) * X - u0);
-            pieces.push_back({band, ucol, level[r], r, row_start[r] + k, kend - k});
+            for (int32_t i = k; i < kend; i++) piece_of[row_start[r] + i] = (int32_t)pieces.size();
+            pieces.push_back({ucol, level[r], row_start[r] + k, kend - k, 0});
             k = kend;
         }
     }
-    std::sort(pieces.begin(), pieces.end(), [](const Piece &a, const Piece &b) {
-        if (a.band != b.band) return a.band < b.band;
-        if (a.ucol != b.ucol) return a.ucol < b.ucol;
-        if (a.level != b.level) return a.level < b.level;
-        return a.first < b.first;
+    const int32_t P = (int32_t)pieces.size();
+    {
+        Dsu dsu(P);
+        for (int64_t i = 0; i < N; i++) {
+            const int32_t a = piece_of[i];
+            for (int64_t k = p->row_ptr[i]; k < p->row_ptr[i + 1]; k++) {
+                const int32_t b = piece_of[p->col[k]];
+                if (a != b && pieces[a].ucol == pieces[b].ucol) dsu.unite(a, b);
+            }
+        }
+        for (int32_t a = 0; a < P; a++) pieces[a].strip = dsu.find(a);
+    }
+    // order pieces: strip by strip (strips by coarse level band, then u-column), level by level
+    std::vector<int32_t> strip_minlevel(P, INT32_MAX);
+    for (int32_t a = 0; a < P; a++)
+        strip_minlevel[pieces[a].strip] = std::min(strip_minlevel[pieces[a].strip], pieces[a].level);
+    std::vector<int32_t> ord(P);
+    std::iota(ord.begin(), ord.end(), 0);
+    const int band = std::max(1, tp.band_levels);
+    std::sort(ord.begin(), ord.end(), [&](int32_t a, int32_t b) {
+        const Piece &A = pieces[a], &B = pieces[b];
+        if (A.strip != B.strip) {
+            const int32_t ba = strip_minlevel[A.strip] / band, bb = strip_minlevel[B.strip] / band;
+            if (ba != bb) return ba < bb;
+            if (A.ucol != B.ucol) return A.ucol < B.ucol;
+            return A.strip < B.strip;
+        }
+        if (A.level != B.level) return A.level < B.level;
+        return A.first < B.first;
     });
+    // cut strips into tiles at level boundaries; a level group that does not fit is split
     p->perm.assign(N, 0);
     T.tile_start.clear();
     {
-        int32_t pos = 0, cur_band = -1, cur_ucol = -1, in_tile = 0;
-        for (const Piece &pc : pieces) {
-            int32_t done = 0;
-            while (done < pc.count) {
-                const bool new_tile = pc.band != cur_band || pc.ucol != cur_ucol || in_tile >= tp.max_tile_points;
-                if (new_tile) {
-                    T.tile_start.push_back(pos);
-                    cur_band = pc.band; cur_ucol = pc.ucol; in_tile = 0;
-                }
-                const int32_t take = std::min(pc.count - done, tp.max_tile_points - in_tile);
-                for (int32_t k = 0; k < take; k++) p->perm[pc.first + done + k] = pos + k;
-                pos += take; done += take; in_tile += take;
+        int32_t pos = 0, in_tile = 0, cur_strip = -1;
+        size_t i = 0;
+        while (i < ord.size()) {
+            size_t e = i;   // level group [i, e)
+            int32_t gcount = 0;
+            while (e < ord.size() && pieces[ord[e]].strip == pieces[ord[i]].strip &&
+                   pieces[ord[e]].level == pieces[ord[i]].level) { gcount += pieces[ord[e]].count; e++; }
+            if (pieces[ord[i]].strip != cur_strip || in_tile + gcount > tp.max_tile_points) {
+                T.tile_start.push_back(pos);
+                in_tile = 0;
+                cur_strip = pieces[ord[i]].strip;
             }
+            for (size_t k = i; k < e; k++) {
+                const Piece &pc = pieces[ord[k]];
+                int32_t done = 0;
+                while (done < pc.count) {
+                    if (in_tile >= tp.max_tile_points) { T.tile_start.push_back(pos); in_tile = 0; }
+                    const int32_t take = std::min(pc.count - done, tp.max_tile_points - in_tile);
+                    for (int32_t q = 0; q < take; q++) p->perm[pc.first + done + q] = pos + q;
+                    pos += take; done += take; in_tile += take;
+                }
+            }
+            i = e;
         }
         T.tile_start.push_back(pos);
+        T.tile_start.erase(std::unique(T.tile_start.begin(), T.tile_start.end()), T.tile_start.end());
     }
     const int32_t n_tiles = (int32_t)T.tile_start.size() - 1;
     p->Np = ((N + kPadPoints - 1) / kPadPoints) * kPadPoints;
     p->iperm.assign(p->Np, -1);
     for (int64_t i = 0; i < N; i++) p->iperm[p->perm[i]] = (int32_t)i;
 
-    // ---- 4. per-tile shared-memory image, copy list, local offsets -----------------------------
+    // ---- 4. per-tile shared-memory image, copy lists, local offsets -----------------------------
     const int W = kEllMax;   // the tiled kernel is compiled for 12 neighbour slots
     T.loc.assign((size_t)W * p->Np, 0);
-    T.copy_ptr.assign(n_tiles + 1, 0);
+    T.meta.assign((size_t)n_tiles * 8, 0);
     T.copies.clear();
-    T.img_points = 0; T.max_tile_points = 0; T.max_copies = 0;
+    T.img_points = 0; T.max_tile_points = 0; T.max_bulk = 0; T.max_single = 0;
     int64_t halo_total = 0;
-    std::vector<int32_t> halo;
+    std::vector<int32_t> halo, halo_off;
+    std::vector<int2> bulk, single;
     auto emit = [&](int32_t g, int32_t s, int32_t len) {
-        // granules: 16 bytes where the global (and, by construction, the shared) offset is even
-        int32_t k = 0;
-        if (len > 0 && ((g + k) & 1)) { T.copies.push_back({g + k, (s + k) | (1 << 16)}); k++; }
-        for (; k + 2 <= len; k += 2) T.copies.push_back({g + k, (s + k) | (2 << 16)});
-        if (k < len) T.copies.push_back({g + k, (s + k) | (1 << 16)});
+        // [odd head] [16-byte aligned body] [odd tail]; global and image offsets share their parity
+        if (len > 0 && (g & 1)) { single.push_back({g, s}); g++; s++; len--; }
+        const int32_t body = len & ~1;
+        if (body > 0) bulk.push_back({g, s | (body << 16)});
+        if (len & 1) single.push_back({g + body, s + body});
     };
     for (int32_t t = 0; t < n_tiles; t++) {
         const int32_t t0 = T.tile_start[t], t1 = T.tile_start[t + 1];
-        halo.clear();
+        halo.clear(); bulk.clear(); single.clear();
         for (int32_t q = t0; q < t1; q++) {
             const int32_t i = p->iperm[q];
             for (int64_t k = p->row_ptr[i]; k < p->row_ptr[i + 1]; k++) {
@@ -202,11 +232,11 @@ int build_tiles(eut_plan *p, const TileParams &tp)
         std::sort(halo.begin(), halo.end());
         halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
         // image: cells 0 and 1 stay zero (target of unused neighbour slots); own points follow at
-        // an offset whose parity equals the global one so that 16-byte granules line up
+        // an offset whose parity equals the global one so that 16-byte copies line up
         const int32_t own_off = 2 + (t0 & 1);
         emit(t0, own_off, t1 - t0);
         int32_t next = own_off + (t1 - t0);
-        std::vector<int32_t> halo_off(halo.size());
+        halo_off.resize(halo.size());
         for (size_t h = 0; h < halo.size();) {
             size_t e = h + 1;
             while (e < halo.size() && halo[e] == halo[e - 1] + 1) e++;
@@ -216,30 +246,39 @@ int build_tiles(eut_plan *p, const TileParams &tp)
             next += (int32_t)(e - h);
             h = e;
         }
-        const int32_t zero_cell = 0;      // never written by a copy, zeroed once by the kernel
         if (next > tp.max_img_points || next * 8 > 65535) return EUT_ERR_UNSUPPORTED;
         T.img_points = std::max(T.img_points, next);
         T.max_tile_points = std::max(T.max_tile_points, t1 - t0);
-        T.copy_ptr[t + 1] = (int32_t)T.copies.size();
-        T.max_copies = std::max(T.max_copies, T.copy_ptr[t + 1] - T.copy_ptr[t]);
+        T.max_bulk = std::max(T.max_bulk, (int)bulk.size());
+        T.max_single = std::max(T.max_single, (int)single.size());
         halo_total += (int64_t)halo.size();
-        // local offsets (in points) of every in-neighbour, mat.in order; unused slots -> zero cell
+        int32_t tx = 0;
+        for (const int2 &b : bulk) tx += (b.y >> 16) * 8;
+        int32_t *m = &T.meta[(size_t)t * 8];
+        m[0] = t0; m[1] = t1 - t0;
+        m[2] = (int32_t)T.copies.size(); m[3] = (int32_t)bulk.size();
+        T.copies.insert(T.copies.end(), bulk.begin(), bulk.end());
+        m[4] = (int32_t)T.copies.size(); m[5] = (int32_t)single.size();
+        T.copies.insert(T.copies.end(), single.begin(), single.end());
+        m[6] = tx; m[7] = next;
+        // image offsets (bytes) of every in-neighbour, mat.in order; unused slots -> zero cell
         for (int32_t q = t0; q < t1; q++) {
             const int32_t i = p->iperm[q];
             const int d = (int)(p->row_ptr[i + 1] - p->row_ptr[i]);
             for (int k = 0; k < W; k++) {
-                int32_t off = zero_cell;
+                int32_t off = 0;
                 if (k < d) {
                     const int32_t nq = p->perm[p->col[p->row_ptr[i] + k]];
                     if (nq >= t0 && nq < t1) off = own_off + (nq - t0);
                     else off = halo_off[std::lower_bound(halo.begin(), halo.end(), nq) - halo.begin()];
                 }
-                T.loc[(size_t)k * p->Np + q] = (uint16_t)(off * 8);   // byte offset inside the image
+                T.loc[(size_t)k * p->Np + q] = (uint16_t)(off * 8);
             }
         }
     }
     T.halo_ratio = (double)halo_total / (double)N;
-    if (T.max_copies > tp.max_copies) return EUT_ERR_UNSUPPORTED;
+    T.n_copies = (int64_t)T.copies.size();
+    if (T.max_bulk > tp.max_bulk || T.max_single > tp.max_single) return EUT_ERR_UNSUPPORTED;
     p->n_tiles = n_tiles;
     return EUT_OK;
 }

@@ -35,7 +35,7 @@ class Plan:
     """The neighbour graph resident on a GPU, consumed exactly as given."""
 
     def __init__(self, mat_in, mat_out, n_points=None, device=0, order=_lib.ORDER_AUTO,
-                 force_generic=False):
+                 force_generic=False, host_only=False):
         mat_in = np.asarray(mat_in).reshape(-1, 2)
         mat_out = np.asarray(mat_out).reshape(-1, 2)
         self._from, self._to = _i32(mat_in[:, 0]), _i32(mat_in[:, 1])
@@ -43,6 +43,7 @@ class Plan:
         if n_points is None:
             n_points = int(mat_out.shape[0])
         flags = int(order) | (_lib.PLAN_FORCE_GENERIC if force_generic else 0)
+        flags |= _lib.PLAN_HOST_ONLY if host_only else 0
         h = C.c_void_p()
         check(_lib.lib().eut_plan_create(C.byref(h), ptr(self._from), ptr(self._to),
                                          self._from.shape[0], ptr(self._id), ptr(self._cnt),
@@ -74,6 +75,16 @@ class Plan:
         col = np.zeros(max(inf.n_edges, 1), dtype=np.int32)
         check(_lib.lib().eut_plan_get_csr(self._h, ptr(rp), ptr(col)))
         return rp, col[:inf.n_edges]
+
+    def tiles(self):
+        """Host tile tables of a `host_only` plan: (meta[n_tiles,8], copies[n,2], loc[12,Np]); see
+        eut_plan_get_tiles in include/eutropia_b200.h for the layout."""
+        inf = self.info
+        meta = np.zeros((max(inf.n_tiles, 1), 8), dtype=np.int32)
+        copies = np.zeros((max(inf.n_copies, 1), 2), dtype=np.int32)
+        loc = np.zeros((12, inf.n_padded), dtype=np.uint16)
+        check(_lib.lib().eut_plan_get_tiles(self._h, ptr(meta), ptr(copies), ptr(loc)))
+        return meta[:inf.n_tiles], copies[:inf.n_copies], loc
 
     def perm(self):
         p = np.zeros(max(self.n_points, 1), dtype=np.int32)

@@ -111,7 +111,9 @@ enum {                       /* eut_plan_create flags */
     EUT_ORDER_ROWBLOCK  = 2, /* whole raster rows reordered breadth-first over the row graph */
     EUT_ORDER_TILED     = 3, /* compact 3-D tiles derived from the graph + shared-memory kernel */
     EUT_ORDER_MASK      = 0xf,
-    EUT_PLAN_FORCE_GENERIC = 0x10 /* use the generic CSR kernel even when the fast path applies */
+    EUT_PLAN_FORCE_GENERIC = 0x10, /* use the generic CSR kernel even when the fast path applies */
+    EUT_PLAN_HOST_ONLY = 0x20      /* run the host analysis only (no CUDA calls): for inspecting the
+                                      ordering / tile tables; such a plan cannot compute */
 };
 
 typedef struct eut_plan_info {
@@ -129,7 +131,9 @@ typedef struct eut_plan_info {
     int32_t tiled;           /* 1: the tiled shared-memory kernel is available */
     int32_t img_points;      /* points per shared-memory image (tiled) */
     int32_t max_tile_points;
-    int32_t max_copies;
+    int32_t max_bulk;        /* most bulk (16-byte aligned run) copies of any tile */
+    int32_t max_single;      /* most single 8-byte copies of any tile */
+    int32_t n_copies;        /* entries in the copy table */
     double  halo_ratio;      /* halo points / own points, summed over tiles (tiled) */
 } eut_plan_info;
 
@@ -142,6 +146,15 @@ EUT_API int eut_plan_get_info(const eut_plan *plan, eut_plan_info *info);
 /* The in-neighbour index map the device uses, translated back to reference ids (1-based), for
  * bit-exact comparison with the CSR derived from mat.in: row_ptr[N+1], col[E]. */
 EUT_API int eut_plan_get_csr(const eut_plan *plan, int64_t *row_ptr, int32_t *col);
+/* Tile tables of a EUT_PLAN_HOST_ONLY plan (sizes from eut_plan_get_info), for inspection and for
+ * the CPU tests of the planner:
+ *   tile_meta[8*n_tiles]  per tile: first internal id, points, first bulk copy, #bulk, first single
+ *                         copy, #single, bytes moved by the bulk copies, image points
+ *   copies[2*n_copies]    bulk: (first internal id, image offset | n_points<<16); single: (id, offset)
+ *   loc[12*n_padded]      byte offset inside the image of every neighbour slot, slot-major
+ * Any pointer may be NULL. */
+EUT_API int eut_plan_get_tiles(const eut_plan *plan, int32_t *tile_meta, int32_t *copies,
+                               uint16_t *loc);
 /* Internal position (0-based) of every reference point id: perm[N]. */
 EUT_API int eut_plan_get_perm(const eut_plan *plan, int32_t *perm);
 
