@@ -187,6 +187,7 @@ int eut_field_set_option(eut_field *f, const char *name, int64_t value)
     if (n == "cpt") f->opt_cpt = (int)value;
     else if (n == "variant") f->opt_variant = (int)value;
     else if (n == "group_cols") f->opt_group_cols = (int)value;
+    else if (n == "nbuf") f->opt_nbuf = (int)value;
     else { set_error("eut_field_set_option: unknown option '%s'", name); return EUT_ERR_ARG; }
     return EUT_OK;
 }

@@ -38,6 +38,7 @@ constexpr double kBDiv = 1.0 / 13;
 
 constexpr int kEllMax = 12;       // widest in-neighbour list the ELL fast path handles
 constexpr int kPadPoints = 64;    // column stride is a multiple of this many points (512 B)
+constexpr int kTileMaxCols = 64;  // compound columns one CTA of the tiled kernel loops over
 
 int ensure_device(int device);
 double now_ms();
@@ -143,6 +144,7 @@ struct eut_field {
     int opt_block = 256;
     int opt_variant = 0;  // 0 auto, 1 ell, 2 generic
     int opt_group_cols = 0;  // 0: substep-major over all active columns; >0: column groups
+    int opt_nbuf = 3;        // staging depth of the tiled kernel (3 or 4 columns)
 };
 
 namespace eut {

@@ -12,6 +12,8 @@
 // Jacobi gather form does here.  Adding +0.0 for an unused neighbour slot is exact as well: the
 // running sum starts at +0.0 and x + (+0.0) == x for every x except -0.0, which a sum that started
 // at +0.0 can never be.
+#include <algorithm>
+
 #include "common.h"
 
 namespace eut {
@@ -142,8 +144,8 @@ __device__ __forceinline__ double lds_f64_if(bool on, uint32_t saddr)
     return v;
 }
 
-template <int PPT, int NBUF>
-__global__ void __launch_bounds__(256, 2)
+template <int PPT, int NBUF, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 k_substep_tile(double *__restrict__ buf, const int64_t col_stride, const int64_t buf_stride,
                const int32_t *__restrict__ tile_meta, const int2 *__restrict__ copies,
                const uint16_t *__restrict__ loc16, const uint8_t *__restrict__ deg,
@@ -154,6 +156,7 @@ k_substep_tile(double *__restrict__ buf, const int64_t col_stride, const int64_t
     constexpr int W = 12;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long s_bar[NBUF];
+    __shared__ long long s_src[kTileMaxCols], s_dst[kTileMaxCols];
     const int tid = threadIdx.x;
     const int tile = blockIdx.x;
     const int a_begin = blockIdx.y * cols_per_cta;
@@ -201,8 +204,15 @@ k_substep_tile(double *__restrict__ buf, const int64_t col_stride, const int64_t
         for (int k = 0; k < W / 2; k++) {
             const uint32_t a = __ldg(loc16 + (int64_t)(2 * k) * col_stride + q);
             const uint32_t b = __ldg(loc16 + (int64_t)(2 * k + 1) * col_stride + q);
-            lo[p][k] = a | (b << 16);
+            lo[p][k] = on ? (a | (b << 16)) : 0u;   // idle lanes read the zero cell
         }
+    }
+    // per-column source / destination offsets of this slice (doubles from `buf`)
+    for (int j = tid; j < n_cols; j += 256) {
+        const int c = __ldg(act_col + a_begin + j);
+        const int b = (__ldg(act_par + a_begin + j) + substep) & 1;
+        s_src[j] = (long long)b * buf_stride + (long long)c * col_stride;
+        s_dst[j] = (long long)(b ^ 1) * buf_stride + (long long)c * col_stride;
     }
     if (tid < NBUF) {
         // image cells 0,1 of every buffer stay zero: the target of unused neighbour slots
@@ -216,10 +226,7 @@ k_substep_tile(double *__restrict__ buf, const int64_t col_stride, const int64_t
 
     auto issue = [&](int j) {
         if (j < n_cols) {
-            const int a = a_begin + j;
-            const int c = __ldg(act_col + a);
-            const int b = (__ldg(act_par + a) + substep) & 1;
-            const double *__restrict__ src = buf + (int64_t)b * buf_stride + (int64_t)c * col_stride;
+            const double *__restrict__ src = buf + s_src[j];
             const int slot = j % NBUF;
             const uint32_t sb = s_base + (uint32_t)slot * (uint32_t)img_bytes;
             const uint32_t bar = bar_base + 8u * slot;
@@ -241,54 +248,54 @@ k_substep_tile(double *__restrict__ buf, const int64_t col_stride, const int64_t
 #pragma unroll
     for (int s = 0; s < NBUF - 1; s++) issue(s);
     for (int j = 0; j < n_cols; j++) {
-        issue(j + NBUF - 1);
-        cp_async_wait<NBUF - 1>();
+        // column j has landed: own 8-byte copies (all groups but the newest NBUF-2), bulk copies
+        // (mbarrier phase), then the block barrier makes every thread's copies visible to all.
+        // The same barrier proves that everybody is done reading buffer (j-1) % NBUF, which is the
+        // one column j+NBUF-1 is staged into next -- one barrier per column.
+        cp_async_wait<NBUF - 2>();
         const int slot = j % NBUF;
         mbar_wait(bar_base + 8u * slot, (uint32_t)((j / NBUF) & 1));
         __syncthreads();
-        const int a = a_begin + j;
-        const int c = __ldg(act_col + a);
-        const int b = (__ldg(act_par + a) + substep) & 1;
-        double *__restrict__ dst = buf + (int64_t)(b ^ 1) * buf_stride + (int64_t)c * col_stride + t0;
+        issue(j + NBUF - 1);
+        double *__restrict__ dst = buf + s_dst[j] + t0;
         const uint32_t sb = s_base + (uint32_t)slot * (uint32_t)img_bytes;
+        // PPT independent summation chains advance in lock step (slot k of every point, then slot
+        // k+1, ...): each chain is serial by contract (mat.in order), but the PPT DADDs of one step
+        // are independent and cover each other's latency; the loads run two steps ahead.
+        double acc[PPT], v[3][PPT];
 #pragma unroll
-        for (int pp = 0; pp < PPT; pp += 2) {
-            // loads of two points first ...
-            double v[2][W], cq[2];
+        for (int p = 0; p < PPT; p++) acc[p] = 0.0;
+#define EUT_OFF(p, k) (((k) & 1) ? (lo[p][(k) >> 1] >> 16) : (lo[p][(k) >> 1] & 0xffffu))
+#define EUT_LOAD(k)                                                                   \
+    _Pragma("unroll") for (int p = 0; p < PPT; p++)                                   \
+        if ((k) < 8 || ((hi_mask >> p) & 1u)) v[(k) % 3][p] = lds_f64(sb + EUT_OFF(p, k));
+#define EUT_ADD(k)                                                                    \
+    _Pragma("unroll") for (int p = 0; p < PPT; p++)                                   \
+        if ((k) < 8 || ((hi_mask >> p) & 1u)) acc[p] = __dadd_rn(acc[p], v[(k) % 3][p]);
+        EUT_LOAD(0) EUT_LOAD(1)
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int p = pp + h;
-                const bool on = (act_mask >> p) & 1u, hi = (hi_mask >> p) & 1u;
-                cq[h] = lds_f64_if(on, sb + own_off + (uint32_t)(tid + p * 256) * 8u);
-#pragma unroll
-                for (int k = 0; k < W; k++) {
-                    const uint32_t off = (k & 1) ? (lo[p][k >> 1] >> 16) : (lo[p][k >> 1] & 0xffffu);
-                    v[h][k] = (k < 8) ? lds_f64_if(on, sb + off) : lds_f64_if(hi, sb + off);
-                }
-            }
-            // ... then the two summation chains, in mat.in order
-            double acc[2] = {0.0, 0.0};
-#pragma unroll
-            for (int k = 0; k < W; k++) {
-                acc[0] = __dadd_rn(acc[0], v[0][k]);
-                acc[1] = __dadd_rn(acc[1], v[1][k]);
-            }
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int p = pp + h;
-                double y = __dmul_rn(acc[h], kBDiv);
-                y = __dsub_rn(y, __dmul_rn(cq[h], wq[p]));
-                if ((act_mask >> p) & 1u) dst[tid + p * 256] = __dadd_rn(cq[h], y);
-            }
+        for (int k = 0; k < W; k++) {
+            if (k + 2 < W) { EUT_LOAD(k + 2) }
+            EUT_ADD(k)
         }
-        __syncthreads();
+#undef EUT_LOAD
+#undef EUT_ADD
+#undef EUT_OFF
+#pragma unroll
+        for (int p = 0; p < PPT; p++) {
+            const bool on = (act_mask >> p) & 1u;
+            const double cq = lds_f64(sb + (on ? own_off + (uint32_t)(tid + p * 256) * 8u : 0u));
+            double y = __dmul_rn(acc[p], kBDiv);
+            y = __dsub_rn(y, __dmul_rn(cq, wq[p]));
+            if ((act_mask >> p) & 1u) dst[tid + p * 256] = __dadd_rn(cq, y);
+        }
     }
 }
 
-int launch_tile(eut_field *f, int n_act, int substep)
+template <int PPT, int NBUF, int MINB>
+static int launch_tile_t(eut_field *f, int n_act, int substep)
 {
     const eut_plan *p = f->plan;
-    constexpr int PPT = 6, NBUF = 3;
     const int img_bytes = ((p->tiles.img_points * 8 + 127) / 128) * 128;
     const size_t smem = (size_t)NBUF * img_bytes;
     // enough CTAs to fill the machine a few times over, as few column slices as possible (the
@@ -297,9 +304,10 @@ int launch_tile(eut_field *f, int n_act, int substep)
     const int64_t want = 4ll * 148 * 2;
     while ((int64_t)p->n_tiles * slices < want && slices < n_act) slices++;
     if (f->opt_cpt > 0) slices = (n_act + f->opt_cpt - 1) / f->opt_cpt;
+    slices = std::max(slices, (n_act + kTileMaxCols - 1) / kTileMaxCols);
     const int cols_per_cta = (n_act + slices - 1) / slices;
     dim3 grid((unsigned)p->n_tiles, (unsigned)((n_act + cols_per_cta - 1) / cols_per_cta), 1);
-    auto kern = k_substep_tile<PPT, NBUF>;
+    auto kern = k_substep_tile<PPT, NBUF, MINB>;
     static bool attr_set[64] = {false};
     if (!attr_set[p->device & 63]) {
         EUT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -309,6 +317,19 @@ int launch_tile(eut_field *f, int n_act, int substep)
                                          p->d_loc16, p->d_deg, p->d_w, f->d_act, f->d_act + f->act_cap,
                                          n_act, substep, img_bytes, cols_per_cta);
     return EUT_OK;
+}
+
+// Points per thread follow the tile size the plan was built with (EUT_TILE_POINTS): 1536-point
+// tiles -> 6 chains per thread, 2 CTAs per SM; <= 1024-point tiles -> 4 chains, 3 CTAs per SM.
+int launch_tile(eut_field *f, int n_act, int substep)
+{
+    const int nbuf = f->opt_nbuf;
+    if (f->plan->tiles.max_tile_points <= 1024) {
+        if (nbuf == 4) return launch_tile_t<4, 4, 3>(f, n_act, substep);
+        return launch_tile_t<4, 3, 3>(f, n_act, substep);
+    }
+    if (nbuf == 4) return launch_tile_t<6, 4, 2>(f, n_act, substep);
+    return launch_tile_t<6, 3, 2>(f, n_act, substep);
 }
 
 template <int W>
