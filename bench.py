@@ -102,20 +102,35 @@ def build_inputs(workload: str, n_cols: int, seed: int, want_conc=True):
     return mesh, conc, cells, ex, substeps
 
 
+def host_threads() -> int:
+    """Host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which is about torch's
+    intra-op threads and not a limit on the box: the reference's policy is `detectCores() - 1`,
+    R/run_simulation.R:137-138; the CPU arm gets all cores)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_sample(mesh, substeps_full, n_cols_full, threads, target_s=12.0):
     """Time the CPU oracle (restatement of diffChangePar, OpenMP over compounds like the reference)
     on a bounded sample of the workload: same mesh, `threads` columns (one per thread, at most the
     workload's columns), as many substeps as fit in about target_s."""
     import oracle
-    from eutropia_b200 import synth
     n = mesh.nfields
-    cols = int(max(1, min(n_cols_full, threads)))
-    conc = synth.synthetic_concentrations(mesh.field_pts, cols, seed=99)
-    iv = np.arange(1, cols + 1, dtype=np.int32)
+    rng = np.random.default_rng(99)
+    # calibration: one substep on one column per thread
+    c1 = int(max(1, min(n_cols_full, threads)))
+    conc = np.asfortranarray(rng.uniform(0.0, 25.0, (n, c1)))
     t0 = time.perf_counter()
-    oracle.diffChangePar(mesh.mat_in, mesh.mat_out, conc, np.ones(cols, np.int32), iv, threads)
-    t1 = time.perf_counter() - t0
-    s = int(max(1, min(substeps_full, target_s / max(t1, 1e-6))))
+    oracle.diffChangePar(mesh.mat_in, mesh.mat_out, conc, np.ones(c1, np.int32), np.arange(1, c1 + 1), threads)
+    t1 = max(time.perf_counter() - t0, 1e-6)
+    # sample: full substep count if it fits, on as many column waves (threads columns each) as fit
+    s = int(max(1, min(substeps_full, target_s / t1)))
+    waves = int(max(1, min(target_s / (t1 * s), n_cols_full / c1)))
+    cols = int(min(n_cols_full, c1 * waves))
+    conc = np.asfortranarray(rng.uniform(0.0, 25.0, (n, cols)))
+    iv = np.arange(1, cols + 1, dtype=np.int32)
     t0 = time.perf_counter()
     oracle.diffChangePar(mesh.mat_in, mesh.mat_out, conc, np.full(cols, s, np.int32), iv, threads)
     dt = time.perf_counter() - t0
@@ -132,7 +147,7 @@ def run_reference(args):
         return
     import oracle
     oracle.build()
-    threads = oracle.max_threads()
+    threads = host_threads()
     mesh_name, cpg, substeps, n_cells, per_cell = WORKLOADS[args.workload]
     mesh, _, _, _, _ = build_inputs(args.workload, 1, seed=1, want_conc=False)
     per_step_target = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
@@ -251,8 +266,8 @@ def run_ours(args):
                                            pin_in.data_ptr(), n, cpg, eb._lib.ptr(niter), eb._lib.ptr(indvar),
                                            cpg, 1, pin_out.data_ptr(), dev))
 
-    e2e_steps = max(1, min(args.steps, 5))
-    for _ in range(2):
+    e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, 5))
+    for _ in range(0 if args.no_e2e else 2):
         e2e_call()
     barrier()
     t0 = time.perf_counter()
@@ -264,7 +279,7 @@ def run_ours(args):
     te = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{dev}")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = updates_per_step * e2e_steps / float(te[0])
+    e2e_value = updates_per_step * e2e_steps / float(te[0]) if e2e_steps else None
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -282,7 +297,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu:
             import oracle
             oracle.build()
-            cpu = cpu_sample(mesh, substeps, cpg, oracle.max_threads())
+            cpu = cpu_sample(mesh, substeps, cpg, host_threads())
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -294,7 +309,8 @@ def run_ours(args):
                        "plan": {"order": int(plan.info.order), "ell_width": int(plan.info.ell_width)}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "k_substep_ell", "launch_ms": launch_ms,
+                         "kernel": "k_substep_tile" if plan.info.tiled else ("k_substep_ell" if plan.info.ell_width else "k_substep_csr"),
+                         "launch_ms": launch_ms,
                          "algorithmic_bytes_per_launch": BYTES_PER_UPDATE * n * cpg},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * cpg * 8,
@@ -302,6 +318,8 @@ def run_ours(args):
                     "api": "eut_diffchange_par (one-shot C ABI, pinned host buffers, graph cached by hash)",
                     "timer": "host wall clock around the blocking calls, max over ranks"},
             "gpu_launches": int(launches), "clocks": clocks,
+            "breakdown_ms_per_step": {"diffusion_substeps": diff_ms / args.steps,
+                                      "scatter_clamp_and_gather": (ms - diff_ms) / args.steps},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -316,6 +334,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="harbor1m", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     ap.add_argument("--opt", action="append", type=lambda s: (s.split("=")[0], int(s.split("=")[1])),
                     help="field option, e.g. --opt cpt=4")
     args = ap.parse_args()

@@ -41,6 +41,10 @@ struct eut_cells {
     int32_t *d_seg_fq = nullptr;    // [n_seg] field position of the group
     int64_t n_seg = 0;
     bool transposed = false;
+    // gather order: entries of every cell sorted by internal field position
+    int32_t *d_g_idx = nullptr;
+    int64_t g_cap = 0;
+    bool g_sorted = false;
     // geometry index for eut_cells_build_lists: field points sorted by (z, x, y)
     int64_t n_pts = 0;
     double *d_gx = nullptr, *d_gy = nullptr;  // sorted coordinates
@@ -145,6 +149,7 @@ static int alloc_entries(eut_cells *c, int64_t M, int64_t T)
     c->M = M;
     c->T = T;
     c->transposed = false;
+    c->g_sorted = false;
     return EUT_OK;
 }
 
@@ -283,26 +288,103 @@ static int finish_lists(eut_cells *c, cudaStream_t s)
 }
 
 // ---- gather ------------------------------------------------------------------------------------
-// one warp per (cell, compound); lanes stride over the cell's entries
+// One warp per (cell, group of G compound columns).  Lanes stride over the cell's entries in the
+// order of their internal field position (g_idx: sorted once per cell map), so the 32 loads of a
+// warp request fall on a few runs of consecutive addresses (x-neighbours of one raster row) instead
+// of 32 different sectors; a lane keeps its (position, acc.prop) pairs in registers and reuses
+// them for the G columns, whose loads are all independent.  Sums are hi+lo pairs, so the walking
+// order does not show in the rounded result.
+template <int G, int EPL>
 __global__ void __launch_bounds__(256)
 k_gather(const double *__restrict__ buf, const int64_t col_stride, const int64_t buf_stride,
          const int32_t *__restrict__ cur, const int64_t *__restrict__ cell_ptr,
-         const int32_t *__restrict__ fq, const double *__restrict__ acc, const double field_vol,
-         double *__restrict__ fmol, const int n_cells, const int n_cols)
+         const int32_t *__restrict__ g_idx, const int32_t *__restrict__ fq,
+         const double *__restrict__ acc, const double field_vol, double *__restrict__ fmol,
+         const int n_cells, const int n_cols, const int n_groups)
 {
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (w >= (int64_t)n_cells * n_cols) return;
-    const int i = (int)(w % n_cells), c = (int)(w / n_cells);
-    const double *__restrict__ col = buf + (int64_t)cur[c] * buf_stride + (int64_t)c * col_stride;
-    dd s{0.0, 0.0};
-    for (int64_t k = cell_ptr[i] + lane; k < cell_ptr[i + 1]; k += 32) {
-        // ((conc / 1000) * fieldVol) * acc.prop   (R/scavenge_compounds.R:17-18)
-        const double v = __dmul_rn(__dmul_rn(__ddiv_rn(col[fq[k]], 1000.0), field_vol), acc[k]);
-        dd_add(s, v);
+    if (w >= (int64_t)n_cells * n_groups) return;
+    const int i = (int)(w / n_groups), c0 = (int)(w % n_groups) * G;
+    dd s[G];
+#pragma unroll
+    for (int u = 0; u < G; u++) s[u] = dd{0.0, 0.0};
+    const int64_t k0 = cell_ptr[i], k1 = cell_ptr[i + 1];
+    for (int64_t kb = k0; kb < k1; kb += 32 * EPL) {
+        int q[EPL];
+        double a[EPL];
+#pragma unroll
+        for (int m = 0; m < EPL; m++) {
+            const int64_t k = kb + lane + 32 * m;
+            q[m] = -1; a[m] = 0.0;
+            if (k < k1) { const int e = g_idx[k]; q[m] = fq[e]; a[m] = acc[e]; }
+        }
+#pragma unroll
+        for (int u = 0; u < G; u++) {
+            const int c = min(c0 + u, n_cols - 1);
+            const double *__restrict__ col = buf + (int64_t)cur[c] * buf_stride + (int64_t)c * col_stride;
+            double v[EPL];
+#pragma unroll
+            for (int m = 0; m < EPL; m++) v[m] = q[m] >= 0 ? __ldg(col + q[m]) : 0.0;
+            // sum_k ((conc_k / 1000) * fieldVol) * acc_k  (R/scavenge_compounds.R:17-22) is evaluated
+            // as ((sum_k conc_k * acc_k) / 1000) * fieldVol: all terms are non-negative, the two
+            // forms differ by a few ulp (<< the 1e-12 bar; R's own long double sum is not
+            // reproducible to the last bit either) and the per-term division leaves the hot loop.
+#pragma unroll
+            for (int m = 0; m < EPL; m++)
+                if (q[m] >= 0) dd_add(s[u], __dmul_rn(v[m], a[m]));
+        }
     }
-    s = dd_warp_sum(s);
-    if (lane == 0) fmol[(int64_t)c * n_cells + i] = dd_value(s);
+#pragma unroll
+    for (int u = 0; u < G; u++) {
+        const dd r = dd_warp_sum(s[u]);
+        if (lane == 0 && c0 + u < n_cols)
+            fmol[(int64_t)(c0 + u) * n_cells + i] = __dmul_rn(__ddiv_rn(dd_value(r), 1000.0), field_vol);
+    }
+}
+
+// key of the per-cell position sort: (cell << 32) | internal position
+__global__ void __launch_bounds__(256)
+k_gather_keys(const int32_t *__restrict__ ecell, const int32_t *__restrict__ fq,
+              unsigned long long *__restrict__ keys, int32_t *__restrict__ vals, const int64_t n)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    keys[k] = ((unsigned long long)(uint32_t)ecell[k] << 32) | (uint32_t)fq[k];
+    vals[k] = (int32_t)k;
+}
+
+static int build_gather_order(eut_cells *c, cudaStream_t s)
+{
+    if (c->g_sorted) return EUT_OK;
+    const int64_t T = c->T;
+    if (T > 0) {
+        EUT_TRY(grow(&c->d_g_idx, &c->g_cap, T));
+        int bits = 1;
+        while ((1ll << bits) < c->plan->Np) bits++;
+        int cbits = 1;
+        while ((1ll << cbits) < c->M + 1) cbits++;
+        size_t sort_bytes = 0;
+        unsigned long long *keys_in = nullptr, *keys_out = nullptr;
+        int32_t *vals_in = nullptr;
+        cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, keys_in, keys_out, vals_in, c->d_g_idx, (int)T, 0,
+                                        32 + cbits, s);
+        const size_t off_keys = ((sort_bytes + 255) / 256) * 256;
+        EUT_TRY(ensure_tmp(c, off_keys + (size_t)T * (8 + 8 + 4) + 1024));
+        char *base = (char *)c->d_tmp;
+        keys_in = (unsigned long long *)(base + off_keys);
+        keys_out = keys_in + T;
+        vals_in = (int32_t *)(keys_out + T);
+        k_gather_keys<<<(unsigned)((T + 255) / 256), 256, 0, s>>>(c->d_ecell, c->d_fq, keys_in, vals_in, T);
+        // position bits below bit `bits` and cell bits from bit 32 up: sort both ranges in one go
+        EUT_CUDA(cub::DeviceRadixSort::SortPairs(base, sort_bytes, keys_in, keys_out, vals_in, c->d_g_idx,
+                                                 (int)T, 0, 32 + cbits, s));
+        (void)bits;
+        c->launches += 2;
+        EUT_CUDA(cudaGetLastError());
+    }
+    c->g_sorted = true;
+    return EUT_OK;
 }
 
 // ---- scatter -----------------------------------------------------------------------------------
@@ -312,28 +394,39 @@ k_ex_colsum(const double *__restrict__ buf, const int64_t col_stride, const int6
             const int32_t *__restrict__ cur, const int64_t *__restrict__ cell_ptr,
             const int32_t *__restrict__ fq, const double *__restrict__ acc, const double field_vol,
             const int64_t *__restrict__ ex_ptr, const int32_t *__restrict__ ex_cpd,
-            const double *__restrict__ ex_flx, double *__restrict__ ex_cs, const int n_cells)
+            const double *__restrict__ ex_flx, double *__restrict__ ex_cs, const int n_cells,
+            const double vol_l)
 {
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= n_cells) return;
     for (int64_t e = ex_ptr[i]; e < ex_ptr[i + 1]; e++) {
-        if (!(ex_flx[e] < 0)) continue;
+        const double ex = ex_flx[e];
+        if (!(ex < 0)) {
+            // production: mM if all went to one field, (ex / 1e12) / (fieldVol / 1e15)  (:732)
+            if (lane == 0) ex_cs[e] = __ddiv_rn(__ddiv_rn(ex, 1e12), vol_l);
+            continue;
+        }
         const int c = ex_cpd[e] - 1;
         const double *__restrict__ col = buf + (int64_t)cur[c] * buf_stride + (int64_t)c * col_stride;
         dd s{0.0, 0.0};
         for (int64_t k = cell_ptr[i] + lane; k < cell_ptr[i + 1]; k += 32)
-            dd_add(s, __dmul_rn(__dmul_rn(__ddiv_rn(col[fq[k]], 1000.0), field_vol), acc[k]));
+            dd_add(s, __dmul_rn(col[fq[k]], acc[k]));   // same form as the gather
         s = dd_warp_sum(s);
-        if (lane == 0) ex_cs[e] = dd_value(s);
+        if (lane == 0) ex_cs[e] = __dmul_rn(__ddiv_rn(dd_value(s), 1000.0), field_vol);
     }
 }
 
-// One thread per touched field point; accumulators for a chunk of CH compounds live in shared
-// memory ([CH][threads], conflict free).  The thread walks the (cell, entry) pairs of its field in
-// cell order and, for every exchange of that cell inside the chunk, adds the contribution in the
-// reference's expression order; then applies sum, NaN->0, add, clamp (R/run_simulation.R:309-319).
-template <int CH, int THREADS>
-__global__ void __launch_bounds__(THREADS)
+// One warp per touched field point.  The warp walks the (cell, entry) pairs of its field in cell
+// order; the exchanges of one cell are evaluated in parallel (lane = exchange: compound, flux,
+// colSum and -- for an uptake -- the field's own concentration are one coalesced / gathered load
+// each), then handed one by one (warp shuffles) to the lane that owns the compound's accumulator
+// (lane = column mod 32, CPL columns per lane, all in registers).  Every (field, compound) sum is
+// thus taken in cell order, like the reference's by-group sum over the concatenated per-cell
+// tables (R/run_simulation.R:309-310).  A cell lists a compound at most once (checked on the
+// host), so the reference's "I.up rows, then I.pd rows" order inside one cell cannot matter.
+// Finally: NaN -> 0, add, clamp (:315-319).
+template <int CPL>
+__global__ void __launch_bounds__(256)
 k_scatter(double *__restrict__ buf, const int64_t col_stride, const int64_t buf_stride,
           const int32_t *__restrict__ cur, const int32_t *__restrict__ seg_start,
           const int32_t *__restrict__ seg_fq, const int32_t *__restrict__ t_entry,
@@ -344,46 +437,64 @@ k_scatter(double *__restrict__ buf, const int64_t col_stride, const int64_t buf_
           const double *__restrict__ ex_flx, const double *__restrict__ ex_cs,
           const uint8_t *__restrict__ is_const, const int n_seg, const int c0, const int n_cols)
 {
-    __shared__ double s_acc[CH][THREADS];
-    const int t = blockIdx.x * THREADS + threadIdx.x;
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (t >= n_seg) return;
+    const unsigned full = 0xffffffffu;
+    // routing table of this warp: slot = column relative to c0, value = (stamp << 5) | source lane
+    __shared__ int s_route[8][32 * CPL];
+    int *route = s_route[threadIdx.x >> 5];
 #pragma unroll
-    for (int j = 0; j < CH; j++) s_acc[j][threadIdx.x] = 0.0;
+    for (int u = 0; u < CPL; u++) route[lane + 32 * u] = -1;
+    __syncwarp();
+    double sum[CPL];
     unsigned touched = 0;
+#pragma unroll
+    for (int u = 0; u < CPL; u++) sum[u] = 0.0;
     const int q = seg_fq[t];
+    int stamp = 0;
     for (int r = seg_start[t]; r < seg_start[t + 1]; r++) {
         const int k = t_entry[r];
         const int i = ecell[k];
-        const double dk = dist[k], ak = acc[k];
-        const double frac = __ddiv_rn(__dsub_rn(dmax[i], dk), fsum[i]);  // :729-730
-        for (int pass = 0; pass < 2; pass++) {                          // I.up rows, then I.pd rows
-            for (int64_t e = ex_ptr[i]; e < ex_ptr[i + 1]; e++) {
+        const double ak = acc[k];
+        const double frac = __ddiv_rn(__dsub_rn(dmax[i], dist[k]), fsum[i]);   // :729-730
+        const int64_t e0 = ex_ptr[i];
+        const int ne = (int)(ex_ptr[i + 1] - e0);
+        for (int base = 0; base < ne; base += 32, stamp++) {
+            const int m = min(32, ne - base);
+            double d = 0.0;
+            if (lane < m) {
+                const int64_t e = e0 + base + lane;
                 const int c = ex_cpd[e] - 1;
-                const int j = c - c0;
-                if (j < 0 || j >= CH) continue;
                 const double ex = ex_flx[e];
-                double d;
-                if (pass == 0) {
-                    if (!(ex < 0)) continue;
-                    const double cv = buf[(int64_t)cur[c] * buf_stride + (int64_t)c * col_stride + q];
-                    const double fpf = __dmul_rn(__dmul_rn(__ddiv_rn(cv, 1000.0), field_vol), ak);
-                    const double am = __ddiv_rn(fpf, ex_cs[e]);                           // :696
-                    d = __ddiv_rn(__ddiv_rn(__dmul_rn(am, ex), 1e12), vol_l);             // :707-708
-                } else {
-                    if (!(ex > 0)) continue;
-                    d = __dmul_rn(frac, __ddiv_rn(__ddiv_rn(ex, 1e12), vol_l));           // :732-734
+                if (c >= c0 && c < c0 + 32 * CPL && c < n_cols && ex != 0.0 && ex == ex) {
+                    if (ex < 0) {
+                        const double cv = buf[(int64_t)cur[c] * buf_stride + (int64_t)c * col_stride + q];
+                        const double fpf = __dmul_rn(__dmul_rn(__ddiv_rn(cv, 1000.0), field_vol), ak);
+                        const double am = __ddiv_rn(fpf, ex_cs[e]);                    // :696
+                        d = __ddiv_rn(__ddiv_rn(__dmul_rn(am, ex), 1e12), vol_l);      // :707-708
+                    } else {
+                        d = __dmul_rn(frac, ex_cs[e]);                                 // :732-734
+                    }
+                    route[c - c0] = (stamp << 5) | lane;
                 }
-                s_acc[j][threadIdx.x] = __dadd_rn(s_acc[j][threadIdx.x], d);
-                touched |= 1u << j;
             }
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < CPL; u++) {
+                const int rt = route[lane + 32 * u];
+                const bool hit = rt >= 0 && (rt >> 5) == stamp;
+                const double dx = __shfl_sync(full, d, hit ? (rt & 31) : 0);
+                if (hit) { sum[u] = __dadd_rn(sum[u], dx); touched |= 1u << u; }
+            }
+            __syncwarp();
         }
     }
 #pragma unroll
-    for (int j = 0; j < CH; j++) {
-        const int c = c0 + j;
-        if (!((touched >> j) & 1u) || c >= n_cols) continue;
+    for (int u = 0; u < CPL; u++) {
+        const int c = c0 + lane + 32 * u;
+        if (!((touched >> u) & 1u) || c >= n_cols) continue;
         if (is_const && is_const[c]) continue;                          // :311-312
-        double d = s_acc[j][threadIdx.x];
+        double d = sum[u];
         if (d != d) d = 0.0;                                             // :315
         double *pc = buf + (int64_t)cur[c] * buf_stride + (int64_t)c * col_stride + q;
         double v = __dadd_rn(*pc, d);                                    // :318
@@ -512,7 +623,7 @@ int eut_cells_destroy(eut_cells *c)
     cudaFree(c->d_gx); cudaFree(c->d_gy); cudaFree(c->d_gfield); cudaFree(c->d_col_start);
     cudaFree(c->d_col_x); cudaFree(c->d_layer_col); cudaFree(c->d_layer_z); cudaFree(c->d_tmp);
     cudaFree(c->d_fmol); cudaFree(c->d_ex_ptr); cudaFree(c->d_ex_cpd); cudaFree(c->d_ex_flx);
-    cudaFree(c->d_ex_cs); cudaFree(c->d_const);
+    cudaFree(c->d_ex_cs); cudaFree(c->d_const); cudaFree(c->d_g_idx);
     delete c;
     return EUT_OK;
 }
@@ -681,10 +792,14 @@ int eut_cells_gather(eut_cells *c, eut_field *f, double field_vol, double *fmol_
     const int64_t n = c->M * f->C;
     if (n == 0) return EUT_OK;
     EUT_TRY(grow(&c->d_fmol, &c->fmol_cap, n));
+    EUT_TRY(build_gather_order(c, 0));
     EUT_CUDA(cudaStreamSynchronize(0));  // list construction runs on the legacy stream
-    const unsigned nb = (unsigned)((n * 32 + 255) / 256);
-    k_gather<<<nb, 256, 0, f->stream>>>(f->d_buf, c->plan->Np, f->C * c->plan->Np, f->d_cur, c->d_cell_ptr,
-                                        c->d_fq, c->d_acc, field_vol, c->d_fmol, (int)c->M, (int)f->C);
+    constexpr int G = 8, EPL = 5;
+    const int n_groups = (int)((f->C + G - 1) / G);
+    const int64_t n_warps = c->M * n_groups;
+    k_gather<G, EPL><<<(unsigned)((n_warps * 32 + 255) / 256), 256, 0, f->stream>>>(
+        f->d_buf, c->plan->Np, f->C * c->plan->Np, f->d_cur, c->d_cell_ptr, c->d_g_idx, c->d_fq, c->d_acc,
+        field_vol, c->d_fmol, (int)c->M, (int)f->C, n_groups);
     f->launches++;
     EUT_CUDA(cudaGetLastError());
     if (fmol_host) {
@@ -703,11 +818,21 @@ int eut_cells_scatter(eut_cells *c, eut_field *f, double field_vol, const uint8_
     const int64_t M = c->M, X = ex_ptr[M];
     if (M == 0 || X == 0 || c->T == 0) return EUT_OK;
     if (!ex_cpd || !ex_flx) { set_error("eut_cells_scatter: NULL exchange arrays"); return EUT_ERR_ARG; }
-    for (int64_t e = 0; e < X; e++)
-        if (ex_cpd[e] < 1 || ex_cpd[e] > f->C) {
-            set_error("index out of bounds: exchange %lld refers to compound column %d of %lld", (long long)e + 1, ex_cpd[e], (long long)f->C);
-            return EUT_ERR_INDEX;
-        }
+    {
+        std::vector<int64_t> stamp(f->C, -1);   // a cell may list a compound only once (EX_ ids are unique)
+        for (int64_t i = 0; i < M; i++)
+            for (int64_t e = ex_ptr[i]; e < ex_ptr[i + 1]; e++) {
+                if (ex_cpd[e] < 1 || ex_cpd[e] > f->C) {
+                    set_error("index out of bounds: exchange %lld refers to compound column %d of %lld", (long long)e + 1, ex_cpd[e], (long long)f->C);
+                    return EUT_ERR_INDEX;
+                }
+                if (stamp[ex_cpd[e] - 1] == i) {
+                    set_error("eut_cells_scatter: cell %lld lists compound column %d twice", (long long)i + 1, ex_cpd[e]);
+                    return EUT_ERR_ARG;
+                }
+                stamp[ex_cpd[e] - 1] = i;
+            }
+    }
     EUT_TRY(build_transposed(c, 0));
     EUT_CUDA(cudaStreamSynchronize(0));
     cudaStream_t s = f->stream;
@@ -732,12 +857,13 @@ int eut_cells_scatter(eut_cells *c, eut_field *f, double field_vol, const uint8_
     const int64_t bs = f->C * c->plan->Np;
     k_ex_colsum<<<(unsigned)((M * 32 + 255) / 256), 256, 0, s>>>(f->d_buf, c->plan->Np, bs, f->d_cur, c->d_cell_ptr,
                                                                 c->d_fq, c->d_acc, field_vol, c->d_ex_ptr,
-                                                                c->d_ex_cpd, c->d_ex_flx, c->d_ex_cs, (int)M);
+                                                                c->d_ex_cpd, c->d_ex_flx, c->d_ex_cs, (int)M,
+                                                                field_vol / 1e15);
     f->launches++;
-    constexpr int CH = 32, TH = 128;
+    constexpr int CPL = 2;
     const double vol_l = field_vol / 1e15;
-    for (int c0 = 0; c0 < f->C; c0 += CH) {
-        k_scatter<CH, TH><<<(unsigned)((c->n_seg + TH - 1) / TH), TH, 0, s>>>(
+    for (int c0 = 0; c0 < f->C; c0 += 32 * CPL) {
+        k_scatter<CPL><<<(unsigned)((c->n_seg * 32 + 255) / 256), 256, 0, s>>>(
             f->d_buf, c->plan->Np, bs, f->d_cur, c->d_seg_start, c->d_seg_fq, c->d_t_entry, c->d_ecell,
             c->d_dist, c->d_acc, c->d_dmax, c->d_fsum, field_vol, vol_l, c->d_ex_ptr, c->d_ex_cpd,
             c->d_ex_flx, c->d_ex_cs, d_const, (int)c->n_seg, c0, (int)f->C);
