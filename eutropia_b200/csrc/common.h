@@ -145,6 +145,10 @@ struct eut_field {
     int opt_variant = 0;  // 0 auto, 1 ell, 2 generic
     int opt_group_cols = 0;  // 0: substep-major over all active columns; >0: column groups
     int opt_nbuf = 3;        // staging depth of the tiled kernel (3 or 4 columns)
+    // halo lists of a slab field (halo.cu)
+    int32_t *d_halo_send = nullptr, *d_halo_recv = nullptr, *d_halo_cols = nullptr;
+    std::vector<int32_t> h_halo_cols;
+    int64_t n_halo_send = 0, n_halo_recv = 0;
 };
 
 namespace eut {

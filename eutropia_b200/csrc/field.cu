@@ -72,6 +72,7 @@ int field_destroy(eut_field *f)
     if (f->down_stream) cudaStreamSynchronize(f->down_stream);
     cudaFree(f->d_buf); cudaFree(f->d_cur); cudaFree(f->d_act); cudaFree(f->d_cols);
     cudaFree(f->d_stats); cudaFree(f->d_stage); cudaFree(f->d_stage2);
+    cudaFree(f->d_halo_send); cudaFree(f->d_halo_recv); cudaFree(f->d_halo_cols);
     for (int i = 0; i < 2; i++) {
         if (f->ev_stage_free[i]) cudaEventDestroy(f->ev_stage_free[i]);
         if (f->ev_stage_ready[i]) cudaEventDestroy(f->ev_stage_ready[i]);

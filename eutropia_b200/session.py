@@ -166,6 +166,19 @@ class Field:
     def fill_column(self, col: int, value: float):
         check(_lib.lib().eut_field_fill_column(self._h, int(col), float(value)))
 
+    # -- halo support for slab sharding (eutropia_b200/slab.py) ---------------------------------
+    def halo_set(self, send_ids, recv_ids):
+        s, r = _i32(send_ids), _i32(recv_ids)
+        check(_lib.lib().eut_field_halo_set(self._h, ptr(s), s.shape[0], ptr(r), r.shape[0]))
+
+    def halo_pack(self, cols, dev_ptr: int):
+        c = _i32(cols)
+        check(_lib.lib().eut_field_halo_pack(self._h, ptr(c), c.shape[0], C.c_void_p(dev_ptr)))
+
+    def halo_unpack(self, cols, dev_ptr: int):
+        c = _i32(cols)
+        check(_lib.lib().eut_field_halo_unpack(self._h, ptr(c), c.shape[0], C.c_void_p(dev_ptr)))
+
 
 class Cells:
     """Ragged cell -> field lists on the device, with gather and scatter against a `Field`."""

@@ -191,6 +191,21 @@ EUT_API int eut_field_column_stats(eut_field *field, double *col_min, double *co
 /* Overwrite a column with one value (D = Inf -> column mean, R/growthEnvironment.R:393-401). */
 EUT_API int eut_field_fill_column(eut_field *field, int32_t col, double value);
 
+/* Halo support for spatial slab sharding (one process per GPU, each with the plan of its slab: own
+ * points + ghost copies of the remote in-neighbours; eutropia_b200/slab.py builds those).  The
+ * reference has no counterpart (it runs on one host); the exchange itself is done by the caller
+ * with NCCL send/recv on the device buffers named here, stream-ordered on eut_field_stream().
+ *   eut_field_halo_set     point ids (1-based, this plan's numbering) whose values are sent to /
+ *                          received from peers, each list in the order of the exchange buffer
+ *   eut_field_halo_pack    dev_out[s * n_cols + j] = current value of column cols[j] at send_ids[s]
+ *   eut_field_halo_unpack  current value of column cols[j] at recv_ids[r] = dev_in[r * n_cols + j]
+ *                          (point-major, so the points of one peer are one contiguous slice)
+ * dev_out / dev_in are DEVICE pointers (e.g. torch tensors). */
+EUT_API int eut_field_halo_set(eut_field *field, const int32_t *send_ids, int64_t n_send,
+                               const int32_t *recv_ids, int64_t n_recv);
+EUT_API int eut_field_halo_pack(eut_field *field, const int32_t *cols, int64_t n_cols, void *dev_out);
+EUT_API int eut_field_halo_unpack(eut_field *field, const int32_t *cols, int64_t n_cols, const void *dev_in);
+
 /* ---- session tier: cells = ragged cell -> field lists + gather / scatter ----------------------
  * Lists follow get_cellFieldEnv_ex's output (R/run_simulation.R:591-624): per cell the field ids
  * (1-based), the cell-field distances and the accessible proportions, in CSR form. */
