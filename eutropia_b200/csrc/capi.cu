@@ -188,6 +188,9 @@ int eut_field_set_option(eut_field *f, const char *name, int64_t value)
     else if (n == "variant") f->opt_variant = (int)value;
     else if (n == "group_cols") f->opt_group_cols = (int)value;
     else if (n == "nbuf") f->opt_nbuf = (int)value;
+    else if (n == "ppt") f->opt_ppt = (int)value;
+    else if (n == "debug") f->opt_debug = (int)value;
+    else if (n == "shape") f->opt_shape = (int)value;
     else { set_error("eut_field_set_option: unknown option '%s'", name); return EUT_ERR_ARG; }
     return EUT_OK;
 }
@@ -296,9 +299,12 @@ int oneshot_run(const int32_t *adj, int64_t n_edges, const int32_t *nn, int64_t 
         return EUT_ERR_ARG;
     }
     std::lock_guard<std::mutex> lock(g_mu);
+    static const bool trace = getenv("EUT_TRACE") != nullptr;
+    const double t_begin = now_ms();
     EUT_TRY(ensure_device(device));
     CachedPlan *cp = nullptr;
     EUT_TRY(get_cached(adj, n_edges, nn, n_nn, n_rows, device, &cp));
+    const double t_plan = now_ms();
     if (!cp->field || cp->field_cols != n_cols) {
         if (cp->field) field_destroy(cp->field);
         cp->field = nullptr;
@@ -352,9 +358,13 @@ int oneshot_run(const int32_t *adj, int64_t n_edges, const int32_t *nn, int64_t 
     for (int64_t c = 0; c < n_cols; c++)
         if (!is_act[c] && n_rows > 0)
             memcpy(conc_out + (size_t)c * n_rows, conc_in + (size_t)c * n_rows, (size_t)n_rows * sizeof(double));
+    const double t_enq = now_ms();
     EUT_CUDA(cudaStreamSynchronize(f->copy_stream));
     EUT_CUDA(cudaStreamSynchronize(f->stream));
     EUT_CUDA(cudaStreamSynchronize(f->down_stream));
+    if (trace)
+        fprintf(stderr, "[eut] one-shot: plan lookup %.2f ms, enqueue %.2f ms, drain %.2f ms\n",
+                t_plan - t_begin, t_enq - t_plan, now_ms() - t_enq);
     return EUT_OK;
 }
 

@@ -52,7 +52,7 @@ namespace eut {
 struct TileParams {
     int tile_cols = 64;          // columns of the pseudo x coordinate per tile
     int band_levels = 16;        // tiles are ordered by coarse level band, then by u column
-    int max_tile_points = 1536;  // = threads per CTA x points per thread of the kernel
+    int max_tile_points = 1024;  // = threads per CTA x points per thread of the kernel
     int max_img_points = 4096;   // shared-memory image limit (points) per buffer
     int max_bulk = 64;           // bulk copies per tile the kernel can hold (2 per lane of warp 0)
     int max_single = 512;        // single 8-byte copies per tile (2 per thread)
@@ -145,6 +145,9 @@ struct eut_field {
     int opt_variant = 0;  // 0 auto, 1 ell, 2 generic
     int opt_group_cols = 0;  // 0: substep-major over all active columns; >0: column groups
     int opt_nbuf = 3;        // staging depth of the tiled kernel (3 or 4 columns)
+    int opt_debug = 0;
+    int opt_ppt = 0;         // > 0: use the first-generation tiled kernel with this many points per thread
+    int opt_shape = 0;       // thread shape of the lean tiled kernel (stencil_tile.cu)
     // halo lists of a slab field (halo.cu)
     int32_t *d_halo_send = nullptr, *d_halo_recv = nullptr, *d_halo_cols = nullptr;
     std::vector<int32_t> h_halo_cols;
@@ -169,6 +172,7 @@ int field_diffuse(eut_field *f, const int32_t *niter, const int32_t *indvar, int
 
 // stencil.cu
 int launch_substep(eut_field *f, int n_act, int substep);
+int launch_tile_u(eut_field *f, int n_act, int substep);   // stencil_tile.cu
 int launch_permute_in(eut_field *f, const double *d_stage, int64_t ld, const int32_t *d_cols,
                       const int32_t *d_cur, int64_t n_cols, cudaStream_t s);
 int launch_permute_out(eut_field *f, double *d_stage, int64_t ld, const int32_t *d_cols,

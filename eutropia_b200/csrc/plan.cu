@@ -5,6 +5,7 @@
 #include <chrono>
 #include <numeric>
 #include <cstdlib>
+#include <thread>
 
 #include "common.h"
 
@@ -48,26 +49,55 @@ int ensure_device(int device)
     return EUT_OK;
 }
 
-uint64_t hash_bytes(const void *data, size_t n, uint64_t seed)
+static uint64_t hash_span(const uint8_t *p, size_t n, uint64_t seed)
 {
-    // 64-bit multiply-rotate over 8-byte words; only used to recognise "same graph as last call".
-    const uint8_t *p = static_cast<const uint8_t *>(data);
-    uint64_t h = seed ^ (n * 0x9E3779B97F4A7C15ull);
-    size_t nw = n / 8;
-    for (size_t i = 0; i < nw; i++) {
+    // 64-bit multiply-rotate over 8-byte words, four independent lanes so the multiplies pipeline
+    uint64_t h[4] = {seed ^ 0x9E3779B97F4A7C15ull, seed ^ 0xC2B2AE3D27D4EB4Full,
+                     seed ^ 0x165667B19E3779F9ull, seed ^ 0xBF58476D1CE4E5B9ull};
+    const size_t nw = n / 8, n4 = nw / 4 * 4;
+    for (size_t i = 0; i < n4; i += 4) {
+        uint64_t w[4];
+        memcpy(w, p + 8 * i, 32);
+        for (int l = 0; l < 4; l++) {
+            h[l] ^= w[l] * 0xC2B2AE3D27D4EB4Full;
+            h[l] = (h[l] << 31) | (h[l] >> 33);
+            h[l] *= 0x9E3779B97F4A7C15ull;
+        }
+    }
+    uint64_t r = h[0] ^ (h[1] * 3) ^ (h[2] * 5) ^ (h[3] * 7) ^ (n * 0x9E3779B97F4A7C15ull);
+    for (size_t i = n4; i < nw; i++) {
         uint64_t w;
         memcpy(&w, p + 8 * i, 8);
-        h ^= w * 0xC2B2AE3D27D4EB4Full;
-        h = (h << 31) | (h >> 33);
-        h *= 0x9E3779B97F4A7C15ull;
+        r = (r ^ w) * 0x9E3779B97F4A7C15ull;
+        r = (r << 29) | (r >> 35);
     }
     uint64_t tail = 0;
     memcpy(&tail, p + 8 * nw, n - 8 * nw);
-    h ^= tail * 0x165667B19E3779F9ull;
-    h ^= h >> 29;
-    h *= 0xBF58476D1CE4E5B9ull;
-    h ^= h >> 32;
-    return h;
+    r ^= tail * 0x165667B19E3779F9ull;
+    r ^= r >> 29;
+    r *= 0xBF58476D1CE4E5B9ull;
+    r ^= r >> 32;
+    return r;
+}
+
+uint64_t hash_bytes(const void *data, size_t n, uint64_t seed)
+{
+    // Only used to recognise "same graph as last call" (R hands mat.in / mat.out over again every
+    // round, R/growthEnvironment.R:385-390).  Large arrays are hashed in parallel slices.
+    const uint8_t *p = static_cast<const uint8_t *>(data);
+    const size_t kSlice = 8u << 20;
+    if (n <= 2 * kSlice) return hash_span(p, n, seed);
+    const size_t n_slices = (n + kSlice - 1) / kSlice;
+    std::vector<uint64_t> part(n_slices);
+    const unsigned n_thr = std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency()));
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < n_thr; t++)
+        pool.emplace_back([&, t]() {
+            for (size_t s = t; s < n_slices; s += n_thr)
+                part[s] = hash_span(p + s * kSlice, std::min(kSlice, n - s * kSlice), seed + s);
+        });
+    for (auto &th : pool) th.join();
+    return hash_span(reinterpret_cast<const uint8_t *>(part.data()), part.size() * 8, seed ^ n);
 }
 
 template <typename T>

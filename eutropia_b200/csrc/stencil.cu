@@ -144,8 +144,8 @@ __device__ __forceinline__ double lds_f64_if(bool on, uint32_t saddr)
     return v;
 }
 
-template <int PPT, int NBUF, int MINB>
-__global__ void __launch_bounds__(256, MINB)
+template <int PPT, int THREADS, int NBUF, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 k_substep_tile(double *__restrict__ buf, const int64_t col_stride, const int64_t buf_stride,
                const int32_t *__restrict__ tile_meta, const int2 *__restrict__ copies,
                const uint16_t *__restrict__ loc16, const uint8_t *__restrict__ deg,
@@ -178,27 +178,31 @@ k_substep_tile(double *__restrict__ buf, const int64_t col_stride, const int64_t
             if (i < m0.w) { const int2 d = __ldg(copies + m0.z + i); bg[e] = d.x; bs[e] = (uint32_t)d.y; }
         }
     }
-    int sg[2] = {0, 0};
-    uint32_t ss[2] = {0, 0};
-    bool son[2];
+    constexpr int SE = (512 + THREADS - 1) / THREADS;   // single copies per thread (<= 512 per tile)
+    int sg[SE];
+    uint32_t ss[SE];
+    bool son[SE];
 #pragma unroll
-    for (int e = 0; e < 2; e++) {
-        const int i = tid + e * 256;
+    for (int e = 0; e < SE; e++) {
+        sg[e] = 0; ss[e] = 0;
+        const int i = tid + e * THREADS;
         son[e] = i < m1.y;
         if (son[e]) { const int2 d = __ldg(copies + m1.x + i); sg[e] = d.x; ss[e] = (uint32_t)d.y * 8u; }
     }
     // neighbour offsets (bytes inside the image), two per register; degree class; outflow weight
     uint32_t lo[PPT][W / 2];
     double wq[PPT];
+    uint32_t own_q[PPT];
     uint32_t act_mask = 0, hi_mask = 0;
 #pragma unroll
     for (int p = 0; p < PPT; p++) {
-        const int lp = tid + p * 256;
+        const int lp = tid + p * THREADS;
         const bool on = lp < cnt;
         const int64_t q = t0 + (on ? lp : 0);
         const int d = (int)__ldg(deg + q);
         act_mask |= (on ? 1u : 0u) << p;
         hi_mask |= ((on && d > 8) ? 1u : 0u) << p;
+        own_q[p] = on ? (uint32_t)(2 + (t0 & 1) + lp) * 8u : 0u;   // own value inside the image
         wq[p] = __ldg(wout + q);
 #pragma unroll
         for (int k = 0; k < W / 2; k++) {
@@ -208,7 +212,7 @@ k_substep_tile(double *__restrict__ buf, const int64_t col_stride, const int64_t
         }
     }
     // per-column source / destination offsets of this slice (doubles from `buf`)
-    for (int j = tid; j < n_cols; j += 256) {
+    for (int j = tid; j < n_cols; j += THREADS) {
         const int c = __ldg(act_col + a_begin + j);
         const int b = (__ldg(act_par + a_begin + j) + substep) & 1;
         s_src[j] = (long long)b * buf_stride + (long long)c * col_stride;
@@ -222,7 +226,6 @@ k_substep_tile(double *__restrict__ buf, const int64_t col_stride, const int64_t
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
-    const uint32_t own_off = (uint32_t)(2 + (t0 & 1)) * 8u;
 
     auto issue = [&](int j) {
         if (j < n_cols) {
@@ -240,7 +243,8 @@ k_substep_tile(double *__restrict__ buf, const int64_t col_stride, const int64_t
                 }
             }
 #pragma unroll
-            for (int e = 0; e < 2; e++) cp_async_8_if(son[e], sb + ss[e], src + sg[e]);
+            for (int e = 0; e < SE; e++)   // warps without single copies skip the block
+                if ((tid & ~31) + e * THREADS < m1.y) cp_async_8_if(son[e], sb + ss[e], src + sg[e]);
         }
         cp_async_commit();
     };
@@ -258,41 +262,33 @@ k_substep_tile(double *__restrict__ buf, const int64_t col_stride, const int64_t
         __syncthreads();
         issue(j + NBUF - 1);
         double *__restrict__ dst = buf + s_dst[j] + t0;
-        const uint32_t sb = s_base + (uint32_t)slot * (uint32_t)img_bytes;
-        // PPT independent summation chains advance in lock step (slot k of every point, then slot
-        // k+1, ...): each chain is serial by contract (mat.in order), but the PPT DADDs of one step
-        // are independent and cover each other's latency; the loads run two steps ahead.
-        double acc[PPT], v[3][PPT];
-#pragma unroll
-        for (int p = 0; p < PPT; p++) acc[p] = 0.0;
-#define EUT_OFF(p, k) (((k) & 1) ? (lo[p][(k) >> 1] >> 16) : (lo[p][(k) >> 1] & 0xffffu))
-#define EUT_LOAD(k)                                                                   \
-    _Pragma("unroll") for (int p = 0; p < PPT; p++)                                   \
-        if ((k) < 8 || ((hi_mask >> p) & 1u)) v[(k) % 3][p] = lds_f64(sb + EUT_OFF(p, k));
-#define EUT_ADD(k)                                                                    \
-    _Pragma("unroll") for (int p = 0; p < PPT; p++)                                   \
-        if ((k) < 8 || ((hi_mask >> p) & 1u)) acc[p] = __dadd_rn(acc[p], v[(k) % 3][p]);
-        EUT_LOAD(0) EUT_LOAD(1)
-#pragma unroll
-        for (int k = 0; k < W; k++) {
-            if (k + 2 < W) { EUT_LOAD(k + 2) }
-            EUT_ADD(k)
-        }
-#undef EUT_LOAD
-#undef EUT_ADD
-#undef EUT_OFF
+        // Per point: all shared-memory loads, then the summation chain in mat.in order (serial by
+        // contract); ptxas interleaves the chains of the PPT points as far as registers allow.
+        // plain shared-memory loads from a uniform image base: ptxas folds base + offset into the
+        // [R + UR] addressing form, one LDS per neighbour after a one-instruction unpack
+        const unsigned char *img = smem_raw + (size_t)slot * img_bytes;
 #pragma unroll
         for (int p = 0; p < PPT; p++) {
-            const bool on = (act_mask >> p) & 1u;
-            const double cq = lds_f64(sb + (on ? own_off + (uint32_t)(tid + p * 256) * 8u : 0u));
-            double y = __dmul_rn(acc[p], kBDiv);
+            const bool on = (act_mask >> p) & 1u, hi = (hi_mask >> p) & 1u;
+            double v[W];
+#pragma unroll
+            for (int k = 0; k < W; k++) {
+                const uint32_t off = (k & 1) ? (lo[p][k >> 1] >> 16) : (lo[p][k >> 1] & 0xffffu);
+                if (k < 8 || hi) v[k] = *reinterpret_cast<const double *>(img + off);
+            }
+            const double cq = *reinterpret_cast<const double *>(img + own_q[p]);
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < W; k++)
+                if (k < 8 || hi) acc = __dadd_rn(acc, v[k]);
+            double y = __dmul_rn(acc, kBDiv);
             y = __dsub_rn(y, __dmul_rn(cq, wq[p]));
-            if ((act_mask >> p) & 1u) dst[tid + p * 256] = __dadd_rn(cq, y);
+            if (on) dst[tid + p * THREADS] = __dadd_rn(cq, y);
         }
     }
 }
 
-template <int PPT, int NBUF, int MINB>
+template <int PPT, int THREADS, int NBUF, int MINB>
 static int launch_tile_t(eut_field *f, int n_act, int substep)
 {
     const eut_plan *p = f->plan;
@@ -307,29 +303,30 @@ static int launch_tile_t(eut_field *f, int n_act, int substep)
     slices = std::max(slices, (n_act + kTileMaxCols - 1) / kTileMaxCols);
     const int cols_per_cta = (n_act + slices - 1) / slices;
     dim3 grid((unsigned)p->n_tiles, (unsigned)((n_act + cols_per_cta - 1) / cols_per_cta), 1);
-    auto kern = k_substep_tile<PPT, NBUF, MINB>;
+    auto kern = k_substep_tile<PPT, THREADS, NBUF, MINB>;
     static bool attr_set[64] = {false};
     if (!attr_set[p->device & 63]) {
         EUT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set[p->device & 63] = true;
     }
-    kern<<<grid, 256, smem, f->stream>>>(f->d_buf, p->Np, f->C * p->Np, p->d_tile_meta, p->d_copies,
-                                         p->d_loc16, p->d_deg, p->d_w, f->d_act, f->d_act + f->act_cap,
-                                         n_act, substep, img_bytes, cols_per_cta);
+    kern<<<grid, THREADS, smem, f->stream>>>(f->d_buf, p->Np, f->C * p->Np, p->d_tile_meta, p->d_copies,
+                                             p->d_loc16, p->d_deg, p->d_w, f->d_act, f->d_act + f->act_cap,
+                                             n_act, substep, img_bytes, cols_per_cta);
     return EUT_OK;
 }
 
-// Points per thread follow the tile size the plan was built with (EUT_TILE_POINTS): 1536-point
-// tiles -> 6 chains per thread, 2 CTAs per SM; <= 1024-point tiles -> 4 chains, 3 CTAs per SM.
+// Thread shape of the tiled kernel: tiles hold up to 1536 points = THREADS x PPT.  Default: 512
+// threads x 3 points, 64 registers, 2 CTAs (32 warps) per SM; option "ppt" selects the others.
 int launch_tile(eut_field *f, int n_act, int substep)
 {
-    const int nbuf = f->opt_nbuf;
-    if (f->plan->tiles.max_tile_points <= 1024) {
-        if (nbuf == 4) return launch_tile_t<4, 4, 3>(f, n_act, substep);
-        return launch_tile_t<4, 3, 3>(f, n_act, substep);
+    const int mtp = f->plan->tiles.max_tile_points;
+    switch (f->opt_ppt) {
+    case 6: return launch_tile_t<6, 256, 3, 2>(f, n_act, substep);
+    case 4: if (mtp <= 1024) return launch_tile_t<4, 256, 3, 3>(f, n_act, substep);
+            return launch_tile_t<4, 384, 3, 2>(f, n_act, substep);
+    case 2: return launch_tile_t<2, 768, 3, 1>(f, n_act, substep);
+    default: return launch_tile_t<3, 512, 3, 2>(f, n_act, substep);
     }
-    if (nbuf == 4) return launch_tile_t<6, 4, 2>(f, n_act, substep);
-    return launch_tile_t<6, 3, 2>(f, n_act, substep);
 }
 
 template <int W>
@@ -360,7 +357,8 @@ int launch_substep(eut_field *f, int n_act, int substep)
     if (n_act <= 0 || p->N == 0) return EUT_OK;
     const int64_t bs = f->C * p->Np;
     if (p->tiled && f->opt_variant != 1) {
-        EUT_TRY(launch_tile(f, n_act, substep));
+        if (f->opt_ppt > 0) EUT_TRY(launch_tile(f, n_act, substep));      // first-generation kernel
+        else EUT_TRY(launch_tile_u(f, n_act, substep));                   // stencil_tile.cu
     } else if (p->ell_w > 0) {
         if (p->ell_w <= 4) EUT_TRY(launch_ell_w<4>(f, n_act, substep));
         else if (p->ell_w <= 8) EUT_TRY(launch_ell_w<8>(f, n_act, substep));

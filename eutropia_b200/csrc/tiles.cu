@@ -128,10 +128,17 @@ int build_tiles(eut_plan *p, const TileParams &tp)
     for (int32_t r = 0; r < R; r++) {
         const int32_t u0 = xs[r] - xmin;
         const int32_t len = row_start[r + 1] - row_start[r];
+        // cuts at multiples of X in u; a remainder shorter than X/2 at either end of the row is
+        // merged into its neighbour piece (no skinny tile columns with more halo than content)
         int32_t k = 0;
         while (k < len) {
-            const int32_t ucol = (u0 + k) / X;
-            const int32_t kend = std::min<int32_t>(len, (ucol + 1) * X - u0);
+            int32_t ucol = (u0 + k) / X;
+            int32_t kend = std::min<int32_t>(len, (ucol + 1) * X - u0);
+            if (k == 0 && kend < len && kend - k < X / 2) {          // short head: extend over the next column
+                ucol += 1;
+                kend = std::min<int32_t>(len, (ucol + 1) * X - u0);
+            }
+            if (len - kend > 0 && len - kend < X / 2) kend = len;    // short tail: absorb it
             for (int32_t i = k; i < kend; i++) piece_of[row_start[r] + i] = (int32_t)pieces.size();
             pieces.push_back({ucol, level[r], row_start[r] + k, kend - k, 0});
             k = kend;
@@ -236,17 +243,67 @@ int build_tiles(eut_plan *p, const TileParams &tp)
         const int32_t own_off = 2 + (t0 & 1);
         emit(t0, own_off, t1 - t0);
         int32_t next = own_off + (t1 - t0);
-        halo_off.resize(halo.size());
+        halo_off.assign(halo.size(), -1);
+        // (a) runs of three or more consecutive ids: contiguous in the image, bulk copied
         for (size_t h = 0; h < halo.size();) {
             size_t e = h + 1;
             while (e < halo.size() && halo[e] == halo[e - 1] + 1) e++;
-            if ((next & 1) != (halo[h] & 1)) next++;
-            for (size_t k = h; k < e; k++) halo_off[k] = next + (int32_t)(k - h);
-            emit(halo[h], next, (int32_t)(e - h));
-            next += (int32_t)(e - h);
+            if (e - h >= 3) {
+                if ((next & 1) != (halo[h] & 1)) next++;
+                for (size_t k = h; k < e; k++) halo_off[k] = next + (int32_t)(k - h);
+                emit(halo[h], next, (int32_t)(e - h));
+                next += (int32_t)(e - h);
+            }
             h = e;
         }
-        if (next > tp.max_img_points || next * 8 > 65535) return EUT_ERR_UNSUPPORTED;
+        // (b) lone halo points (the x-1 / x+1 and diagonal neighbours at the ends of a row piece):
+        // a warp reads such a point together with 31 contiguous cells of a row, so it is placed at
+        // an image offset congruent (mod 16 cells = 128 bytes = all banks) to "one before / one
+        // after" the cells its warp mates read -- the 32 addresses then cover every bank once and
+        // the load is conflict free.  Layout: a 16-column grid after the runs, column = residue.
+        {
+            auto off_of = [&](int32_t nq) -> int32_t {
+                if (nq >= t0 && nq < t1) return own_off + (nq - t0);
+                return halo_off[std::lower_bound(halo.begin(), halo.end(), nq) - halo.begin()];
+            };
+            std::vector<int32_t> want(halo.size(), -1);
+            for (int32_t q = t0; q < t1; q++) {
+                const int32_t i = p->iperm[q];
+                const int d = (int)(p->row_ptr[i + 1] - p->row_ptr[i]);
+                for (int k = 0; k < d; k++) {
+                    const int32_t nq = p->perm[p->col[p->row_ptr[i] + k]];
+                    if (nq >= t0 && nq < t1) continue;
+                    const size_t hi_ = std::lower_bound(halo.begin(), halo.end(), nq) - halo.begin();
+                    if (halo_off[hi_] >= 0 || want[hi_] >= 0) continue;
+                    for (int side = 1; side >= -1 && want[hi_] < 0; side -= 2) {   // warp mate q+1, then q-1
+                        const int32_t q2 = q + side;
+                        if (q2 < t0 || q2 >= t1) continue;
+                        const int32_t i2 = p->iperm[q2];
+                        if (i2 != i + side) continue;   // not the x-neighbour in the same raster row
+                        if ((int)(p->row_ptr[i2 + 1] - p->row_ptr[i2]) <= k) continue;
+                        const int32_t o2 = off_of(p->perm[p->col[p->row_ptr[i2] + k]]);
+                        if (o2 >= 0) want[hi_] = ((o2 - side) % 16 + 16) % 16;
+                    }
+                }
+            }
+            next = (next + 15) / 16 * 16;
+            int32_t fill[16] = {0};
+            int32_t rr = 0;
+            for (size_t h = 0; h < halo.size(); h++) {
+                if (halo_off[h] >= 0) continue;
+                const int32_t r = want[h] >= 0 ? want[h] : (rr++ & 15);
+                halo_off[h] = next + fill[r] * 16 + r;
+                fill[r]++;
+                single.push_back({halo[h], halo_off[h]});
+            }
+            next += 16 * *std::max_element(fill, fill + 16);
+        }
+        if (next > tp.max_img_points || next * 8 > 65535) {
+            if (getenv("EUT_TRACE"))
+                fprintf(stderr, "[eut] tile planner: tile %d (%d points, %zu halo) needs an image of %d points > %d\n",
+                        t, t1 - t0, halo.size(), next, tp.max_img_points);
+            return EUT_ERR_UNSUPPORTED;
+        }
         T.img_points = std::max(T.img_points, next);
         T.max_tile_points = std::max(T.max_tile_points, t1 - t0);
         T.max_bulk = std::max(T.max_bulk, (int)bulk.size());
@@ -278,7 +335,12 @@ int build_tiles(eut_plan *p, const TileParams &tp)
     }
     T.halo_ratio = (double)halo_total / (double)N;
     T.n_copies = (int64_t)T.copies.size();
-    if (T.max_bulk > tp.max_bulk || T.max_single > tp.max_single) return EUT_ERR_UNSUPPORTED;
+    if (T.max_bulk > tp.max_bulk || T.max_single > tp.max_single) {
+        if (getenv("EUT_TRACE"))
+            fprintf(stderr, "[eut] tile planner: %d bulk / %d single copies in one tile exceed %d / %d\n",
+                    T.max_bulk, T.max_single, tp.max_bulk, tp.max_single);
+        return EUT_ERR_UNSUPPORTED;
+    }
     p->n_tiles = n_tiles;
     return EUT_OK;
 }

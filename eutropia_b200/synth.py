@@ -43,6 +43,10 @@ def config_mesh(name: str):
     if name == "square16m":       # config 5
         s = square_side_for(16_000_000)
         return _mesh.make_mesh(f"Rectangle_{s}_{s}", 1.0, 3)
+    if name.startswith("squareL"):      # squareL<layers>:<points>
+        layers = int(name[7:name.index(":")])
+        s = square_side_for(int(name.split(":")[1]), layers=layers)
+        return _mesh.make_mesh(f"Rectangle_{s}_{s}", 1.0, layers)
     if name.startswith("square:"):
         s = square_side_for(int(name.split(":")[1]))
         return _mesh.make_mesh(f"Rectangle_{s}_{s}", 1.0, 3)

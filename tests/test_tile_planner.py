@@ -70,7 +70,7 @@ def test_tiles_fill_up_on_large_mesh():
     plan = eb.Plan(m.mat_in, m.mat_out, order=_lib.ORDER_TILED, host_only=True)
     inf = plan.info
     meta, _, _ = plan.tiles()
-    assert inf.tiled == 1 and np.median(meta[:, 1]) > 1000      # tiles are close to the 1536-point capacity
+    assert inf.tiled == 1 and np.median(meta[:, 1]) > 0.8 * inf.max_tile_points   # tiles are close to capacity
     assert inf.halo_ratio < 0.7
 
 
