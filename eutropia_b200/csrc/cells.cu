@@ -44,6 +44,8 @@ struct eut_cells {
     // gather order: entries of every cell sorted by internal field position
     int32_t *d_g_idx = nullptr;
     int64_t g_cap = 0;
+    int32_t *d_cell_order = nullptr;   // cells sorted by the field position of their first entry
+    int64_t order_cap = 0;
     bool g_sorted = false;
     // geometry index for eut_cells_build_lists: field points sorted by (z, x, y)
     int64_t n_pts = 0;
@@ -300,12 +302,15 @@ k_gather(const double *__restrict__ buf, const int64_t col_stride, const int64_t
          const int32_t *__restrict__ cur, const int64_t *__restrict__ cell_ptr,
          const int32_t *__restrict__ g_idx, const int32_t *__restrict__ fq,
          const double *__restrict__ acc, const double field_vol, double *__restrict__ fmol,
-         const int n_cells, const int n_cols, const int n_groups)
+         const int n_cells, const int n_cols, const int n_groups, const int32_t *__restrict__ cell_order)
 {
+    // column group major, cells in the order of their position in the field: the G columns of a
+    // group (G x 8 MB at 1 M points) stay in L2 while every cell reads them, and neighbouring
+    // warps touch neighbouring sectors
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= (int64_t)n_cells * n_groups) return;
-    const int i = (int)(w / n_groups), c0 = (int)(w % n_groups) * G;
+    const int i = cell_order[(int)(w % n_cells)], c0 = (int)(w / n_cells) * G;
     dd s[G];
 #pragma unroll
     for (int u = 0; u < G; u++) s[u] = dd{0.0, 0.0};
@@ -354,6 +359,17 @@ k_gather_keys(const int32_t *__restrict__ ecell, const int32_t *__restrict__ fq,
     vals[k] = (int32_t)k;
 }
 
+__global__ void __launch_bounds__(256)
+k_cell_keys(const int64_t *__restrict__ cell_ptr, const int32_t *__restrict__ g_idx,
+            const int32_t *__restrict__ fq, int32_t *__restrict__ keys, int32_t *__restrict__ vals,
+            const int n_cells)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cells) return;
+    keys[i] = cell_ptr[i + 1] > cell_ptr[i] ? fq[g_idx[cell_ptr[i]]] : 0x7fffffff;
+    vals[i] = i;
+}
+
 static int build_gather_order(eut_cells *c, cudaStream_t s)
 {
     if (c->g_sorted) return EUT_OK;
@@ -380,6 +396,23 @@ static int build_gather_order(eut_cells *c, cudaStream_t s)
         EUT_CUDA(cub::DeviceRadixSort::SortPairs(base, sort_bytes, keys_in, keys_out, vals_in, c->d_g_idx,
                                                  (int)T, 0, 32 + cbits, s));
         (void)bits;
+        c->launches += 2;
+        EUT_CUDA(cudaGetLastError());
+    }
+    // cells ordered by the field position of their first (lowest) entry
+    if (c->M > 0) {
+        EUT_TRY(grow(&c->d_cell_order, &c->order_cap, c->M));
+        size_t sort_bytes = 0;
+        int32_t *k_in = nullptr, *k_out = nullptr, *v_in = nullptr;
+        cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, k_in, k_out, v_in, c->d_cell_order, (int)c->M, 0, 32, s);
+        const size_t off_k = ((sort_bytes + 255) / 256) * 256;
+        EUT_TRY(ensure_tmp(c, off_k + (size_t)c->M * 12 + 1024));
+        char *base = (char *)c->d_tmp;
+        k_in = (int32_t *)(base + off_k);
+        k_out = k_in + c->M;
+        v_in = k_out + c->M;
+        k_cell_keys<<<(unsigned)((c->M + 255) / 256), 256, 0, s>>>(c->d_cell_ptr, c->d_g_idx, c->d_fq, k_in, v_in, (int)c->M);
+        EUT_CUDA(cub::DeviceRadixSort::SortPairs(base, sort_bytes, k_in, k_out, v_in, c->d_cell_order, (int)c->M, 0, 32, s));
         c->launches += 2;
         EUT_CUDA(cudaGetLastError());
     }
@@ -452,13 +485,27 @@ k_scatter(double *__restrict__ buf, const int64_t col_stride, const int64_t buf_
     for (int u = 0; u < CPL; u++) sum[u] = 0.0;
     const int q = seg_fq[t];
     int stamp = 0;
-    for (int r = seg_start[t]; r < seg_start[t + 1]; r++) {
-        const int k = t_entry[r];
+    const int r_begin = seg_start[t], r_end = seg_start[t + 1];
+    for (int rb = r_begin; rb < r_end; rb += 32) {
+    // the per-cell quantities of up to 32 incident cells are fetched by the lanes in parallel (one
+    // chain of dependent loads for all of them instead of one per cell), then handed out by shuffle
+    double l_ak = 0.0, l_frac = 0.0;
+    long long l_e0 = 0;
+    int l_ne = 0;
+    if (rb + lane < r_end) {
+        const int k = t_entry[rb + lane];
         const int i = ecell[k];
-        const double ak = acc[k];
-        const double frac = __ddiv_rn(__dsub_rn(dmax[i], dist[k]), fsum[i]);   // :729-730
-        const int64_t e0 = ex_ptr[i];
-        const int ne = (int)(ex_ptr[i + 1] - e0);
+        l_ak = acc[k];
+        l_frac = __ddiv_rn(__dsub_rn(dmax[i], dist[k]), fsum[i]);   // :729-730
+        l_e0 = ex_ptr[i];
+        l_ne = (int)(ex_ptr[i + 1] - l_e0);
+    }
+    const int nr = min(32, r_end - rb);
+    for (int rr = 0; rr < nr; rr++) {
+        const double ak = __shfl_sync(full, l_ak, rr);
+        const double frac = __shfl_sync(full, l_frac, rr);
+        const int64_t e0 = __shfl_sync(full, l_e0, rr);
+        const int ne = __shfl_sync(full, l_ne, rr);
         for (int base = 0; base < ne; base += 32, stamp++) {
             const int m = min(32, ne - base);
             double d = 0.0;
@@ -488,6 +535,7 @@ k_scatter(double *__restrict__ buf, const int64_t col_stride, const int64_t buf_
             }
             __syncwarp();
         }
+    }
     }
 #pragma unroll
     for (int u = 0; u < CPL; u++) {
@@ -623,7 +671,7 @@ int eut_cells_destroy(eut_cells *c)
     cudaFree(c->d_gx); cudaFree(c->d_gy); cudaFree(c->d_gfield); cudaFree(c->d_col_start);
     cudaFree(c->d_col_x); cudaFree(c->d_layer_col); cudaFree(c->d_layer_z); cudaFree(c->d_tmp);
     cudaFree(c->d_fmol); cudaFree(c->d_ex_ptr); cudaFree(c->d_ex_cpd); cudaFree(c->d_ex_flx);
-    cudaFree(c->d_ex_cs); cudaFree(c->d_const); cudaFree(c->d_g_idx);
+    cudaFree(c->d_ex_cs); cudaFree(c->d_const); cudaFree(c->d_g_idx); cudaFree(c->d_cell_order);
     delete c;
     return EUT_OK;
 }
@@ -799,7 +847,7 @@ int eut_cells_gather(eut_cells *c, eut_field *f, double field_vol, double *fmol_
     const int64_t n_warps = c->M * n_groups;
     k_gather<G, EPL><<<(unsigned)((n_warps * 32 + 255) / 256), 256, 0, f->stream>>>(
         f->d_buf, c->plan->Np, f->C * c->plan->Np, f->d_cur, c->d_cell_ptr, c->d_g_idx, c->d_fq, c->d_acc,
-        field_vol, c->d_fmol, (int)c->M, (int)f->C, n_groups);
+        field_vol, c->d_fmol, (int)c->M, (int)f->C, n_groups, c->d_cell_order);
     f->launches++;
     EUT_CUDA(cudaGetLastError());
     if (fmol_host) {

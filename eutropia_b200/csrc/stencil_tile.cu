@@ -216,6 +216,9 @@ int launch_tile_u(eut_field *f, int n_act, int substep)
     if (shape == 1 && mtp <= 4 * 384) return launch_u<4, 384, 3, 1>(f, n_act, substep);
     if (shape == 2 && mtp <= 3 * 512) return launch_u<3, 512, 3, 1>(f, n_act, substep);
     if (shape == 3 && mtp <= 5 * 256) return launch_u<5, 256, 3, 2>(f, n_act, substep);
+    if (shape == 4 && mtp <= 3 * 256) return launch_u<3, 256, 3, 3>(f, n_act, substep);
+    if (shape == 5 && mtp <= 2 * 256) return launch_u<2, 256, 3, 4>(f, n_act, substep);
+    if (shape == 6 && mtp <= 4 * 256) return launch_u<4, 256, 2, 2>(f, n_act, substep);
     if (mtp <= 4 * 256) return launch_u<4, 256, 3, 2>(f, n_act, substep);
     if (mtp <= 4 * 384) return launch_u<4, 384, 3, 1>(f, n_act, substep);
     set_error("tiled kernel: tile of %d points exceeds the compiled thread shapes", mtp);
