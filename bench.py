@@ -309,7 +309,7 @@ def run_ours(args):
                        "plan": {"order": int(plan.info.order), "ell_width": int(plan.info.ell_width)}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "k_substep_tile" if plan.info.tiled else ("k_substep_ell" if plan.info.ell_width else "k_substep_csr"),
+                         "kernel": "k_substep_seg" if plan.info.segmented else "k_substep_tile" if plan.info.tiled else ("k_substep_ell" if plan.info.ell_width else "k_substep_csr"),
                          "launch_ms": launch_ms,
                          "algorithmic_bytes_per_launch": BYTES_PER_UPDATE * n * cpg},
             "cpu_baseline": cpu,

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libeutropia_b200.so")
 
 OK, ERR_INDEX, ERR_ARG, ERR_ALLOC, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED, ERR_NCCL = range(8)
 
-ORDER_AUTO, ORDER_IDENTITY, ORDER_ROWBLOCK, ORDER_TILED = 0, 1, 2, 3
+ORDER_AUTO, ORDER_IDENTITY, ORDER_ROWBLOCK, ORDER_TILED, ORDER_SEGMENTS = 0, 1, 2, 3, 4
 PLAN_FORCE_GENERIC = 0x10
 PLAN_HOST_ONLY = 0x20
 
@@ -37,6 +37,9 @@ class PlanInfo(C.Structure):
         ("tiled", C.c_int32), ("img_points", C.c_int32), ("max_tile_points", C.c_int32),
         ("max_bulk", C.c_int32), ("max_single", C.c_int32), ("n_copies", C.c_int32),
         ("halo_ratio", C.c_double),
+        ("segmented", C.c_int32), ("seg_points", C.c_int32), ("max_tile_segs", C.c_int32),
+        ("max_tile_generic", C.c_int32), ("n_segments", C.c_int64), ("n_generic", C.c_int64),
+        ("n_seg_covered", C.c_int64),
     ]
 
 
@@ -67,6 +70,7 @@ def lib() -> C.CDLL:
         "eut_plan_get_csr": (C.c_int, [vp, vp, vp]),
         "eut_plan_get_perm": (C.c_int, [vp, vp]),
         "eut_plan_get_tiles": (C.c_int, [vp, vp, vp, vp]),
+        "eut_plan_get_segs": (C.c_int, [vp, vp, vp, vp, vp]),
         "eut_field_create": (C.c_int, [C.POINTER(vp), vp, i64]),
         "eut_field_destroy": (C.c_int, [vp]),
         "eut_field_upload": (C.c_int, [vp, vp, i64, vp, i64]),
@@ -103,7 +107,7 @@ def lib() -> C.CDLL:
 EXPORTS = (
     "eut_last_error eut_abi_version eut_device_count eut_diffchange eut_diffchange_par "
     "eut_oneshot_reset eut_plan_create eut_plan_destroy eut_plan_get_info eut_plan_get_csr "
-    "eut_plan_get_perm eut_plan_get_tiles eut_field_create eut_field_destroy eut_field_upload eut_field_download "
+    "eut_plan_get_perm eut_plan_get_tiles eut_plan_get_segs eut_field_create eut_field_destroy eut_field_upload eut_field_download "
     "eut_field_diffuse eut_field_sync eut_field_stream eut_field_set_stream "
     "eut_field_launch_count eut_field_set_option eut_field_column_stats eut_field_fill_column "
     "eut_field_halo_set eut_field_halo_pack eut_field_halo_unpack "

@@ -62,6 +62,15 @@ int eut_plan_get_info(const eut_plan *p, eut_plan_info *info)
     info->max_tile_points = p->tiles.max_tile_points; info->max_bulk = p->tiles.max_bulk;
     info->max_single = p->tiles.max_single; info->n_copies = (int32_t)p->tiles.n_copies;
     info->halo_ratio = p->tiles.halo_ratio;
+    const auto &S = p->segs;
+    info->segmented = p->segmented ? 1 : 0; info->seg_points = S.R;
+    info->max_tile_segs = S.max_tile_segs; info->max_tile_generic = S.max_gen;
+    info->n_segments = S.n_segs; info->n_generic = S.n_gens; info->n_seg_covered = S.seg_points;
+    if (p->segmented) {
+        info->img_points = S.img_points; info->max_tile_points = S.max_tile_points;
+        info->max_bulk = S.max_bulk; info->max_single = S.max_single;
+        info->n_copies = (int32_t)S.n_copies; info->halo_ratio = S.halo_ratio;
+    }
     return EUT_OK;
 }
 
@@ -112,6 +121,18 @@ int eut_plan_get_tiles(const eut_plan *p, int32_t *tile_meta, int32_t *copies, u
     if (tile_meta) std::copy(T.meta.begin(), T.meta.end(), tile_meta);
     if (copies) memcpy(copies, T.copies.data(), T.copies.size() * sizeof(int2));
     if (loc) std::copy(T.loc.begin(), T.loc.end(), loc);
+    return EUT_OK;
+}
+
+int eut_plan_get_segs(const eut_plan *p, int32_t *seg_meta, int32_t *copies, uint16_t *segs, uint16_t *gens)
+{
+    if (!p || !p->segmented) { set_error("eut_plan_get_segs: plan has no segment tables"); return EUT_ERR_ARG; }
+    if (!p->host_only) { set_error("eut_plan_get_segs: only for EUT_PLAN_HOST_ONLY plans"); return EUT_ERR_UNSUPPORTED; }
+    const auto &S = p->segs;
+    if (seg_meta) std::copy(S.meta.begin(), S.meta.end(), seg_meta);
+    if (copies) memcpy(copies, S.copies.data(), S.copies.size() * sizeof(int2));
+    if (segs) std::copy(S.segs.begin(), S.segs.end(), segs);
+    if (gens) std::copy(S.gens.begin(), S.gens.end(), gens);
     return EUT_OK;
 }
 

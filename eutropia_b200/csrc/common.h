@@ -73,11 +73,58 @@ struct TilePlanHost {
 }  // namespace eut
 
 // ---------------------------------------------------------------------------------------------
+// row analysis (rows.cu) and the segment planner (segs.cu)
+// ---------------------------------------------------------------------------------------------
+namespace eut {
+struct RowAnalysis {
+    int32_t n_rows = 0, xmin = 0;
+    std::vector<int32_t> row_of;      // [N]   row of every reference id
+    std::vector<int32_t> row_start;   // [R+1] first reference id of every row
+    std::vector<int64_t> adj_ptr;     // [R+1] adjacent rows of every row, ascending
+    std::vector<int32_t> adj_row, adj_delta;
+    std::vector<uint8_t> adj_pair;    // some point of the row has two neighbours in the other row
+    std::vector<int32_t> level, xs;   // [R]   BFS level, column coordinate of the row's first point
+};
+struct SegParams {
+    int R = 7;                   // points per segment (odd: conflict-free 8-byte strides)
+    int tile_cols = 56;          // columns of the pseudo x coordinate per tile (8 segments)
+    int band_levels = 16;
+    int max_tile_segs = 224;     // consumer threads per CTA x segments per thread of the kernel
+    int max_tile_points = 4000;  // 12-bit offsets into the tile's result buffer
+    int max_img_points = 8192;   // shared-memory image limit (cells) per buffer
+    int max_bulk = 128;          // bulk copies per tile the kernel can hold (4 per lane of warp 0)
+    int max_single = 512;        // single 8-byte copies per tile
+};
+struct SegPlanHost {
+    std::vector<int32_t> tile_start;  // [n_tiles+1] internal ids
+    // per tile 12 ints: first id, points, first bulk copy, #bulk, first single copy, #single, bytes
+    // moved by the bulk copies, image cells, first segment, #segments, first generic point, #generic
+    std::vector<int32_t> meta;
+    std::vector<int2> copies;         // as TilePlanHost::copies
+    // per segment 8 x uint16: image cell of the first value of the streams O, A, B, C, D, E, F
+    // (0 = absent stream: the zero header), then result-buffer cell | length << 12
+    std::vector<uint16_t> segs;
+    // per generic point 16 x uint16: image cells of the 12 neighbour slots (0 = unused), own image
+    // cell, result-buffer cell, 0, 0
+    std::vector<uint16_t> gens;
+    int R = 0, zero_cells = 0, img_points = 0, max_tile_points = 0, max_tile_segs = 0, max_bulk = 0,
+        max_single = 0, max_gen = 0;
+    int64_t n_copies = 0, n_segs = 0, n_gens = 0, seg_points = 0;
+    double halo_ratio = 0;
+};
+}  // namespace eut
+
+// ---------------------------------------------------------------------------------------------
 // plan: neighbour graph resident on one GPU
 // ---------------------------------------------------------------------------------------------
 struct eut_plan {
     eut::TilePlanHost tiles;
+    eut::SegPlanHost segs;
     bool tiled = false;
+    bool segmented = false;      // segs (not tiles) describes the tiles; kernel: stencil_seg.cu
+    int32_t *d_seg_meta = nullptr;
+    uint4 *d_segs = nullptr;     // one per segment
+    uint4 *d_gens = nullptr;     // two per generic point
     bool host_only = false;
     int32_t *d_tile_meta = nullptr;
     int2 *d_copies = nullptr;
@@ -161,6 +208,8 @@ int plan_build(eut_plan *p, const int32_t *from, const int32_t *to, int64_t n_ed
 void plan_free(eut_plan *p);
 uint64_t hash_bytes(const void *data, size_t n, uint64_t seed);
 int build_tiles(eut_plan *p, const TileParams &tp);
+void analyse_rows(const eut_plan *p, RowAnalysis &ra);
+int build_segs(eut_plan *p, const SegParams &sp);
 
 // field.cu
 int field_create(eut_field **out, eut_plan *plan, int64_t n_cols);
@@ -173,6 +222,7 @@ int field_diffuse(eut_field *f, const int32_t *niter, const int32_t *indvar, int
 // stencil.cu
 int launch_substep(eut_field *f, int n_act, int substep);
 int launch_tile_u(eut_field *f, int n_act, int substep);   // stencil_tile.cu
+int launch_seg(eut_field *f, int n_act, int substep);      // stencil_seg.cu
 int launch_permute_in(eut_field *f, const double *d_stage, int64_t ld, const int32_t *d_cols,
                       const int32_t *d_cur, int64_t n_cols, cudaStream_t s);
 int launch_permute_out(eut_field *f, double *d_stage, int64_t ld, const int32_t *d_cols,

@@ -247,8 +247,22 @@ int plan_build(eut_plan *p, const int32_t *from, const int32_t *to, int64_t n_ed
     // -- ordering -----------------------------------------------------------------------------
     const bool ell_ok = regular && p->max_in <= kEllMax && !(flags & EUT_PLAN_FORCE_GENERIC);
     uint32_t order = flags & EUT_ORDER_MASK;
-    if (order == EUT_ORDER_AUTO) order = ell_ok ? EUT_ORDER_TILED : EUT_ORDER_ROWBLOCK;
+    if (order == EUT_ORDER_AUTO) {
+        const char *e = getenv("EUT_ORDER");
+        order = !ell_ok ? EUT_ORDER_ROWBLOCK : (e && atoi(e) == EUT_ORDER_TILED ? EUT_ORDER_TILED : EUT_ORDER_SEGMENTS);
+    }
     p->tiled = false;
+    p->segmented = false;
+    if (order == EUT_ORDER_SEGMENTS && N > 0 && ell_ok) {
+        SegParams sp;
+        if (const char *e = getenv("EUT_SEG_R")) sp.R = atoi(e);
+        sp.tile_cols = 8 * sp.R;
+        if (const char *e = getenv("EUT_SEG_COLS")) sp.tile_cols = atoi(e);
+        if (const char *e = getenv("EUT_SEG_TILE")) sp.max_tile_segs = std::min(448, std::max(8, atoi(e)));
+        if (const char *e = getenv("EUT_TILE_BAND")) sp.band_levels = atoi(e);
+        if (build_segs(p, sp) == EUT_OK) p->segmented = true;
+        else order = EUT_ORDER_TILED;      // not lattice-like enough / tiles too large: first tiled kernel
+    } else if (order == EUT_ORDER_SEGMENTS) order = EUT_ORDER_ROWBLOCK;
     if (order == EUT_ORDER_TILED && N > 0 && ell_ok) {
         TileParams tp;
         if (const char *e = getenv("EUT_TILE_COLS")) tp.tile_cols = atoi(e);
@@ -257,7 +271,7 @@ int plan_build(eut_plan *p, const int32_t *from, const int32_t *to, int64_t n_ed
         if (build_tiles(p, tp) == EUT_OK) p->tiled = true;
         else order = EUT_ORDER_ROWBLOCK;   // graph not lattice-like enough: ELL kernel
     } else if (order == EUT_ORDER_TILED) order = EUT_ORDER_ROWBLOCK;
-    if (!p->tiled) {
+    if (!p->tiled && !p->segmented) {
         if (order == EUT_ORDER_ROWBLOCK && N > 0) order_rowblock(p);
         else { order = EUT_ORDER_IDENTITY; order_identity(p); }
         p->Np = ((N + kPadPoints - 1) / kPadPoints) * kPadPoints;
@@ -303,6 +317,19 @@ int plan_build(eut_plan *p, const int32_t *from, const int32_t *to, int64_t n_ed
             p->tiles.loc.clear(); p->tiles.loc.shrink_to_fit();
             p->tiles.copies.clear(); p->tiles.copies.shrink_to_fit();
         }
+        if (p->segmented) {
+            SegPlanHost &S = p->segs;
+            EUT_TRY(upload(&p->d_seg_meta, S.meta, &p->device_bytes));
+            EUT_TRY(upload(&p->d_copies, S.copies, &p->device_bytes));
+            std::vector<uint4> tmp(S.segs.size() / 8);
+            if (!tmp.empty()) memcpy(tmp.data(), S.segs.data(), S.segs.size() * sizeof(uint16_t));
+            EUT_TRY(upload(&p->d_segs, tmp, &p->device_bytes));
+            tmp.assign(S.gens.size() / 8, make_uint4(0, 0, 0, 0));
+            if (!tmp.empty()) memcpy(tmp.data(), S.gens.data(), S.gens.size() * sizeof(uint16_t));
+            EUT_TRY(upload(&p->d_gens, tmp, &p->device_bytes));
+            S.segs.clear(); S.segs.shrink_to_fit(); S.gens.clear(); S.gens.shrink_to_fit();
+            S.copies.clear(); S.copies.shrink_to_fit();
+        }
     } else {
         p->ell_w = 0;
         std::vector<int64_t> rp(N + 1, 0), op(N + 1, 0);
@@ -333,6 +360,7 @@ void plan_free(eut_plan *p)
     cudaFree(p->d_iperm); cudaFree(p->d_row_ptr); cudaFree(p->d_col); cudaFree(p->d_out_ptr);
     cudaFree(p->d_out_w);
     cudaFree(p->d_tile_meta); cudaFree(p->d_copies); cudaFree(p->d_loc16);
+    cudaFree(p->d_seg_meta); cudaFree(p->d_segs); cudaFree(p->d_gens);
 }
 
 }  // namespace eut

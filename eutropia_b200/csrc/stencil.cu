@@ -356,7 +356,9 @@ int launch_substep(eut_field *f, int n_act, int substep)
     const eut_plan *p = f->plan;
     if (n_act <= 0 || p->N == 0) return EUT_OK;
     const int64_t bs = f->C * p->Np;
-    if (p->tiled && f->opt_variant != 1) {
+    if (p->segmented && f->opt_variant != 1) {
+        EUT_TRY(launch_seg(f, n_act, substep));                           // stencil_seg.cu
+    } else if (p->tiled && f->opt_variant != 1) {
         if (f->opt_ppt > 0) EUT_TRY(launch_tile(f, n_act, substep));      // first-generation kernel
         else EUT_TRY(launch_tile_u(f, n_act, substep));                   // stencil_tile.cu
     } else if (p->ell_w > 0) {

@@ -1,0 +1,379 @@
+// Segment substep kernel: one Jacobi substep of diffChange (src/diffChange.cpp:14-30) with register
+// reuse along the raster row.  Tables from segs.cu.
+//
+//   CTA  = tile x slice of compound columns, warp specialised:
+//     * one PRODUCER warp stages, NBUF columns ahead, the tile image of every column (own rows +
+//       halo rows, holes left +0.0) with cp.async.bulk (UBLKCP; transaction count on an mbarrier)
+//       plus 8-byte cp.async for odd ends / apron cells (cp.async.mbarrier.arrive.noinc on the same
+//       mbarrier), and drains the finished columns: ONE cp.async.bulk shared->global per column, so
+//       the results cost no LSU wavefronts and are full-sector writes;
+//     * CWARPS CONSUMER warps compute.  thread = SPT segments of up to R consecutive points; per
+//       segment seven image offsets (the streams O, A..F of segs.cu): 7R+6 LDS.64 per R points
+//       instead of 13R.  The R summation chains run in lock step, each strictly in the canonical
+//       order A A B B C O- O+ D E E F F (= mat.in order; verified per point by the planner),
+//       starting from +0.0.  Streams a whole warp does not have (bottom / top layer) are skipped by
+//       a warp-uniform branch; a lane that lacks a stream its warp runs reads the zero header.
+//       Results go to a shared-memory result buffer in internal-id order (STS, lane stride R cells).
+//   There is no CTA-wide barrier in the column loop: image slots and result buffers are handed
+//   over with full/empty mbarriers, so a warp that is ahead (bottom/top-layer warps have 30 % less
+//   work) keeps going for up to NBUF-1 columns.
+//   generic points (failed the planner's check; rare) use twelve explicit slots read from global.
+//
+// Arithmetic: only __dadd_rn / __dmul_rn / __dsub_rn, identical to the other substep kernels.
+#include <algorithm>
+
+#include "common.h"
+
+namespace eut {
+
+namespace {
+__device__ __forceinline__ void s_cp_async_8(uint32_t saddr, const void *g)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void s_cp_async_16(uint32_t saddr, const void *g)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void s_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void s_cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void s_mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void s_mbar_expect_tx_arrive(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void s_mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile("{\n .reg .pred p;\n"
+                 "WAIT_%=:\n"
+                 " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 " @p bra DONE_%=;\n"
+                 " bra WAIT_%=;\n"
+                 "DONE_%=:\n}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void s_bulk_g2s(uint32_t saddr, const void *g, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(saddr), "l"(g), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void s_bulk_s2g(void *g, uint32_t saddr, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(g), "r"(saddr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void s_bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void s_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void s_fence_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void s_mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void s_cp_async_arrive_noinc(uint32_t bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void s_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory"); }
+}  // namespace
+
+
+template <int R, int SPT, int CWARPS, int NBUF, int OB, int MINB>
+__global__ void __launch_bounds__((CWARPS + 1) * 32, MINB)
+k_substep_seg(double *__restrict__ buf, const int64_t col_stride, const int64_t buf_stride,
+              const int32_t *__restrict__ seg_meta, const int2 *__restrict__ copies,
+              const uint4 *__restrict__ segs, const uint4 *__restrict__ gens,
+              const double *__restrict__ wout, const int32_t *__restrict__ act_col,
+              const int32_t *__restrict__ act_par, const int n_act, const int substep,
+              const int img_bytes, const int out_bytes, const int cols_per_cta, const int dbg)
+{
+    constexpr int THREADS = (CWARPS + 1) * 32;
+    constexpr int CTHREADS = CWARPS * 32;
+    constexpr int BE = 4;                                  // bulk copies per producer lane
+    constexpr int SE = 16;                                 // single copies per producer lane
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // mbarriers: full[NBUF], empty[NBUF], out_full[OB], out_empty[OB]
+    __shared__ __align__(8) unsigned long long s_bar[2 * NBUF + 2 * OB];
+    __shared__ long long s_src[kTileMaxCols], s_dst[kTileMaxCols];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int tile = blockIdx.x;
+    const int a_begin = blockIdx.y * cols_per_cta;
+    const int n_cols = min(n_act, a_begin + cols_per_cta) - a_begin;
+    if (n_cols <= 0) return;
+    const int4 m0 = __ldg(reinterpret_cast<const int4 *>(seg_meta) + 3 * tile);
+    const int4 m1 = __ldg(reinterpret_cast<const int4 *>(seg_meta) + 3 * tile + 1);
+    const int4 m2 = __ldg(reinterpret_cast<const int4 *>(seg_meta) + 3 * tile + 2);
+    const int t0 = m0.x, cnt = m0.y;
+    const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t out_base = s_base + (uint32_t)NBUF * (uint32_t)img_bytes;
+    const uint32_t bar_full = (uint32_t)__cvta_generic_to_shared(s_bar);
+    const uint32_t bar_empty = bar_full + 8u * NBUF;
+    const uint32_t bar_ofull = bar_empty + 8u * NBUF;
+    const uint32_t bar_oempty = bar_ofull + 8u * OB;
+
+    for (int j = tid; j < n_cols; j += THREADS) {
+        const int c = __ldg(act_col + a_begin + j);
+        const int b = (__ldg(act_par + a_begin + j) + substep) & 1;
+        s_src[j] = (long long)b * buf_stride + (long long)c * col_stride;
+        s_dst[j] = (long long)(b ^ 1) * buf_stride + (long long)c * col_stride + t0;
+    }
+    // holes and the zero header of every staging buffer are +0.0 for the whole kernel: the copies
+    // only ever write cells that exist
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(smem_raw);
+        const int n16 = NBUF * img_bytes / 16;
+        for (int i = tid; i < n16; i += THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (tid == 0) {
+        for (int i = 0; i < NBUF; i++) { s_mbar_init(bar_full + 8u * i, 1 + 32); s_mbar_init(bar_empty + 8u * i, CWARPS); }
+        for (int i = 0; i < OB; i++) { s_mbar_init(bar_ofull + 8u * i, CWARPS); s_mbar_init(bar_oempty + 8u * i, 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    s_fence_async();                                       // generic-proxy zero fill before async-proxy copies
+    __syncthreads();
+
+    if (tid >= CTHREADS) {
+        // ======================= producer warp =================================================
+        int bg[BE];
+        uint32_t bs[BE];
+#pragma unroll
+        for (int e = 0; e < BE; e++) {
+            bg[e] = 0; bs[e] = 0;
+            const int i = lane + e * 32;
+            if (i < m0.w) { const int2 d = __ldg(copies + m0.z + i); bg[e] = d.x; bs[e] = (uint32_t)d.y; }
+        }
+        int sg[SE];
+        uint32_t ss[SE];
+#pragma unroll
+        for (int e = 0; e < SE; e++) {
+            const int i = lane + e * 32;
+            sg[e] = -1; ss[e] = 0;
+            if (i < m1.y) { const int2 d = __ldg(copies + m1.x + i); sg[e] = d.x; ss[e] = (uint32_t)d.y * 8u; }
+        }
+        __syncwarp();
+        const int head = t0 & 1;                           // first point sits at an odd global index
+        const int body = (cnt - head) & ~1;
+        auto issue = [&](int c) {
+            const int slot = c % NBUF;
+            if (c >= NBUF) s_mbar_wait(bar_empty + 8u * slot, (uint32_t)((c / NBUF) - 1) & 1u);
+            const double *__restrict__ src = buf + s_src[c];
+            const uint32_t sb = s_base + (uint32_t)slot * (uint32_t)img_bytes;
+            const uint32_t bar = bar_full + 8u * slot;
+            if (lane == 0) s_mbar_expect_tx_arrive(bar, (dbg & 2) ? 0u : (uint32_t)m1.z);
+            __syncwarp();
+#pragma unroll
+            for (int e = 0; e < BE; e++) {
+                const uint32_t n = bs[e] >> 16;
+                if (n && !(dbg & 2)) s_bulk_g2s(sb + (bs[e] & 0xffffu) * 8u, src + bg[e], n * 8u, bar);
+            }
+#pragma unroll
+            for (int e = 0; e < SE; e++)
+                if (sg[e] >= 0 && !(dbg & 8)) s_cp_async_8(sb + ss[e], src + sg[e]);
+            s_cp_async_arrive_noinc(bar);
+        };
+        // Column j is finished when all consumer warps have arrived on out_full[j] (they release the
+        // image slot at the same moment).  First refill the freed slot -- the loads are what the
+        // consumers will wait for -- then start draining the results; the result buffer of column
+        // j-1 is handed back once its store has finished reading shared memory.
+        const int pre = min(NBUF, n_cols);
+        for (int c = 0; c < pre; c++) issue(c);
+        for (int j = 0; j < n_cols; j++) {
+            const int ob_i = j % OB;
+            s_mbar_wait(bar_ofull + 8u * ob_i, (uint32_t)(j / OB) & 1u);
+            if (j + NBUF < n_cols) issue(j + NBUF);
+            double *__restrict__ dst = buf + s_dst[j];
+            const uint32_t ob = out_base + (uint32_t)ob_i * (uint32_t)out_bytes;
+            const double *res = reinterpret_cast<const double *>(smem_raw + (size_t)NBUF * img_bytes + (size_t)ob_i * out_bytes);
+            if (lane == 0) {
+                if (body > 0 && !(dbg & 4)) s_bulk_s2g(dst + head, ob + 16u * head, (uint32_t)body * 8u);
+                s_bulk_commit();
+            }
+            if (lane == 1 && head) dst[0] = res[1];
+            if (lane == 2 && head + body < cnt) dst[cnt - 1] = res[head + cnt - 1];
+            if (j > 0) {
+                if (lane == 0) s_bulk_wait_read<1>();      // the store of column j-1 has drained its buffer
+                __syncwarp();
+                if (lane == 0) s_mbar_arrive(bar_oempty + 8u * ((j - 1) % OB));
+            }
+        }
+        if (lane == 0) s_bulk_wait_read<0>();
+        return;
+    }
+
+    // =========================== consumer warps ================================================
+    // segments: byte offsets of the seven streams inside the image, result cell, length, weights
+    uint32_t so[SPT][7], sout[SPT];
+    int slen[SPT];
+    double sw[SPT][R];
+    uint32_t lo_mask = 0, up_mask = 0;                     // warp-uniform: some lane has A/B resp. E/F
+    const int head = t0 & 1;
+#pragma unroll
+    for (int s = 0; s < SPT; s++) {
+        const int i = tid + s * CTHREADS;
+        uint4 r = make_uint4(1u, 0u, 0u, 0u);              // idle lane: O at cell 1, everything else absent
+        if (i < m2.y) r = __ldg(segs + m2.x + i);
+        so[s][0] = (r.x & 0xffffu) * 8u; so[s][1] = (r.x >> 16) * 8u;
+        so[s][2] = (r.y & 0xffffu) * 8u; so[s][3] = (r.y >> 16) * 8u;
+        so[s][4] = (r.z & 0xffffu) * 8u; so[s][5] = (r.z >> 16) * 8u;
+        so[s][6] = (r.w & 0xffffu) * 8u;
+        sout[s] = ((r.w >> 16) & 0xfffu) * 8u;
+        slen[s] = (int)(r.w >> 28);
+        const int q0 = t0 + (int)((r.w >> 16) & 0xfffu) - head;
+#pragma unroll
+        for (int j = 0; j < R; j++) sw[s][j] = (j < slen[s]) ? __ldg(wout + q0 + j) : 0.0;
+        lo_mask |= (__any_sync(0xffffffffu, (so[s][1] | so[s][2]) != 0u) ? 1u : 0u) << s;
+        up_mask |= (__any_sync(0xffffffffu, (so[s][5] | so[s][6]) != 0u) ? 1u : 0u) << s;
+    }
+    auto s_lds = [](const unsigned char *a) { return *reinterpret_cast<const double *>(a); };
+    auto s_sts = [](unsigned char *a, double v) { *reinterpret_cast<double *>(a) = v; };
+    for (int j = 0; j < n_cols; j++) {
+        const int slot = j % NBUF, ob_i = j % OB;
+        s_mbar_wait(bar_full + 8u * slot, (uint32_t)(j / NBUF) & 1u);
+        const unsigned char *img = smem_raw + (size_t)slot * img_bytes;
+        unsigned char *ob = smem_raw + (size_t)NBUF * img_bytes + (size_t)ob_i * out_bytes;
+        double res[SPT][R];
+#pragma unroll
+        for (int s = 0; s < SPT; s++) {
+            if (dbg & 1) {
+#pragma unroll
+                for (int i = 0; i < R; i++) res[s][i] = sw[s][i];
+                continue;
+            }
+            double o[R + 2], acc[R];
+            {
+                const unsigned char *a = img + so[s][0] - 8u;
+#pragma unroll
+                for (int i = 0; i < R + 2; i++) o[i] = s_lds(a + 8u * i);
+            }
+#pragma unroll
+            for (int i = 0; i < R; i++) acc[i] = 0.0;
+            auto pair_stream = [&](uint32_t off) {
+                double v[R + 1];
+                const unsigned char *a = img + off;
+#pragma unroll
+                for (int i = 0; i < R + 1; i++) v[i] = s_lds(a + 8u * i);
+#pragma unroll
+                for (int i = 0; i < R; i++) acc[i] = __dadd_rn(acc[i], v[i]);
+#pragma unroll
+                for (int i = 0; i < R; i++) acc[i] = __dadd_rn(acc[i], v[i + 1]);
+            };
+            auto single_stream = [&](uint32_t off) {
+                double v[R];
+                const unsigned char *a = img + off;
+#pragma unroll
+                for (int i = 0; i < R; i++) v[i] = s_lds(a + 8u * i);
+#pragma unroll
+                for (int i = 0; i < R; i++) acc[i] = __dadd_rn(acc[i], v[i]);
+            };
+            if ((lo_mask >> s) & 1u) { pair_stream(so[s][1]); pair_stream(so[s][2]); }
+            single_stream(so[s][3]);
+#pragma unroll
+            for (int i = 0; i < R; i++) acc[i] = __dadd_rn(acc[i], o[i]);          // left neighbour
+#pragma unroll
+            for (int i = 0; i < R; i++) acc[i] = __dadd_rn(acc[i], o[i + 2]);      // right neighbour
+            single_stream(so[s][4]);
+            if ((up_mask >> s) & 1u) { pair_stream(so[s][5]); pair_stream(so[s][6]); }
+#pragma unroll
+            for (int i = 0; i < R; i++) {
+                double y = __dmul_rn(acc[i], kBDiv);
+                y = __dsub_rn(y, __dmul_rn(o[i + 1], sw[s][i]));
+                res[s][i] = __dadd_rn(o[i + 1], y);
+            }
+        }
+        if (j >= OB) s_mbar_wait(bar_oempty + 8u * ob_i, (uint32_t)((j / OB) - 1) & 1u);
+#pragma unroll
+        for (int s = 0; s < SPT; s++)
+#pragma unroll
+            for (int i = 0; i < R; i++)
+                if (i < slen[s]) s_sts(ob + sout[s] + 8u * i, res[s][i]);
+        // generic points: twelve explicit slots, records re-read per column (L1 resident)
+        for (int g = tid; g < m2.w; g += CTHREADS) {
+            const uint4 r0 = __ldg(gens + 2 * (m2.z + g)), r1 = __ldg(gens + 2 * (m2.z + g) + 1);
+            const uint32_t c[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                acc = __dadd_rn(acc, s_lds(img + (c[k] & 0xffffu) * 8u));
+                acc = __dadd_rn(acc, s_lds(img + (c[k] >> 16) * 8u));
+            }
+            const double cq = s_lds(img + (c[6] & 0xffffu) * 8u);
+            const uint32_t oc = c[6] >> 16;
+            double y = __dmul_rn(acc, kBDiv);
+            y = __dsub_rn(y, __dmul_rn(cq, __ldg(wout + t0 + (int)oc - head)));
+            s_sts(ob + oc * 8u, __dadd_rn(cq, y));
+        }
+        s_fence_async();        // results (generic proxy) before the producer's bulk store (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+            s_mbar_arrive(bar_empty + 8u * slot);          // this warp is done reading the image slot
+            s_mbar_arrive(bar_ofull + 8u * ob_i);          // ... and its results of column j are in the buffer
+        }
+    }
+}
+
+template <int R, int SPT, int CWARPS, int NBUF, int OB, int MINB>
+static int launch_seg_t(eut_field *f, int n_act, int substep)
+{
+    const eut_plan *p = f->plan;
+    const SegPlanHost &S = p->segs;
+    if (S.R != R || S.max_tile_segs > SPT * CWARPS * 32 || S.max_bulk > 128 || S.max_single > 512) {
+        set_error("segment kernel: plan has R=%d, %d segments per tile; kernel shape is R=%d, %d", S.R,
+                  S.max_tile_segs, R, SPT * CWARPS * 32);
+        return EUT_ERR_UNSUPPORTED;
+    }
+    const int img_bytes = ((S.img_points * 8 + 127) / 128) * 128;
+    const int out_bytes = (((S.max_tile_points + 2) * 8 + 127) / 128) * 128;
+    const size_t smem = (size_t)NBUF * img_bytes + (size_t)OB * out_bytes;
+    if (smem > 220 * 1024) {
+        set_error("segment kernel: %zu bytes of shared memory per CTA", smem);
+        return EUT_ERR_UNSUPPORTED;
+    }
+    int slices = 1;
+    const int64_t want = 4ll * 148 * MINB;
+    while ((int64_t)p->n_tiles * slices < want && slices < n_act) slices++;
+    if (f->opt_cpt > 0) slices = (n_act + f->opt_cpt - 1) / f->opt_cpt;
+    slices = std::max(slices, (n_act + kTileMaxCols - 1) / kTileMaxCols);
+    const int cols_per_cta = (n_act + slices - 1) / slices;
+    dim3 grid((unsigned)p->n_tiles, (unsigned)((n_act + cols_per_cta - 1) / cols_per_cta), 1);
+    auto kern = k_substep_seg<R, SPT, CWARPS, NBUF, OB, MINB>;
+    static bool attr_set[64] = {false};
+    if (!attr_set[p->device & 63]) {
+        EUT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr_set[p->device & 63] = true;
+    }
+    kern<<<grid, (CWARPS + 1) * 32, smem, f->stream>>>(f->d_buf, p->Np, f->C * p->Np, p->d_seg_meta, p->d_copies,
+                                                       p->d_segs, p->d_gens, p->d_w, f->d_act, f->d_act + f->act_cap,
+                                                       n_act, substep, img_bytes, out_bytes, cols_per_cta, f->opt_debug);
+    return EUT_OK;
+}
+
+// Kernel shapes: (R, segments per thread, consumer warps, image slots, result buffers, CTAs per SM).
+// The plan's tile capacity (EUT_SEG_TILE, default 224 segments) picks the shape.
+int launch_seg(eut_field *f, int n_act, int substep)
+{
+    const SegPlanHost &S = f->plan->segs;
+    const int nb = f->opt_nbuf == 2 ? 2 : (f->opt_nbuf == 4 ? 4 : 3);
+    const int shape = f->opt_shape;
+    if (S.R == 7) {
+        if (S.max_tile_segs <= 224) {
+            if (shape == 1) return launch_seg_t<7, 1, 7, 3, 2, 2>(f, n_act, substep);
+            if (nb == 2) return launch_seg_t<7, 1, 7, 2, 2, 2>(f, n_act, substep);
+            if (nb == 4) return launch_seg_t<7, 1, 7, 4, 2, 2>(f, n_act, substep);
+            return launch_seg_t<7, 1, 7, 3, 3, 2>(f, n_act, substep);
+        }
+        if (S.max_tile_segs <= 448) {
+            if (shape == 1) return launch_seg_t<7, 1, 14, 3, 2, 1>(f, n_act, substep);
+            if (nb == 2) return launch_seg_t<7, 2, 7, 2, 2, 1>(f, n_act, substep);
+            return launch_seg_t<7, 2, 7, 3, 2, 1>(f, n_act, substep);
+        }
+    }
+    if (S.R == 5 && S.max_tile_segs <= 224) return launch_seg_t<5, 1, 7, 3, 2, 2>(f, n_act, substep);
+    if (S.R == 9 && S.max_tile_segs <= 224) return launch_seg_t<9, 1, 7, 3, 2, 2>(f, n_act, substep);
+    set_error("segment kernel: no compiled shape for R=%d with %d segments per tile", S.R, S.max_tile_segs);
+    return EUT_ERR_UNSUPPORTED;
+}
+
+}  // namespace eut

@@ -51,74 +51,11 @@ int build_tiles(eut_plan *p, const TileParams &tp)
     T = TilePlanHost();
     if (N == 0) return EUT_ERR_UNSUPPORTED;
 
-    // ---- 1. rows ------------------------------------------------------------------------------
-    auto has_in = [&](int64_t dst, int32_t src) {
-        for (int64_t k = p->row_ptr[dst]; k < p->row_ptr[dst + 1]; k++)
-            if (p->col[k] == src) return true;
-        return false;
-    };
-    std::vector<int32_t> row_of(N);
-    std::vector<int32_t> row_start;
-    for (int64_t i = 0; i < N; i++) {
-        const bool linked = i > 0 && has_in(i, (int32_t)(i - 1)) && has_in(i - 1, (int32_t)i);
-        if (!linked) row_start.push_back((int32_t)i);
-        row_of[i] = (int32_t)row_start.size() - 1;
-    }
-    const int32_t R = (int32_t)row_start.size();
-    row_start.push_back((int32_t)N);
-
-    // ---- 2. row adjacency with alignment offsets, BFS -> level, column origin ------------------
-    std::vector<int64_t> adj_ptr(R + 1, 0);
-    std::vector<int32_t> adj_row, adj_delta;
-    {
-        std::vector<std::pair<int32_t, int32_t>> local;
-        for (int32_t r = 0; r < R; r++) {
-            local.clear();
-            for (int32_t i = row_start[r]; i < row_start[r + 1]; i++) {
-                const int32_t ki = i - row_start[r];
-                for (int64_t k = p->row_ptr[i]; k < p->row_ptr[i + 1]; k++) {
-                    const int32_t j = p->col[k];
-                    const int32_t rj = row_of[j];
-                    if (rj == r) continue;
-                    const int32_t delta = (j - row_start[rj]) - ki;
-                    bool found = false;
-                    for (auto &e : local)
-                        if (e.first == rj) { e.second = std::min(e.second, delta); found = true; break; }
-                    if (!found) local.emplace_back(rj, delta);
-                }
-            }
-            std::sort(local.begin(), local.end());
-            for (auto &e : local) { adj_row.push_back(e.first); adj_delta.push_back(e.second); }
-            adj_ptr[r + 1] = (int64_t)adj_row.size();
-        }
-    }
-    std::vector<int32_t> level(R, -1), xs(R, 0);
-    int32_t xmin = 0;
-    {
-        std::vector<int32_t> queue;
-        queue.reserve(R);
-        int32_t level_base = 0;   // components are stacked along the level axis
-        for (int32_t seed = 0; seed < R; seed++) {
-            if (level[seed] >= 0) continue;
-            size_t head = queue.size();
-            level[seed] = level_base; xs[seed] = 0;
-            queue.push_back(seed);
-            int32_t maxl = level_base;
-            while (head < queue.size()) {
-                const int32_t r = queue[head++];
-                maxl = std::max(maxl, level[r]);
-                xmin = std::min(xmin, xs[r]);
-                for (int64_t a = adj_ptr[r]; a < adj_ptr[r + 1]; a++) {
-                    const int32_t rr = adj_row[a];
-                    if (level[rr] >= 0) continue;
-                    level[rr] = level[r] + 1;
-                    xs[rr] = xs[r] - adj_delta[a];   // neighbour at k_other = k_own + delta shares u
-                    queue.push_back(rr);
-                }
-            }
-            level_base = maxl + 2;
-        }
-    }
+    // ---- 1./2. rows, row adjacency, levels and column origins (rows.cu) -------------------------
+    RowAnalysis ra;
+    analyse_rows(p, ra);
+    const std::vector<int32_t> &row_start = ra.row_start, &level = ra.level, &xs = ra.xs;
+    const int32_t R = ra.n_rows, xmin = ra.xmin;
 
     // ---- 3. pieces, strips, tiles -------------------------------------------------------------
     const int X = std::max(2, tp.tile_cols);

@@ -110,6 +110,8 @@ enum {                       /* eut_plan_create flags */
     EUT_ORDER_IDENTITY  = 1, /* keep the reference's (layer-major) order */
     EUT_ORDER_ROWBLOCK  = 2, /* whole raster rows reordered breadth-first over the row graph */
     EUT_ORDER_TILED     = 3, /* compact 3-D tiles derived from the graph + shared-memory kernel */
+    EUT_ORDER_SEGMENTS  = 4, /* tiles of row segments: register reuse along the raster row (the
+                                default when the graph qualifies; falls back to TILED, ROWBLOCK) */
     EUT_ORDER_MASK      = 0xf,
     EUT_PLAN_FORCE_GENERIC = 0x10, /* use the generic CSR kernel even when the fast path applies */
     EUT_PLAN_HOST_ONLY = 0x20      /* run the host analysis only (no CUDA calls): for inspecting the
@@ -135,6 +137,13 @@ typedef struct eut_plan_info {
     int32_t max_single;      /* most single 8-byte copies of any tile */
     int32_t n_copies;        /* entries in the copy table */
     double  halo_ratio;      /* halo points / own points, summed over tiles (tiled) */
+    int32_t segmented;       /* 1: the row-segment kernel is available (EUT_ORDER_SEGMENTS) */
+    int32_t seg_points;      /* R: points per full segment */
+    int32_t max_tile_segs;   /* most segments of any tile */
+    int32_t max_tile_generic;/* most generic (twelve explicit slots) points of any tile */
+    int64_t n_segments;
+    int64_t n_generic;       /* points that failed the canonical-order check */
+    int64_t n_seg_covered;   /* points covered by segments (= N - n_generic) */
 } eut_plan_info;
 
 EUT_API int eut_plan_create(eut_plan **out,
@@ -155,6 +164,18 @@ EUT_API int eut_plan_get_csr(const eut_plan *plan, int64_t *row_ptr, int32_t *co
  * Any pointer may be NULL. */
 EUT_API int eut_plan_get_tiles(const eut_plan *plan, int32_t *tile_meta, int32_t *copies,
                                uint16_t *loc);
+/* Segment tables of a EUT_PLAN_HOST_ONLY plan built with EUT_ORDER_SEGMENTS (segs.cu):
+ *   seg_meta[12*n_tiles]  per tile: first internal id, points, first bulk copy, #bulk, first single
+ *                         copy, #single, bulk bytes, image cells, first segment, #segments, first
+ *                         generic point, #generic
+ *   copies[2*n_copies]    as eut_plan_get_tiles
+ *   segs[8*n_segments]    image cell of the first value of the streams O, A, B, C, D, E, F
+ *                         (0 = absent), result cell | length << 12
+ *   gens[16*n_generic]    image cells of the 12 neighbour slots (0 = unused), own cell, result
+ *                         cell, 0, 0
+ * Any pointer may be NULL. */
+EUT_API int eut_plan_get_segs(const eut_plan *plan, int32_t *seg_meta, int32_t *copies,
+                              uint16_t *segs, uint16_t *gens);
 /* Internal position (0-based) of every reference point id: perm[N]. */
 EUT_API int eut_plan_get_perm(const eut_plan *plan, int32_t *perm);
 

@@ -1,0 +1,138 @@
+"""CPU suite: the segment planner (eutropia_b200/csrc/segs.cu) through a host-only plan.  The tables
+the segment kernel consumes are replayed in numpy: every tile's shared-memory image is assembled from
+its copy lists (holes stay +0.0), every segment's R summation chains are evaluated in the kernel's
+canonical stream order, and the result must equal -- bit for bit -- the sum over the point's mat.in
+neighbours in mat.in order.  Every point must be produced exactly once."""
+import numpy as np
+import pytest
+
+import eutropia_b200 as eb
+from eutropia_b200 import _lib, mesh
+
+
+def reference_inflow(m, value):
+    """Sequential fp64 sum of value[from] per destination in mat.in row order (src/diffChange.cpp:19-21)."""
+    n = m.nfields
+    to = m.mat_in[:, 1].astype(np.int64) - 1
+    order = np.argsort(to, kind="stable")
+    frm = (m.mat_in[:, 0].astype(np.int64) - 1)[order]
+    deg = np.bincount(to, minlength=n)
+    row_ptr = np.concatenate([[0], np.cumsum(deg)])
+    acc = np.zeros(n)
+    for k in range(int(deg.max())):
+        has = deg > k
+        acc[has] = acc[has] + value[frm[row_ptr[:-1][has] + k]]
+    return acc
+
+
+def replay(m, plan, check_alignment=True):
+    inf = plan.info
+    assert inf.segmented == 1
+    n, R = m.nfields, inf.seg_points
+    perm = plan.perm()
+    assert np.array_equal(np.sort(perm), np.arange(n))
+    meta, copies, segs, gens = plan.segs()
+    assert meta[0, 0] == 0 and np.array_equal(meta[1:, 0], np.cumsum(meta[:-1, 1])) and meta[:, 1].sum() == n
+    assert meta[:, 3].max() <= 128 and meta[:, 5].max() <= 512 and meta[:, 9].max() <= 512
+    value = np.random.default_rng(0).uniform(1, 2, n)     # by reference id; sums depend on the order
+    want = reference_inflow(m, value)
+    iperm = np.empty(n, dtype=np.int64); iperm[perm] = np.arange(n)
+    vq = value[iperm]                                     # by internal position
+    got = np.full(n, np.nan)
+    produced = np.zeros(n, dtype=np.int64)
+    for t in range(meta.shape[0]):
+        t0, cnt, b0, nb, s0, ns, tx, img, g0, ng, x0, nx = meta[t]
+        image = np.zeros(img + 1)
+        filled = np.zeros(img + 1, dtype=bool)
+        moved = 0
+        for g, y in copies[b0:b0 + nb]:
+            so, npts = y & 0xffff, y >> 16
+            if check_alignment:
+                assert g % 2 == 0 and so % 2 == 0 and npts % 2 == 0 and npts > 0   # 16-byte rule of cp.async.bulk
+            assert not filled[so:so + npts].any()
+            image[so:so + npts] = vq[g:g + npts]; filled[so:so + npts] = True
+            moved += 8 * npts
+        assert moved == tx
+        for g, so in copies[s0:s0 + ns]:
+            assert not filled[so]
+            image[so] = vq[g]; filled[so] = True
+        assert not filled[:inf.seg_points + 3].any()          # the zero header
+        head = t0 & 1
+        S = segs[g0:g0 + ng].astype(np.int64)
+        if ng:
+            ln = S[:, 7] >> 12
+            out = S[:, 7] & 0xfff
+            assert ln.min() >= 1 and ln.max() <= R
+            for j in range(R):
+                on = j < ln
+                a = S[on]
+                acc = np.zeros(a.shape[0])
+                for col, extra in ((1, 0), (1, 1), (2, 0), (2, 1), (3, 0)):       # A A B B C
+                    acc = acc + image[a[:, col] + j + extra]
+                acc = acc + image[a[:, 0] + j - 1]                                   # left
+                acc = acc + image[a[:, 0] + j + 1]                                   # right
+                for col, extra in ((4, 0), (5, 0), (5, 1), (6, 0), (6, 1)):       # D E E F F
+                    acc = acc + image[a[:, col] + j + extra]
+                q = t0 + out[on] + j - head
+                assert np.array_equal(image[a[:, 0] + j], vq[q])                   # own value where the kernel reads it
+                got[q] = acc
+                np.add.at(produced, q, 1)
+        G = gens[x0:x0 + nx].astype(np.int64)
+        if nx:
+            acc = np.zeros(nx)
+            for k in range(12):
+                acc = acc + image[G[:, k]]
+            q = t0 + G[:, 13] - head
+            assert np.array_equal(image[G[:, 12]], vq[q])
+            got[q] = acc
+            np.add.at(produced, q, 1)
+        assert produced[t0:t0 + cnt].min() == 1 and produced[t0:t0 + cnt].max() == 1
+    assert np.array_equal(got, want[iperm])                # bit-exact, mat.in order
+    return inf
+
+
+@pytest.mark.parametrize("name,layers", [("Rectangle_40_33", 3), ("Petri_23", 6), ("harbor", 4),
+                                         ("Rectangle_70_12", 1), ("Rectangle_11_10", 2), ("Petri_60", 3)])
+def test_segment_tables_replay(name, layers):
+    poly = mesh.harbor_polygon(90.0) if name == "harbor" else name
+    m = mesh.make_mesh(poly, 1.0, layers)
+    plan = eb.Plan(m.mat_in, m.mat_out, order=_lib.ORDER_SEGMENTS, host_only=True)
+    inf = replay(m, plan)
+    assert inf.n_seg_covered + inf.n_generic == m.nfields
+    assert inf.n_generic <= 0.02 * m.nfields + 8          # the lattice is regular up to its border
+
+
+def test_segments_fill_up_on_large_mesh():
+    m = mesh.make_mesh("Rectangle_300_300", 1.0, 3)
+    plan = eb.Plan(m.mat_in, m.mat_out, order=_lib.ORDER_SEGMENTS, host_only=True)
+    inf = plan.info
+    meta, _, _, _ = plan.segs()
+    assert inf.segmented == 1 and inf.n_generic == 0
+    assert inf.n_seg_covered / (inf.n_segments * inf.seg_points) > 0.9     # segments are mostly full
+    assert np.median(meta[:, 9]) > 0.8 * 224                                 # tiles are close to capacity
+    assert inf.halo_ratio < 0.5
+
+
+def test_shuffled_ids_still_exact():
+    """A renumbered mesh is no longer raster ordered: rows are short or absent, most points become
+    generic -- the tables must stay exact (or the planner declines)."""
+    m = mesh.make_mesh("Rectangle_20_14", 1.0, 3)
+    n = m.nfields
+    rng = np.random.default_rng(4)
+    relabel = np.arange(1, n + 1)
+    blocks = relabel.reshape(-1, 1) if n % 7 else relabel.reshape(-1, 7)
+    blocks = blocks[rng.permutation(blocks.shape[0])]
+    relabel = np.empty(n, dtype=np.int64); relabel[blocks.reshape(-1) - 1] = np.arange(1, n + 1)
+    mat_in = np.stack([relabel[m.mat_in[:, 0] - 1], relabel[m.mat_in[:, 1] - 1]], axis=1)
+    srt = np.lexsort((mat_in[:, 0], mat_in[:, 1]))
+    mat_in = mat_in[srt].astype(np.int32)
+    mat_out = np.stack([np.arange(1, n + 1), np.bincount(mat_in[:, 0], minlength=n + 1)[1:] + 1], axis=1).astype(np.int32)
+
+    class M:
+        pass
+    mm = M(); mm.nfields = n; mm.mat_in = mat_in; mm.mat_out = mat_out
+    plan = eb.Plan(mat_in, mat_out, order=_lib.ORDER_SEGMENTS, host_only=True)
+    if plan.info.segmented:
+        replay(mm, plan, check_alignment=True)
+    else:
+        assert plan.info.order in (_lib.ORDER_TILED, _lib.ORDER_ROWBLOCK)

@@ -45,7 +45,7 @@ def _worker(rank, world, port, outdir, backend_name):
         ref = oracle.diffChangePar(m.mat_in, m.mat_out, conc, niter, indvar, 2)
         own_global = part.local_global[part.own_local]
         np.savez(os.path.join(outdir, f"r{rank}.npz"), ok=np.array_equal(own, ref[own_global]),
-                 tiled=int(be.plan.info.tiled), n_own=own_global.size)
+                 tiled=int(be.plan.info.tiled or be.plan.info.segmented), n_own=own_global.size)
         be.close()
     finally:
         dist.destroy_process_group()

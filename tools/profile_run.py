@@ -40,6 +40,6 @@ if any(k == "cells" for k, _ in opts):
     field.sync()
 print("done", mesh.nfields, cols, substeps, field.launch_count)
 inf = plan.info
-print("plan: order", inf.order, "tiled", inf.tiled, "tiles", inf.n_tiles, "img_points", inf.img_points,
+print("plan: order", inf.order, "tiled", inf.tiled, "segmented", inf.segmented, "segs", inf.n_segments, "generic", inf.n_generic, "tiles", inf.n_tiles, "img_points", inf.img_points,
       "max_tile", inf.max_tile_points, "max_bulk", inf.max_bulk, "max_single", inf.max_single, "halo_ratio %.3f" % inf.halo_ratio,
       "build_ms %.0f" % inf.build_ms, "graph MB %.1f" % (inf.device_bytes / 2**20))
