@@ -91,9 +91,10 @@ struct SegParams {
     int band_levels = 16;
     int max_tile_segs = 224;     // consumer threads per CTA x segments per thread of the kernel
     int max_tile_points = 4000;  // 12-bit offsets into the tile's result buffer
-    int max_img_points = 8192;   // shared-memory image limit (cells) per buffer
+    int max_img_points = 8190;   // shared-memory image limit (cells) per buffer: 16-bit byte offsets
     int max_bulk = 128;          // bulk copies per tile the kernel can hold (4 per lane of warp 0)
     int max_single = 512;        // single 8-byte copies per tile
+    int pad_rows = 1;            // pad ragged row pieces in storage to 8 (mod 16) cells
 };
 struct SegPlanHost {
     std::vector<int32_t> tile_start;  // [n_tiles+1] internal ids
@@ -101,8 +102,11 @@ struct SegPlanHost {
     // moved by the bulk copies, image cells, first segment, #segments, first generic point, #generic
     std::vector<int32_t> meta;
     std::vector<int2> copies;         // as TilePlanHost::copies
-    // per segment 8 x uint16: image cell of the first value of the streams O, A, B, C, D, E, F
-    // (0 = absent stream: the zero header), then result-buffer cell | length << 12
+    // per segment 24 x uint16 (byte offsets inside the image; 0 = zero header):
+    //   [0..6]  first in-line cell of the streams O, A, B, C, D, E, F (pair streams: cell 0's slot)
+    //   [7]     result-buffer cell | length << 12
+    //   [8,9]   left / right neighbour of the segment in its own row
+    //   [10..17] first / last cell of the pair streams A, B, E, F
     std::vector<uint16_t> segs;
     // per generic point 16 x uint16: image cells of the 12 neighbour slots (0 = unused), own image
     // cell, result-buffer cell, 0, 0
@@ -123,7 +127,7 @@ struct eut_plan {
     bool tiled = false;
     bool segmented = false;      // segs (not tiles) describes the tiles; kernel: stencil_seg.cu
     int32_t *d_seg_meta = nullptr;
-    uint4 *d_segs = nullptr;     // one per segment
+    uint4 *d_segs = nullptr;     // three per segment
     uint4 *d_gens = nullptr;     // two per generic point
     bool host_only = false;
     int32_t *d_tile_meta = nullptr;

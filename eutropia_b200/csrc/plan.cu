@@ -260,6 +260,7 @@ int plan_build(eut_plan *p, const int32_t *from, const int32_t *to, int64_t n_ed
         if (const char *e = getenv("EUT_SEG_COLS")) sp.tile_cols = atoi(e);
         if (const char *e = getenv("EUT_SEG_TILE")) sp.max_tile_segs = std::min(448, std::max(8, atoi(e)));
         if (const char *e = getenv("EUT_TILE_BAND")) sp.band_levels = atoi(e);
+        if (const char *e = getenv("EUT_SEG_PAD")) sp.pad_rows = atoi(e);
         if (build_segs(p, sp) == EUT_OK) p->segmented = true;
         else order = EUT_ORDER_TILED;      // not lattice-like enough / tiles too large: first tiled kernel
     } else if (order == EUT_ORDER_SEGMENTS) order = EUT_ORDER_ROWBLOCK;
@@ -321,7 +322,7 @@ int plan_build(eut_plan *p, const int32_t *from, const int32_t *to, int64_t n_ed
             SegPlanHost &S = p->segs;
             EUT_TRY(upload(&p->d_seg_meta, S.meta, &p->device_bytes));
             EUT_TRY(upload(&p->d_copies, S.copies, &p->device_bytes));
-            std::vector<uint4> tmp(S.segs.size() / 8);
+            std::vector<uint4> tmp(S.segs.size() / 8);   // 24 x uint16 = 3 x uint4 per segment
             if (!tmp.empty()) memcpy(tmp.data(), S.segs.data(), S.segs.size() * sizeof(uint16_t));
             EUT_TRY(upload(&p->d_segs, tmp, &p->device_bytes));
             tmp.assign(S.gens.size() / 8, make_uint4(0, 0, 0, 0));

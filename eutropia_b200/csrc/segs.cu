@@ -16,13 +16,16 @@
 // Nothing here assumes the geometry.  The streams of a segment are guessed from the row analysis
 // (rows.cu) and then VERIFIED point by point: the canonical cell sequence, restricted to cells that
 // exist as points, must equal the point's mat.in neighbour list exactly (same ids, same order).
-// Cells that do not exist (polygon boundary, ragged row ends) are holes of the shared-memory image
-// and stay +0.0; adding +0.0 to a chain that started at +0.0 is exact, so border points are regular
-// too.  Points that fail the check alone are "generic" points and keep twelve explicit slots.
+// Cells that do not exist (polygon boundary, ragged row ends) read the zero header of the image;
+// adding +0.0 to a chain that started at +0.0 is exact, so border points are regular too.  Points
+// that fail alone are "generic" points and keep twelve explicit slots.
 //
-// Per tile the image is [zero header | one image row per touched graph row, covering every cell a
-// canonical read can touch]; the copy lists move the existing cells (bulk copies for 16-byte
-// aligned runs of consecutive internal ids, 8-byte copies for odd ends and apron cells).
+// Per tile the shared-memory image is [zero header | the tile's own points, dense, in internal order
+// | halo runs | lone halo points].  Internal order inside a tile is level by level, so a tile's own
+// block is ONE bulk copy and the rows it needs from the neighbouring tiles of its strip are a few
+// contiguous runs (the copy count, not the bytes, bounds the producer warp: ~60 cycles per
+// cp.async.bulk).  A stream must be contiguous in this image except for its two end cells -- the
+// left / right neighbours of a row piece live in the next tile column -- which get explicit offsets.
 #include <algorithm>
 #include <numeric>
 
@@ -33,7 +36,6 @@ namespace eut {
 namespace {
 struct Piece {
     int32_t ucol, level, first, count, strip;
-    int32_t seg0, nseg, gen0, ngen;     // ranges in the global segment / generic lists
 };
 struct Dsu {
     std::vector<int32_t> p;
@@ -46,11 +48,6 @@ struct Pattern {
     int32_t row[NSTREAM];
     int32_t sh[NSTREAM];      // u of the stream's first cell minus u of the point
 };
-struct Seg {
-    int32_t first, len;       // reference id of the first point
-    Pattern pat;
-};
-struct RowWin { int32_t row, lo, hi, base; };
 }  // namespace
 
 int build_segs(eut_plan *p, const SegParams &sp)
@@ -83,7 +80,7 @@ int build_segs(eut_plan *p, const SegParams &sp)
             }
             if (len - kend > 0 && len - kend < X / 2) kend = len;
             for (int32_t i = k; i < kend; i++) piece_of[ra.row_start[r] + i] = (int32_t)pieces.size();
-            pieces.push_back({ucol, ra.level[r], ra.row_start[r] + k, kend - k, 0, 0, 0, 0, 0});
+            pieces.push_back({ucol, ra.level[r], ra.row_start[r] + k, kend - k, 0});
             k = kend;
         }
     }
@@ -167,33 +164,6 @@ int build_segs(eut_plan *p, const SegParams &sp)
             if (p->col[p->row_ptr[i] + k] != want[k]) return false;
         return true;
     };
-    std::vector<Seg> segs;
-    std::vector<int32_t> gens;
-    segs.reserve((size_t)(N / R + P));
-    for (int32_t a = 0; a < P; a++) {
-        Piece &pc = pieces[a];
-        pc.seg0 = (int32_t)segs.size(); pc.gen0 = (int32_t)gens.size();
-        int32_t i = pc.first;
-        const int32_t end = pc.first + pc.count;
-        while (i < end) {
-            Pattern pat, best;
-            int32_t len = 0;
-            while (len < R && i + len < end) {
-                if (len > 0 && check_point(i + len, best)) { len++; continue; }
-                // first point, or a point that brings a row the pattern does not have yet: refine
-                if (!derive(i, len + 1, pat)) break;
-                bool ok = true;
-                for (int32_t j = 0; j <= len && ok; j++) ok = check_point(i + j, pat);
-                if (!ok) break;
-                best = pat;
-                len++;
-            }
-            if (len == 0) { gens.push_back(i); i++; }
-            else { segs.push_back({i, len, best}); i += len; }
-        }
-        pc.nseg = (int32_t)segs.size() - pc.seg0; pc.ngen = (int32_t)gens.size() - pc.gen0;
-    }
-
     // ---- order pieces, cut strips into tiles ----------------------------------------------------
     std::vector<int32_t> strip_minlevel(P, INT32_MAX);
     for (int32_t a = 0; a < P; a++)
@@ -212,19 +182,22 @@ int build_segs(eut_plan *p, const SegParams &sp)
         if (A.level != B.level) return A.level < B.level;
         return A.first < B.first;
     });
-    auto units = [](const Piece &pc) { return pc.nseg + (pc.ngen + 1) / 2; };
+    // capacity is counted in lanes: a piece of n points needs about ceil(n / R) segments (ragged
+    // pieces a few more; the overflow becomes generic points below)
+    auto units = [&](const Piece &pc) { return (pc.count + R - 1) / R; };
+    // capacity in points is checked against an upper bound of the stored length (see below)
+    auto stored = [&](int32_t count) { return sp.pad_rows ? count + 15 : count; };
     p->perm.assign(N, 0);
     std::vector<int32_t> tile_piece0;    // index into ord of every tile's first piece
-    S.tile_start.clear();
     {
-        int32_t pos = 0, in_units = 0, in_pts = 0, cur_strip = -1;
+        int32_t in_units = 0, in_pts = 0, cur_strip = -1;
         size_t i = 0;
-        auto open_tile = [&](size_t at) { S.tile_start.push_back(pos); tile_piece0.push_back((int32_t)at); in_units = 0; in_pts = 0; };
+        auto open_tile = [&](size_t at) { tile_piece0.push_back((int32_t)at); in_units = 0; in_pts = 0; };
         while (i < ord.size()) {
             size_t e = i;
             int32_t gunits = 0, gpts = 0;
             while (e < ord.size() && pieces[ord[e]].strip == pieces[ord[i]].strip &&
-                   pieces[ord[e]].level == pieces[ord[i]].level) { gunits += units(pieces[ord[e]]); gpts += pieces[ord[e]].count; e++; }
+                   pieces[ord[e]].level == pieces[ord[i]].level) { gunits += units(pieces[ord[e]]); gpts += stored(pieces[ord[e]].count); e++; }
             if (pieces[ord[i]].strip != cur_strip || in_units + gunits > sp.max_tile_segs ||
                 in_pts + gpts > sp.max_tile_points) {
                 open_tile(i);
@@ -232,48 +205,78 @@ int build_segs(eut_plan *p, const SegParams &sp)
             }
             for (size_t k = i; k < e; k++) {
                 const Piece &pc = pieces[ord[k]];
-                if (in_pts > 0 && (in_units + units(pc) > sp.max_tile_segs || in_pts + pc.count > sp.max_tile_points))
+                if (in_pts > 0 && (in_units + units(pc) > sp.max_tile_segs || in_pts + stored(pc.count) > sp.max_tile_points))
                     open_tile(k);
-                if (units(pc) > sp.max_tile_segs || pc.count > sp.max_tile_points) return EUT_ERR_UNSUPPORTED;
-                pos += pc.count; in_pts += pc.count; in_units += units(pc);
+                if (units(pc) > sp.max_tile_segs || stored(pc.count) > sp.max_tile_points) return EUT_ERR_UNSUPPORTED;
+                in_pts += stored(pc.count); in_units += units(pc);
             }
             i = e;
         }
-        S.tile_start.push_back(pos);
         tile_piece0.push_back((int32_t)ord.size());
     }
-    const int32_t n_tiles = (int32_t)S.tile_start.size() - 1;
-    // Inside a tile the pieces -- and with them the internal ids, the segments and the lanes that
-    // run them -- follow the reference id: layer by layer, row by row.  Consecutive lanes then hold
-    // consecutive segments of a row and consecutive rows of a layer (the bank rule below relies on
-    // it), and warps are uniform in their stream set except where a layer ends.
-    for (int32_t t = 0; t < n_tiles; t++) {
-        std::sort(ord.begin() + tile_piece0[t], ord.begin() + tile_piece0[t + 1],
-                  [&](int32_t a, int32_t b) { return pieces[a].first < pieces[b].first; });
-        int32_t pos = S.tile_start[t];
-        for (int32_t k = tile_piece0[t]; k < tile_piece0[t + 1]; k++) {
-            const Piece &pc = pieces[ord[k]];
-            for (int32_t q = 0; q < pc.count; q++) p->perm[pc.first + q] = pos + q;
-            pos += pc.count;
+    const int32_t n_tiles = (int32_t)tile_piece0.size() - 1;
+    // Storage inside a tile.  Pieces follow the reference order (layer by layer, row by row), so the
+    // rows a segment's streams read are a fixed number of pieces away from its own row: the previous
+    // / next piece for C / D, a constant piece count for the other layers.  The own block of a tile
+    // is dense in the image, so cell(row k, column u) = base_k + (u - ustart_k).  If
+    //     rho_k = (base_k - ustart_k) mod 16   advances by the same step s from piece to piece,
+    // all seven streams of every segment move together mod 16 and half warps can be packed without
+    // bank conflicts (lane assignment below).  Regular tiles have this for free (equal ustart, 56
+    // cells per piece: s = 8).  Ragged tiles (polygon border: rows start and end anywhere) get gap
+    // cells after each piece, 0..15 of them, and the step s that needs the fewest.  Gap cells are
+    // never read as neighbours, hold 0, and cost their share of HBM traffic (n_padded vs n_points).
+    S.tile_start.assign(1, 0);
+    {
+        int32_t pos = 0;
+        std::vector<int32_t> gap;
+        for (int32_t t = 0; t < n_tiles; t++) {
+            std::sort(ord.begin() + tile_piece0[t], ord.begin() + tile_piece0[t + 1],
+                      [&](int32_t a, int32_t b) { return pieces[a].first < pieces[b].first; });
+            const int32_t k0 = tile_piece0[t], k1 = tile_piece0[t + 1];
+            gap.assign(k1 - k0, 0);
+            if (sp.pad_rows && k1 - k0 > 1) {
+                int64_t best_total = INT64_MAX;
+                int best_s = 8;
+                for (int s = 1; s < 16; s++) {
+                    int64_t total = 0;
+                    for (int32_t k = k0; k + 1 < k1; k++) {
+                        const Piece &a = pieces[ord[k]], &b = pieces[ord[k + 1]];
+                        total += (((s + u_of(b.first) - u_of(a.first) - a.count) % 16) + 16) % 16;
+                    }
+                    if (total < best_total || (total == best_total && s == 8)) { best_total = total; best_s = s; }
+                }
+                for (int32_t k = k0; k + 1 < k1; k++) {
+                    const Piece &a = pieces[ord[k]], &b = pieces[ord[k + 1]];
+                    gap[k - k0] = (((best_s + u_of(b.first) - u_of(a.first) - a.count) % 16) + 16) % 16;
+                }
+            }
+            for (int32_t k = k0; k < k1; k++) {
+                const Piece &pc = pieces[ord[k]];
+                for (int32_t q = 0; q < pc.count; q++) p->perm[pc.first + q] = pos + q;
+                pos += pc.count + gap[k - k0];
+            }
+            S.tile_start.push_back(pos);
         }
     }
-    p->Np = ((N + kPadPoints - 1) / kPadPoints) * kPadPoints;
+    p->Np = (((int64_t)S.tile_start.back() + kPadPoints - 1) / kPadPoints) * kPadPoints;
     p->iperm.assign(p->Np, -1);
     for (int64_t i = 0; i < N; i++) p->iperm[p->perm[i]] = (int32_t)i;
 
-    // ---- per tile: image rows, copy lists, segment and generic records ---------------------------
-    const int ZH = (R + 3 + 1) & ~1;           // zero header: absent streams and idle lanes read it
+    // ---- per tile: image, copy lists, segments ----------------------------------------------------
+    // image = [zero header | own points, dense, in internal order (ONE bulk copy) | halo runs: maximal
+    // runs of consecutive internal ids among the in-neighbours outside the tile, small gaps filled
+    // (bulk copies) | lone halo points (8-byte copies)].  Everything a stream reads must be contiguous
+    // in this image except the two end cells of the O and pair streams, which get explicit offsets
+    // (the row ends: their neighbours belong to the next tile column, or do not exist -> zero cell).
+    const int ZH = (R + 3 + 1) & ~1;
     S.R = R; S.zero_cells = ZH;
     S.meta.assign((size_t)n_tiles * 12, 0);
-    S.segs.reserve(segs.size() * 8);
-    S.gens.reserve(gens.size() * 16);
     int64_t halo_total = 0;
-    std::vector<RowWin> wins;
+    std::vector<int32_t> halo, halo_off;
     std::vector<int2> bulk, single;
-    std::vector<std::pair<int32_t, int32_t>> tsegs;   // (class, index into segs)
+    struct Rec { int cls; uint16_t w[24]; };
+    std::vector<Rec> recs;
     std::vector<int32_t> tgens;
-    std::vector<std::vector<int32_t>> refs;           // per image row: (half warp * 7 + stream) * 16 + (u mod 16)
-    std::vector<int32_t> order_rows, bank_cnt;
     auto emit = [&](int32_t g, int32_t s, int32_t len) {
         if ((g ^ s) & 1) {      // parities differ: no 16-byte aligned pairing exists
             for (int32_t k = 0; k < len; k++) single.push_back({g + k, s + k});
@@ -284,162 +287,183 @@ int build_segs(eut_plan *p, const SegParams &sp)
         if (body > 0) bulk.push_back({g, s | (body << 16)});
         if (len & 1) single.push_back({g + body, s + body});
     };
+    const int kGap = 6;          // halo runs closer than this are merged (the cells between come along)
     for (int32_t t = 0; t < n_tiles; t++) {
         const int32_t t0 = S.tile_start[t], t1 = S.tile_start[t + 1];
-        wins.clear(); bulk.clear(); single.clear(); tsegs.clear(); tgens.clear();
-        auto touch = [&](int32_t row, int32_t lo, int32_t hi) { wins.push_back({row, lo, hi, 0}); };
-        for (int32_t k = tile_piece0[t]; k < tile_piece0[t + 1]; k++) {
-            const Piece &pc = pieces[ord[k]];
-            const int32_t r = ra.row_of[pc.first];
-            touch(r, u_of(pc.first), u_of(pc.first) + pc.count - 1);
-            for (int32_t s = pc.seg0; s < pc.seg0 + pc.nseg; s++) {
-                const Seg &sg = segs[s];
-                const int32_t u0 = u_of(sg.first);
-                touch(r, u0 - 1, u0 + sg.len);
-                int cls = 0;
-                for (int x = 0; x < NSTREAM; x++) {
-                    if (sg.pat.row[x] < 0) continue;
-                    const bool pair = (x == SA || x == SB || x == SE_ || x == SF);
-                    touch(sg.pat.row[x], u0 + sg.pat.sh[x], u0 + sg.pat.sh[x] + sg.len - 1 + (pair ? 1 : 0));
-                    if (x == SA || x == SB) cls |= 1;
-                    if (x == SE_ || x == SF) cls |= 2;
-                }
-                tsegs.emplace_back(cls, s);
-            }
-            for (int32_t g = pc.gen0; g < pc.gen0 + pc.ngen; g++) {
-                const int32_t i = gens[g];
-                for (int64_t e = p->row_ptr[i]; e < p->row_ptr[i + 1]; e++) {
-                    const int32_t n = p->col[e];
-                    touch(ra.row_of[n], u_of(n), u_of(n));
-                }
-                tgens.push_back(i);
+        halo.clear(); bulk.clear(); single.clear(); recs.clear(); tgens.clear();
+        for (int32_t q = t0; q < t1; q++) {
+            const int32_t i = p->iperm[q];
+            if (i < 0) continue;                       // gap cell
+            for (int64_t k = p->row_ptr[i]; k < p->row_ptr[i + 1]; k++) {
+                const int32_t nq = p->perm[p->col[k]];
+                if (nq < t0 || nq >= t1) halo.push_back(nq);
             }
         }
-        // merge the windows per row
-        std::sort(wins.begin(), wins.end(), [](const RowWin &a, const RowWin &b) { return a.row < b.row; });
-        {
-            size_t w = 0;
-            for (size_t k = 0; k < wins.size(); k++) {
-                if (w > 0 && wins[w - 1].row == wins[k].row) {
-                    wins[w - 1].lo = std::min(wins[w - 1].lo, wins[k].lo);
-                    wins[w - 1].hi = std::max(wins[w - 1].hi, wins[k].hi);
-                } else wins[w++] = wins[k];
+        std::sort(halo.begin(), halo.end());
+        halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
+        const int32_t own_off = ZH + ((t0 ^ ZH) & 1);
+        emit(t0, own_off, t1 - t0);
+        int32_t next = own_off + (t1 - t0);
+        halo_off.assign(halo.size(), -1);
+        for (size_t h = 0; h < halo.size();) {
+            size_t e = h + 1;
+            while (e < halo.size() && halo[e] - halo[e - 1] <= kGap) e++;
+            const int32_t span = halo[e - 1] - halo[h] + 1;
+            if (span >= 3) {
+                if ((next & 1) != (halo[h] & 1)) next++;
+                for (size_t k = h; k < e; k++) halo_off[k] = next + (halo[k] - halo[h]);
+                emit(halo[h], next, span);
+                halo_total += span;
+                next += span;
             }
-            wins.resize(w);
+            h = e;
         }
-        // Placement.  What matters for the shared-memory pipe is cell(row, u) mod 16 (an 8-byte
-        // bank pair): an LDS.64 of a stream is conflict free iff the 16 lanes of a half warp read 16
-        // different residues.  Every image row gets a residue rho = (base - lo) mod 16, chosen
-        // greedily -- own rows in lane order, then the halo rows -- to minimise the conflicts with
-        // the rows placed before it, counted over all (half warp, stream) groups that read it.
-        // On the regular interior this reproduces "consecutive rows of a layer differ by 8 cells";
-        // ragged tiles get the best the greedy finds.  The parity of rho is not free: the row's
-        // longest run of consecutive internal ids must keep 16-byte aligned bulk copies.
-        const size_t nw = wins.size();
-        auto win_of = [&](int32_t row) -> int32_t {
-            return (int32_t)(std::lower_bound(wins.begin(), wins.end(), row,
-                                              [](const RowWin &w, int32_t r) { return w.row < r; }) - wins.begin());
-        };
-        std::vector<int32_t> best_of(nw, -1);
-        for (size_t k = 0; k < nw; k++) {
-            const RowWin &w = wins[k];
-            const int32_t k0 = std::max(0, w.lo - ra.xs[w.row]);
-            const int32_t k1 = std::min(row_len(w.row), w.hi - ra.xs[w.row] + 1);
-            if (k1 <= k0) continue;                                           // nothing but holes
-            const int32_t e0 = ra.row_start[w.row] + k0, e1 = ra.row_start[w.row] + k1;
-            int32_t best_len = 0;
-            for (int32_t i = e0; i < e1;) {
-                int32_t j = i + 1;
-                while (j < e1 && p->perm[j] == p->perm[j - 1] + 1) j++;
-                if (j - i > best_len) { best_len = j - i; best_of[k] = i; }
-                i = j;
-            }
-        }
-        refs.assign(nw, std::vector<int32_t>());
-        order_rows.clear();
-        for (size_t g = 0; g < tsegs.size(); g++) {
-            const Seg &sg = segs[tsegs[g].second];
-            const int32_t r = ra.row_of[sg.first], u0 = u_of(sg.first);
-            const int32_t h = (int32_t)(g / 16);
-            const int32_t wo = win_of(r);
-            if (order_rows.empty() || order_rows.back() != wo) order_rows.push_back(wo);
-            refs[wo].push_back((h * 7 + 0) * 16 + (u0 & 15));
-            for (int x = 0; x < NSTREAM; x++)
-                if (sg.pat.row[x] >= 0)
-                    refs[win_of(sg.pat.row[x])].push_back((h * 7 + 1 + x) * 16 + ((u0 + sg.pat.sh[x]) & 15));
-        }
-        {
-            std::vector<uint8_t> seen(nw, 0);
-            for (const int32_t k : order_rows) seen[k] = 1;
-            for (size_t k = 0; k < nw; k++) if (!seen[k]) order_rows.push_back((int32_t)k);
-        }
-        bank_cnt.assign(((tsegs.size() + 15) / 16 + 1) * 7 * 16, 0);
-        std::vector<int32_t> rho(nw, 0);
-        for (const int32_t k : order_rows) {
-            const RowWin &w = wins[k];
-            int want_par = -1;
-            if (best_of[k] >= 0) want_par = (p->perm[best_of[k]] - u_of(best_of[k])) & 1;
-            int32_t best_rho = want_par < 0 ? 0 : want_par, best_cost = INT32_MAX;
-            for (int32_t c = 0; c < 16; c++) {
-                if (want_par >= 0 && (c & 1) != want_par) continue;
-                int32_t cost = 0;
-                for (const int32_t rf : refs[k]) {
-                    const int32_t grp = rf >> 4, res = (rf + c) & 15;
-                    cost += bank_cnt[grp * 16 + res];
-                    bank_cnt[grp * 16 + res]++;                               // conflicts inside the row count too
-                }
-                for (const int32_t rf : refs[k]) bank_cnt[(rf >> 4) * 16 + ((rf + c) & 15)]--;
-                if (cost < best_cost) { best_cost = cost; best_rho = c; }
-            }
-            rho[k] = best_rho;
-            for (const int32_t rf : refs[k]) bank_cnt[(rf >> 4) * 16 + ((rf + best_rho) & 15)]++;
-            (void)w;
-        }
-        // chain the rows so that each starts where the previous one ended (mod 16): little padding
-        int32_t next = ZH;
-        {
-            std::vector<uint8_t> placed(nw, 0);
-            for (size_t n_placed = 0; n_placed < nw; n_placed++) {
-                int32_t pick = -1, pick_pad = 99;
-                for (size_t k = 0; k < nw; k++) {
-                    if (placed[k]) continue;
-                    const int32_t pad = (((rho[k] + wins[k].lo - next) % 16) + 16) % 16;
-                    if (pad < pick_pad) { pick_pad = pad; pick = (int32_t)k; }
-                    if (pad == 0) break;
-                }
-                RowWin &w = wins[pick];
-                placed[pick] = 1;
-                next += pick_pad;
-                w.base = next;
-                if (best_of[pick] >= 0) {
-                    const int32_t k0 = std::max(0, w.lo - ra.xs[w.row]);
-                    const int32_t k1 = std::min(row_len(w.row), w.hi - ra.xs[w.row] + 1);
-                    const int32_t e0 = ra.row_start[w.row] + k0, e1 = ra.row_start[w.row] + k1;
-                    for (int32_t i = e0; i < e1;) {
-                        int32_t j = i + 1;
-                        while (j < e1 && p->perm[j] == p->perm[j - 1] + 1) j++;
-                        const int32_t q = p->perm[i];
-                        emit(q, w.base + (u_of(i) - w.lo), j - i);
-                        if (q < t0 || q >= t1) halo_total += j - i;
-                        i = j;
-                    }
-                }
-                next += w.hi - w.lo + 1;
-            }
-        }
-        next += R + 2;                              // masked lanes of short segments read past their row
-        if (next > sp.max_img_points || next > 65535) {
+        for (size_t h = 0; h < halo.size(); h++)
+            if (halo_off[h] < 0) { halo_off[h] = next++; single.push_back({halo[h], halo_off[h]}); halo_total++; }
+        next += R + 2;                              // masked lanes of short segments read past their stream
+        if (next > sp.max_img_points || next * 8 > 65535) {
             if (getenv("EUT_TRACE"))
                 fprintf(stderr, "[eut] segment planner: tile %d (%d points) needs an image of %d cells > %d\n",
                         t, t1 - t0, next, sp.max_img_points);
             return EUT_ERR_UNSUPPORTED;
         }
-        auto cell_of = [&](int32_t row, int32_t u) -> int32_t {
-            const auto it = std::lower_bound(wins.begin(), wins.end(), row,
-                                             [](const RowWin &w, int32_t r) { return w.row < r; });
-            return it->base + (u - it->lo);
+        // image cell of a point (reference id); -1 if the tile does not hold it
+        auto cell_of = [&](int32_t i) -> int32_t {
+            const int32_t nq = p->perm[i];
+            if (nq >= t0 && nq < t1) return own_off + (nq - t0);
+            const auto it = std::lower_bound(halo.begin(), halo.end(), nq);
+            if (it == halo.end() || *it != nq) return -1;
+            return halo_off[it - halo.begin()];
         };
-        const int32_t out0 = t0 & 1;                // result-buffer cell parity = global parity
+        // cell of the canonical neighbour (row rr, column u): 0 = hole (reads the zero header)
+        auto cell_at = [&](int32_t rr, int32_t u) -> int32_t {
+            if (rr < 0) return 0;
+            const int32_t k = u - ra.xs[rr];
+            if (k < 0 || k >= row_len(rr)) return 0;
+            return cell_of(ra.row_start[rr] + k);
+        };
+        // the layout side of a segment: fills the record, or fails
+        auto layout = [&](int32_t first, int32_t len, const Pattern &pat, int32_t piece_end, Rec &rec) -> bool {
+            const int32_t r = ra.row_of[first], u0 = u_of(first);
+            const bool full = (len == R);
+            for (int k = 0; k < 24; k++) rec.w[k] = 0;
+            const int32_t base_o = cell_of(first);
+            if (!full && first + len >= piece_end) return false;    // o[len + 1] is read in line
+            const int32_t c_left = cell_at(r, u0 - 1), c_right = full ? cell_at(r, u0 + R) : 0;
+            if (base_o < 0 || c_left < 0 || c_right < 0) return false;
+            rec.w[0] = (uint16_t)(base_o * 8);
+            rec.w[8] = (uint16_t)(c_left * 8);
+            rec.w[9] = (uint16_t)(c_right * 8);
+            rec.cls = 0;
+            static const int slot_first[NSTREAM] = {10, 12, -1, -1, 14, 16};
+            for (int x = 0; x < NSTREAM; x++) {
+                const int32_t rr = pat.row[x];
+                if (rr < 0) continue;
+                const int32_t ub = u0 + pat.sh[x];
+                if (x == SC || x == SD) {                            // single stream: all cells in line
+                    const int32_t b = cell_at(rr, ub);
+                    if (b <= 0) return false;
+                    for (int32_t i = 1; i < len; i++)
+                        if (cell_at(rr, ub + i) != b + i) return false;
+                    rec.w[1 + x] = (uint16_t)(b * 8);
+                } else {                                             // pair stream: cells 0 .. len
+                    const int32_t c1 = cell_at(rr, ub + 1);
+                    if (c1 <= 1) return false;
+                    const int32_t last_inline = full ? R - 1 : len;
+                    for (int32_t i = 2; i <= last_inline; i++)
+                        if (cell_at(rr, ub + i) != c1 + (i - 1)) return false;
+                    rec.w[1 + x] = (uint16_t)((c1 - 1) * 8);
+                    const int32_t c0 = cell_at(rr, ub), cl = full ? cell_at(rr, ub + R) : 0;
+                    if (c0 < 0 || cl < 0) return false;
+                    rec.w[slot_first[x]] = (uint16_t)(c0 * 8);
+                    rec.w[slot_first[x] + 1] = (uint16_t)(cl * 8);
+                    rec.cls |= (x == SA || x == SB) ? 1 : 2;
+                }
+            }
+            rec.w[7] = (uint16_t)((p->perm[first] - t0 + (t0 & 1)) | (len << 12));
+            return true;
+        };
+        for (int32_t k = tile_piece0[t]; k < tile_piece0[t + 1]; k++) {
+            const Piece &pc = pieces[ord[k]];
+            int32_t i = pc.first;
+            const int32_t end = pc.first + pc.count;
+            while (i < end) {
+                // longest run the graph check accepts ...
+                Pattern pat, best;
+                int32_t len = 0;
+                while (len < R && i + len < end) {
+                    if (len > 0 && check_point(i + len, best)) { len++; continue; }
+                    if (!derive(i, len + 1, pat)) break;
+                    bool ok = true;
+                    for (int32_t j = 0; j <= len && ok; j++) ok = check_point(i + j, pat);
+                    if (!ok) break;
+                    best = pat;
+                    len++;
+                }
+                // ... shortened until the image layout accepts it as well
+                Rec rec;
+                bool placed = false;
+                while (len > 0 && !placed) {
+                    if (derive(i, len, pat)) {
+                        bool ok = true;
+                        for (int32_t j = 0; j < len && ok; j++) ok = check_point(i + j, pat);
+                        if (ok && layout(i, len, pat, end, rec)) placed = true;
+                    }
+                    if (!placed) len--;
+                }
+                if (placed) { recs.push_back(rec); S.seg_points += len; i += len; }
+                else { tgens.push_back(i); i++; }
+            }
+        }
+        // Lane assignment.  Lanes of a warp should run the same stream set (class), and the 16 lanes of
+        // a half warp should read 16 different 8-byte bank pairs: an LDS.64 is conflict free iff the
+        // lanes' cells differ mod 16.  All streams of a segment move with its own cell (the rows of a
+        // regular tile are a constant distance apart); in ragged tiles they do not, so half warps are
+        // filled greedily with the segment that adds the fewest residue clashes over all seven streams
+        // (ties: the fullest own-cell residue bucket, which keeps the remainder balanced).
+        std::stable_sort(recs.begin(), recs.end(), [](const Rec &a, const Rec &b) { return a.cls < b.cls; });
+        {
+            std::vector<Rec> out;
+            out.reserve(recs.size());
+            std::vector<uint8_t> taken(recs.size(), 0);
+            int bucket[16];
+            uint32_t used[7] = {0, 0, 0, 0, 0, 0, 0};
+            size_t c0 = 0;
+            while (c0 < recs.size()) {
+                size_t c1 = c0;
+                while (c1 < recs.size() && recs[c1].cls == recs[c0].cls) c1++;
+                for (int r = 0; r < 16; r++) bucket[r] = 0;
+                for (size_t k = c0; k < c1; k++) bucket[(recs[k].w[0] / 8) & 15]++;
+                for (size_t n = c0; n < c1; n++) {
+                    if (out.size() % 16 == 0) for (int x = 0; x < 7; x++) used[x] = 0;
+                    int64_t pick = -1;
+                    int pick_cost = 99, pick_bucket = -1;
+                    for (size_t k = c0; k < c1; k++) {
+                        if (taken[k]) continue;
+                        int cost = 0;
+                        for (int x = 0; x < 7; x++)
+                            if (recs[k].w[x]) cost += (used[x] >> ((recs[k].w[x] / 8) & 15)) & 1u;
+                        const int bsz = bucket[(recs[k].w[0] / 8) & 15];
+                        if (cost < pick_cost || (cost == pick_cost && bsz > pick_bucket)) { pick = (int64_t)k; pick_cost = cost; pick_bucket = bsz; }
+                    }
+                    taken[pick] = 1;
+                    bucket[(recs[pick].w[0] / 8) & 15]--;
+                    for (int x = 0; x < 7; x++)
+                        if (recs[pick].w[x]) used[x] |= 1u << ((recs[pick].w[x] / 8) & 15);
+                    out.push_back(recs[pick]);
+                }
+                c0 = c1;
+            }
+            recs.swap(out);
+        }
+        // more segments than lanes: the excess is computed point by point
+        while ((int32_t)recs.size() > sp.max_tile_segs) {
+            const Rec &rc = recs.back();
+            const int32_t q0 = t0 + (rc.w[7] & 0xfff) - (t0 & 1), len = rc.w[7] >> 12;
+            for (int32_t j = 0; j < len; j++) tgens.push_back(p->iperm[q0 + j]);
+            S.seg_points -= len;
+            recs.pop_back();
+        }
         int32_t *m = &S.meta[(size_t)t * 12];
         m[0] = t0; m[1] = t1 - t0;
         m[2] = (int32_t)S.copies.size(); m[3] = (int32_t)bulk.size();
@@ -449,38 +473,26 @@ int build_segs(eut_plan *p, const SegParams &sp)
         int32_t tx = 0;
         for (const int2 &b : bulk) tx += (b.y >> 16) * 8;
         m[6] = tx; m[7] = next;
-        m[8] = (int32_t)(S.segs.size() / 8); m[9] = (int32_t)tsegs.size();
+        m[8] = (int32_t)(S.segs.size() / 24); m[9] = (int32_t)recs.size();
         m[10] = (int32_t)(S.gens.size() / 16); m[11] = (int32_t)tgens.size();
-        for (const auto &ts : tsegs) {
-            const Seg &sg = segs[ts.second];
-            const int32_t r = ra.row_of[sg.first], u0 = u_of(sg.first);
-            S.segs.push_back((uint16_t)cell_of(r, u0));
-            for (int x = 0; x < NSTREAM; x++)
-                S.segs.push_back(sg.pat.row[x] < 0 ? (uint16_t)0 : (uint16_t)cell_of(sg.pat.row[x], u0 + sg.pat.sh[x]));
-            S.segs.push_back((uint16_t)((p->perm[sg.first] - t0 + out0) | (sg.len << 12)));
-            S.seg_points += sg.len;
-        }
+        for (const Rec &rc : recs) S.segs.insert(S.segs.end(), rc.w, rc.w + 24);
         for (const int32_t i : tgens) {
             const int d = (int)(p->row_ptr[i + 1] - p->row_ptr[i]);
-            for (int k = 0; k < 12; k++) {
-                uint16_t c = 0;
-                if (k < d) { const int32_t n = p->col[p->row_ptr[i] + k]; c = (uint16_t)cell_of(ra.row_of[n], u_of(n)); }
-                S.gens.push_back(c);
-            }
-            S.gens.push_back((uint16_t)cell_of(ra.row_of[i], u_of(i)));
-            S.gens.push_back((uint16_t)(p->perm[i] - t0 + out0));
+            for (int k = 0; k < 12; k++) S.gens.push_back(k < d ? (uint16_t)cell_of(p->col[p->row_ptr[i] + k]) : (uint16_t)0);
+            S.gens.push_back((uint16_t)cell_of(i));
+            S.gens.push_back((uint16_t)(p->perm[i] - t0 + (t0 & 1)));
             S.gens.push_back(0); S.gens.push_back(0);
         }
         S.img_points = std::max(S.img_points, next);
         S.max_tile_points = std::max(S.max_tile_points, t1 - t0);
-        S.max_tile_segs = std::max(S.max_tile_segs, (int)tsegs.size());
+        S.max_tile_segs = std::max(S.max_tile_segs, (int)recs.size());
         S.max_gen = std::max(S.max_gen, (int)tgens.size());
         S.max_bulk = std::max(S.max_bulk, (int)bulk.size());
         S.max_single = std::max(S.max_single, (int)single.size());
     }
     S.halo_ratio = (double)halo_total / (double)N;
     S.n_copies = (int64_t)S.copies.size();
-    S.n_segs = (int64_t)(S.segs.size() / 8);
+    S.n_segs = (int64_t)(S.segs.size() / 24);
     S.n_gens = (int64_t)(S.gens.size() / 16);
     if (S.max_bulk > sp.max_bulk || S.max_single > sp.max_single) {
         if (getenv("EUT_TRACE"))

@@ -335,14 +335,16 @@ static int launch_ell_w(eut_field *f, int n_act, int substep)
     const eut_plan *p = f->plan;
     int cpt = f->opt_cpt > 0 ? f->opt_cpt : (n_act >= 8 ? 8 : (n_act >= 4 ? 4 : (n_act >= 2 ? 2 : 1)));
     const int block = 256;
-    dim3 grid((unsigned)((p->N + block - 1) / block), 1, 1);
+    // all Np internal positions: a plan may leave gaps between its points (segs.cu pads ragged row
+    // pieces); gap cells have degree 0 and weight 0 and keep their value
+    dim3 grid((unsigned)((p->Np + block - 1) / block), 1, 1);
     const int64_t bs = f->C * p->Np;
     const int32_t *act_col = f->d_act, *act_par = f->d_act + f->act_cap;
 #define EUT_LAUNCH_ELL(CPT)                                                                      \
     grid.y = (unsigned)((n_act + CPT - 1) / CPT);                                                \
     k_substep_ell<W, CPT><<<grid, block, 0, f->stream>>>(f->d_buf, p->Np, bs, p->d_nbr, p->d_deg, \
                                                          p->d_w, act_col, act_par, n_act, substep, \
-                                                         (int)p->N)
+                                                         (int)p->Np)
     if (cpt >= 8) { EUT_LAUNCH_ELL(8); }
     else if (cpt >= 4) { EUT_LAUNCH_ELL(4); }
     else if (cpt >= 2) { EUT_LAUNCH_ELL(2); }
@@ -440,15 +442,16 @@ int launch_permute_out(eut_field *f, double *d_stage, int64_t ld, const int32_t 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_column_stats(const double *__restrict__ buf, const int64_t col_stride, const int64_t buf_stride,
-               const int32_t *__restrict__ cur, const int n_points, double *__restrict__ stats,
-               const int n_cols)
+               const int32_t *__restrict__ cur, const int32_t *__restrict__ iperm, const int n_padded,
+               const int n_points, double *__restrict__ stats, const int n_cols)
 {
     // one block per column; deterministic tree reduction (fixed block size, fixed stride)
     const int c = blockIdx.x;
     const double *src = buf + (int64_t)cur[c] * buf_stride + (int64_t)c * col_stride;
     double mn = INFINITY, mx = -INFINITY, sm = 0.0;
     bool nan = false;
-    for (int q = threadIdx.x; q < n_points; q += blockDim.x) {
+    for (int q = threadIdx.x; q < n_padded; q += blockDim.x) {
+        if (iperm[q] < 0) continue;                        // padding / gap cell
         double v = src[q];
         nan |= (v != v);
         mn = fmin(mn, v); mx = fmax(mx, v); sm += v;
@@ -485,8 +488,8 @@ int launch_column_stats(eut_field *f, const int32_t *d_cur)
 {
     const eut_plan *p = f->plan;
     if (f->C == 0) return EUT_OK;
-    k_column_stats<<<(unsigned)f->C, 256, 0, f->stream>>>(f->d_buf, p->Np, f->C * p->Np, d_cur,
-                                                          (int)p->N, f->d_stats, (int)f->C);
+    k_column_stats<<<(unsigned)f->C, 256, 0, f->stream>>>(f->d_buf, p->Np, f->C * p->Np, d_cur, p->d_iperm,
+                                                          (int)p->Np, (int)p->N, f->d_stats, (int)f->C);
     f->launches++;
     EUT_CUDA(cudaGetLastError());
     return EUT_OK;
@@ -497,7 +500,7 @@ int launch_fill_column(eut_field *f, int32_t col0, double value)
     const eut_plan *p = f->plan;
     if (p->N == 0) return EUT_OK;
     double *dst = f->d_buf + (int64_t)f->cur[col0] * f->C * p->Np + (int64_t)col0 * p->Np;
-    k_fill<<<(unsigned)((p->N + 255) / 256), 256, 0, f->stream>>>(dst, value, (int)p->N);
+    k_fill<<<(unsigned)((p->Np + 255) / 256), 256, 0, f->stream>>>(dst, value, (int)p->Np);
     f->launches++;
     EUT_CUDA(cudaGetLastError());
     return EUT_OK;

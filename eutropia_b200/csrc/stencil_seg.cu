@@ -124,7 +124,7 @@ k_substep_seg(double *__restrict__ buf, const int64_t col_stride, const int64_t 
     // only ever write cells that exist
     {
         uint4 *z = reinterpret_cast<uint4 *>(smem_raw);
-        const int n16 = NBUF * img_bytes / 16;
+        const int n16 = (NBUF * img_bytes + OB * out_bytes) / 16;   // result buffers too: gap cells store 0
         for (int i = tid; i < n16; i += THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     if (tid == 0) {
@@ -205,7 +205,7 @@ k_substep_seg(double *__restrict__ buf, const int64_t col_stride, const int64_t 
 
     // =========================== consumer warps ================================================
     // segments: byte offsets of the seven streams inside the image, result cell, length, weights
-    uint32_t so[SPT][7], sout[SPT];
+    uint32_t so[SPT][7], sout[SPT], rd[SPT][5];            // rd: packed first | last << 16 of O, A, B, E, F
     int slen[SPT];
     double sw[SPT][R];
     uint32_t lo_mask = 0, up_mask = 0;                     // warp-uniform: some lane has A/B resp. E/F
@@ -213,19 +213,21 @@ k_substep_seg(double *__restrict__ buf, const int64_t col_stride, const int64_t 
 #pragma unroll
     for (int s = 0; s < SPT; s++) {
         const int i = tid + s * CTHREADS;
-        uint4 r = make_uint4(1u, 0u, 0u, 0u);              // idle lane: O at cell 1, everything else absent
-        if (i < m2.y) r = __ldg(segs + m2.x + i);
-        so[s][0] = (r.x & 0xffffu) * 8u; so[s][1] = (r.x >> 16) * 8u;
-        so[s][2] = (r.y & 0xffffu) * 8u; so[s][3] = (r.y >> 16) * 8u;
-        so[s][4] = (r.z & 0xffffu) * 8u; so[s][5] = (r.z >> 16) * 8u;
-        so[s][6] = (r.w & 0xffffu) * 8u;
+        uint4 r = make_uint4(8u, 0u, 0u, 0u);              // idle lane: O at cell 1, everything else absent
+        uint4 r1 = make_uint4(0u, 0u, 0u, 0u), r2 = r1;
+        if (i < m2.y) { r = __ldg(segs + 3 * (m2.x + i)); r1 = __ldg(segs + 3 * (m2.x + i) + 1); r2 = __ldg(segs + 3 * (m2.x + i) + 2); }
+        so[s][0] = r.x & 0xffffu; so[s][1] = r.x >> 16;
+        so[s][2] = r.y & 0xffffu; so[s][3] = r.y >> 16;
+        so[s][4] = r.z & 0xffffu; so[s][5] = r.z >> 16;
+        so[s][6] = r.w & 0xffffu;
+        rd[s][0] = r1.x; rd[s][1] = r1.y; rd[s][2] = r1.z; rd[s][3] = r1.w; rd[s][4] = r2.x;
         sout[s] = ((r.w >> 16) & 0xfffu) * 8u;
         slen[s] = (int)(r.w >> 28);
         const int q0 = t0 + (int)((r.w >> 16) & 0xfffu) - head;
 #pragma unroll
         for (int j = 0; j < R; j++) sw[s][j] = (j < slen[s]) ? __ldg(wout + q0 + j) : 0.0;
-        lo_mask |= (__any_sync(0xffffffffu, (so[s][1] | so[s][2]) != 0u) ? 1u : 0u) << s;
-        up_mask |= (__any_sync(0xffffffffu, (so[s][5] | so[s][6]) != 0u) ? 1u : 0u) << s;
+        lo_mask |= (__any_sync(0xffffffffu, (so[s][1] | so[s][2] | rd[s][1] | rd[s][2]) != 0u) ? 1u : 0u) << s;
+        up_mask |= (__any_sync(0xffffffffu, (so[s][5] | so[s][6] | rd[s][3] | rd[s][4]) != 0u) ? 1u : 0u) << s;
     }
     auto s_lds = [](const unsigned char *a) { return *reinterpret_cast<const double *>(a); };
     auto s_sts = [](unsigned char *a, double v) { *reinterpret_cast<double *>(a) = v; };
@@ -244,17 +246,21 @@ k_substep_seg(double *__restrict__ buf, const int64_t col_stride, const int64_t 
             }
             double o[R + 2], acc[R];
             {
-                const unsigned char *a = img + so[s][0] - 8u;
+                const unsigned char *a = img + so[s][0];
+                o[0] = s_lds(img + (rd[s][0] & 0xffffu));
 #pragma unroll
-                for (int i = 0; i < R + 2; i++) o[i] = s_lds(a + 8u * i);
+                for (int i = 0; i < R; i++) o[i + 1] = s_lds(a + 8u * i);
+                o[R + 1] = s_lds(img + (rd[s][0] >> 16));
             }
 #pragma unroll
             for (int i = 0; i < R; i++) acc[i] = 0.0;
-            auto pair_stream = [&](uint32_t off) {
+            auto pair_stream = [&](uint32_t off, uint32_t ends) {
                 double v[R + 1];
                 const unsigned char *a = img + off;
+                v[0] = s_lds(img + (ends & 0xffffu));
 #pragma unroll
-                for (int i = 0; i < R + 1; i++) v[i] = s_lds(a + 8u * i);
+                for (int i = 1; i < R; i++) v[i] = s_lds(a + 8u * i);
+                v[R] = s_lds(img + (ends >> 16));
 #pragma unroll
                 for (int i = 0; i < R; i++) acc[i] = __dadd_rn(acc[i], v[i]);
 #pragma unroll
@@ -268,14 +274,14 @@ k_substep_seg(double *__restrict__ buf, const int64_t col_stride, const int64_t 
 #pragma unroll
                 for (int i = 0; i < R; i++) acc[i] = __dadd_rn(acc[i], v[i]);
             };
-            if ((lo_mask >> s) & 1u) { pair_stream(so[s][1]); pair_stream(so[s][2]); }
+            if ((lo_mask >> s) & 1u) { pair_stream(so[s][1], rd[s][1]); pair_stream(so[s][2], rd[s][2]); }
             single_stream(so[s][3]);
 #pragma unroll
             for (int i = 0; i < R; i++) acc[i] = __dadd_rn(acc[i], o[i]);          // left neighbour
 #pragma unroll
             for (int i = 0; i < R; i++) acc[i] = __dadd_rn(acc[i], o[i + 2]);      // right neighbour
             single_stream(so[s][4]);
-            if ((up_mask >> s) & 1u) { pair_stream(so[s][5]); pair_stream(so[s][6]); }
+            if ((up_mask >> s) & 1u) { pair_stream(so[s][5], rd[s][3]); pair_stream(so[s][6], rd[s][4]); }
 #pragma unroll
             for (int i = 0; i < R; i++) {
                 double y = __dmul_rn(acc[i], kBDiv);
@@ -362,6 +368,8 @@ int launch_seg(eut_field *f, int n_act, int substep)
             if (shape == 1) return launch_seg_t<7, 1, 7, 3, 2, 2>(f, n_act, substep);
             if (nb == 2) return launch_seg_t<7, 1, 7, 2, 2, 2>(f, n_act, substep);
             if (nb == 4) return launch_seg_t<7, 1, 7, 4, 2, 2>(f, n_act, substep);
+            if (shape == 2) return launch_seg_t<7, 1, 7, 5, 2, 2>(f, n_act, substep);
+            if (shape == 3) return launch_seg_t<7, 1, 7, 2, 2, 3>(f, n_act, substep);
             return launch_seg_t<7, 1, 7, 3, 3, 2>(f, n_act, substep);
         }
         if (S.max_tile_segs <= 448) {

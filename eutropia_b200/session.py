@@ -88,11 +88,11 @@ class Plan:
 
     def segs(self):
         """Host segment tables of a `host_only` plan built with ORDER_SEGMENTS: (meta[n_tiles,12],
-        copies[n,2], segs[n_segments,8], gens[n_generic,16]); see eut_plan_get_segs."""
+        copies[n,2], segs[n_segments,24], gens[n_generic,16]); see eut_plan_get_segs."""
         inf = self.info
         meta = np.zeros((max(inf.n_tiles, 1), 12), dtype=np.int32)
         copies = np.zeros((max(inf.n_copies, 1), 2), dtype=np.int32)
-        segs = np.zeros((max(inf.n_segments, 1), 8), dtype=np.uint16)
+        segs = np.zeros((max(inf.n_segments, 1), 24), dtype=np.uint16)
         gens = np.zeros((max(inf.n_generic, 1), 16), dtype=np.uint16)
         check(_lib.lib().eut_plan_get_segs(self._h, ptr(meta), ptr(copies), ptr(segs), ptr(gens)))
         return meta[:inf.n_tiles], copies[:inf.n_copies], segs[:inf.n_segments], gens[:inf.n_generic]

@@ -169,8 +169,10 @@ EUT_API int eut_plan_get_tiles(const eut_plan *plan, int32_t *tile_meta, int32_t
  *                         copy, #single, bulk bytes, image cells, first segment, #segments, first
  *                         generic point, #generic
  *   copies[2*n_copies]    as eut_plan_get_tiles
- *   segs[8*n_segments]    image cell of the first value of the streams O, A, B, C, D, E, F
- *                         (0 = absent), result cell | length << 12
+ *   segs[24*n_segments]   byte offsets inside the image (0 = the zero header): [0..6] first in-line
+ *                         cell of the streams O, A, B, C, D, E, F; [7] result cell | length << 12;
+ *                         [8,9] left / right neighbour of the segment in its own row; [10..17]
+ *                         first / last cell of the pair streams A, B, E, F; rest 0
  *   gens[16*n_generic]    image cells of the 12 neighbour slots (0 = unused), own cell, result
  *                         cell, 0, 0
  * Any pointer may be NULL. */

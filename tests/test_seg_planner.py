@@ -25,21 +25,23 @@ def reference_inflow(m, value):
     return acc
 
 
-def replay(m, plan, check_alignment=True):
+def replay(m, plan, check_alignment=True, max_growth=1.6):
     inf = plan.info
     assert inf.segmented == 1
     n, R = m.nfields, inf.seg_points
     perm = plan.perm()
-    assert np.array_equal(np.sort(perm), np.arange(n))
+    npad = inf.n_padded
+    assert np.unique(perm).size == n and perm.min() >= 0 and perm.max() < npad    # injective; gaps allowed
     meta, copies, segs, gens = plan.segs()
-    assert meta[0, 0] == 0 and np.array_equal(meta[1:, 0], np.cumsum(meta[:-1, 1])) and meta[:, 1].sum() == n
-    assert meta[:, 3].max() <= 128 and meta[:, 5].max() <= 512 and meta[:, 9].max() <= 512
+    assert meta[0, 0] == 0 and np.array_equal(meta[1:, 0], np.cumsum(meta[:-1, 1]))
+    assert n <= meta[:, 1].sum() <= npad and meta[:, 1].sum() <= max_growth * n + 64
+    assert meta[:, 3].max() <= 128 and meta[:, 5].max() <= 512 and meta[:, 9].max() <= 448
     value = np.random.default_rng(0).uniform(1, 2, n)     # by reference id; sums depend on the order
     want = reference_inflow(m, value)
-    iperm = np.empty(n, dtype=np.int64); iperm[perm] = np.arange(n)
-    vq = value[iperm]                                     # by internal position
-    got = np.full(n, np.nan)
-    produced = np.zeros(n, dtype=np.int64)
+    iperm = np.full(npad, -1, dtype=np.int64); iperm[perm] = np.arange(n)
+    vq = np.where(iperm >= 0, value[np.maximum(iperm, 0)], np.nan)   # by internal position; gap cells poison
+    got = np.full(npad, np.nan)
+    produced = np.zeros(npad, dtype=np.int64)
     for t in range(meta.shape[0]):
         t0, cnt, b0, nb, s0, ns, tx, img, g0, ng, x0, nx = meta[t]
         image = np.zeros(img + 1)
@@ -60,19 +62,33 @@ def replay(m, plan, check_alignment=True):
         head = t0 & 1
         S = segs[g0:g0 + ng].astype(np.int64)
         if ng:
+            assert np.all(S[:, list(range(7)) + list(range(8, 18))] % 8 == 0)
             ln = S[:, 7] >> 12
             out = S[:, 7] & 0xfff
             assert ln.min() >= 1 and ln.max() <= R
+            C = S // 8                                           # cells
+            def pair(a, col, red, j):                            # values of cells j and j+1 of a pair stream
+                def cell(k):
+                    inline = image[a[:, col] + k]
+                    v = np.where(k == 0, image[a[:, red]], inline)
+                    return np.where(k == R, image[a[:, red + 1]], v)
+                return cell(j), cell(j + 1)
             for j in range(R):
                 on = j < ln
-                a = S[on]
+                a = C[on]
                 acc = np.zeros(a.shape[0])
-                for col, extra in ((1, 0), (1, 1), (2, 0), (2, 1), (3, 0)):       # A A B B C
-                    acc = acc + image[a[:, col] + j + extra]
-                acc = acc + image[a[:, 0] + j - 1]                                   # left
-                acc = acc + image[a[:, 0] + j + 1]                                   # right
-                for col, extra in ((4, 0), (5, 0), (5, 1), (6, 0), (6, 1)):       # D E E F F
-                    acc = acc + image[a[:, col] + j + extra]
+                for col, red in ((1, 10), (2, 12)):                              # A A B B
+                    v0, v1 = pair(a, col, red, j)
+                    acc = acc + v0; acc = acc + v1
+                acc = acc + image[a[:, 3] + j]                                       # C
+                left = np.where(j == 0, image[a[:, 8]], image[a[:, 0] + j - 1])
+                right = np.where(j == R - 1, image[a[:, 9]], image[a[:, 0] + j + 1])
+                acc = acc + left
+                acc = acc + right
+                acc = acc + image[a[:, 4] + j]                                       # D
+                for col, red in ((5, 14), (6, 16)):                              # E E F F
+                    v0, v1 = pair(a, col, red, j)
+                    acc = acc + v0; acc = acc + v1
                 q = t0 + out[on] + j - head
                 assert np.array_equal(image[a[:, 0] + j], vq[q])                   # own value where the kernel reads it
                 got[q] = acc
@@ -86,8 +102,8 @@ def replay(m, plan, check_alignment=True):
             assert np.array_equal(image[G[:, 12]], vq[q])
             got[q] = acc
             np.add.at(produced, q, 1)
-        assert produced[t0:t0 + cnt].min() == 1 and produced[t0:t0 + cnt].max() == 1
-    assert np.array_equal(got, want[iperm])                # bit-exact, mat.in order
+        assert np.array_equal(produced[t0:t0 + cnt], (iperm[t0:t0 + cnt] >= 0).astype(np.int64))
+    assert np.array_equal(got[perm], want)                 # bit-exact, mat.in order
     return inf
 
 
@@ -99,7 +115,7 @@ def test_segment_tables_replay(name, layers):
     plan = eb.Plan(m.mat_in, m.mat_out, order=_lib.ORDER_SEGMENTS, host_only=True)
     inf = replay(m, plan)
     assert inf.n_seg_covered + inf.n_generic == m.nfields
-    assert inf.n_generic <= 0.02 * m.nfields + 8          # the lattice is regular up to its border
+    assert inf.n_generic <= 0.08 * m.nfields + 8          # generic points only along the border (small meshes: mostly border)
 
 
 def test_segments_fill_up_on_large_mesh():
@@ -107,7 +123,7 @@ def test_segments_fill_up_on_large_mesh():
     plan = eb.Plan(m.mat_in, m.mat_out, order=_lib.ORDER_SEGMENTS, host_only=True)
     inf = plan.info
     meta, _, _, _ = plan.segs()
-    assert inf.segmented == 1 and inf.n_generic == 0
+    assert inf.segmented == 1 and inf.n_generic <= 0.005 * m.nfields
     assert inf.n_seg_covered / (inf.n_segments * inf.seg_points) > 0.9     # segments are mostly full
     assert np.median(meta[:, 9]) > 0.8 * 224                                 # tiles are close to capacity
     assert inf.halo_ratio < 0.5
@@ -133,6 +149,6 @@ def test_shuffled_ids_still_exact():
     mm = M(); mm.nfields = n; mm.mat_in = mat_in; mm.mat_out = mat_out
     plan = eb.Plan(mat_in, mat_out, order=_lib.ORDER_SEGMENTS, host_only=True)
     if plan.info.segmented:
-        replay(mm, plan, check_alignment=True)
+        replay(mm, plan, check_alignment=True, max_growth=4.0)
     else:
         assert plan.info.order in (_lib.ORDER_TILED, _lib.ORDER_ROWBLOCK)

@@ -19,6 +19,7 @@ inf = plan.info
 print("plan %.1fs segmented=%d order=%d tiles=%d img=%d max_pts=%d max_segs=%d max_gen=%d bulk=%d single=%d halo=%.3f"
       % (time.time() - t, inf.segmented, inf.order, inf.n_tiles, inf.img_points, inf.max_tile_points, inf.max_tile_segs,
          inf.max_tile_generic, inf.max_bulk, inf.max_single, inf.halo_ratio))
+print("n_padded / n_points = %.4f" % (inf.n_padded / inf.n_points))
 print("segments %d generic %d fill %.3f" % (inf.n_segments, inf.n_generic, inf.n_seg_covered / max(1, inf.n_segments * inf.seg_points)))
 if inf.segmented:
     meta, copies, segs, gens = plan.segs()
@@ -33,14 +34,14 @@ if inf.segmented:
         S = segs[g0:g0 + ng].astype(np.int64)
         pad = (-ng) % 16
         if pad:
-            S = np.concatenate([S, np.tile(np.array([[1, 0, 0, 0, 0, 0, 0, 0]]), (pad, 1))])
-        H = S.reshape(-1, 16, 8)
+            S = np.concatenate([S, np.tile(np.array([[8] + [0] * 23]), (pad, 1))])
+        H = S.reshape(-1, 16, 24) // 8
         for s in range(7):
             c = H[:, :, s]
             wf = np.zeros(H.shape[0])
             for h in range(H.shape[0]):
-                u, k = np.unique(c[h], return_counts=True)          # same address = broadcast
-                wf[h] = np.bincount(u % 16, minlength=16).max()
+                u = np.unique(c[h][c[h] > 0])                         # same address / zero header = broadcast
+                wf[h] = max(1, np.bincount(u % 16, minlength=16).max())
             tot[s] += wf.sum()
         cnt += H.shape[0]
     print("modelled wavefronts per half-warp load, streams O A B C D E F:", np.round(tot / cnt, 3))
