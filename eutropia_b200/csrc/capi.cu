@@ -351,10 +351,28 @@ int oneshot_run(const int32_t *adj, int64_t n_edges, const int32_t *nn, int64_t 
         act.push_back(i);
     }
     // Pipeline over chunks of active columns: H2D(g+1) | substeps(g) | D2H(g-1) on three streams.
+    // The call lasts  H2D(first chunk) + all substeps + D2H(last chunk):  the first and the last
+    // chunk are kept small (a quarter of the staging buffer), the ones in between full size.
     const int64_t chunk = f->stage_cols;
+    const int64_t small = std::max<int64_t>(1, chunk / 4);
+    std::vector<size_t> cuts;
+    {
+        const size_t n = act.size();
+        size_t a = 0;
+        cuts.push_back(0);
+        if (n > (size_t)(2 * small + chunk / 2)) {
+            a = (size_t)small; cuts.push_back(a);
+            while (n - a > (size_t)(chunk + small)) { a += (size_t)chunk; cuts.push_back(a); }
+            if (n - a > (size_t)small) { a = n - (size_t)small; cuts.push_back(a); }
+        } else {
+            while (n - a > (size_t)chunk) { a += (size_t)chunk; cuts.push_back(a); }
+        }
+        cuts.push_back(n);
+    }
     std::vector<int32_t> cols, nit;
-    for (size_t a0 = 0; a0 < act.size(); a0 += chunk) {
-        const size_t a1 = std::min(act.size(), a0 + (size_t)chunk);
+    for (size_t ci = 0; ci + 1 < cuts.size(); ci++) {
+        const size_t a0 = cuts[ci], a1 = cuts[ci + 1];
+        if (a1 <= a0) continue;
         cols.clear(); nit.clear();
         for (size_t a = a0; a < a1; a++) { cols.push_back(indvar[act[a]]); nit.push_back(niter[act[a]]); }
         // host column j of this chunk is conc_in column cols[j]-1: upload one column at a time when

@@ -94,7 +94,8 @@ struct SegParams {
     int max_img_points = 8190;   // shared-memory image limit (cells) per buffer: 16-bit byte offsets
     int max_bulk = 128;          // bulk copies per tile the kernel can hold (4 per lane of warp 0)
     int max_single = 512;        // single 8-byte copies per tile
-    int pad_rows = 1;            // pad ragged row pieces in storage to 8 (mod 16) cells
+    int pad_rows = 1;            // gap cells after ragged row pieces: 0 none, 1 per-tile residue step (default),
+                                 // 3 global rule position - u == 8 * colour (mod 16): conflict free, ~6 % gaps
 };
 struct SegPlanHost {
     std::vector<int32_t> tile_start;  // [n_tiles+1] internal ids

@@ -89,7 +89,7 @@ uint64_t hash_bytes(const void *data, size_t n, uint64_t seed)
     if (n <= 2 * kSlice) return hash_span(p, n, seed);
     const size_t n_slices = (n + kSlice - 1) / kSlice;
     std::vector<uint64_t> part(n_slices);
-    const unsigned n_thr = std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency()));
+    const unsigned n_thr = std::min<unsigned>(16, std::max(1u, std::thread::hardware_concurrency()));
     std::vector<std::thread> pool;
     for (unsigned t = 0; t < n_thr; t++)
         pool.emplace_back([&, t]() {
@@ -261,6 +261,7 @@ int plan_build(eut_plan *p, const int32_t *from, const int32_t *to, int64_t n_ed
         if (const char *e = getenv("EUT_SEG_TILE")) sp.max_tile_segs = std::min(448, std::max(8, atoi(e)));
         if (const char *e = getenv("EUT_TILE_BAND")) sp.band_levels = atoi(e);
         if (const char *e = getenv("EUT_SEG_PAD")) sp.pad_rows = atoi(e);
+        if (const char *e = getenv("EUT_SEG_MAXPTS")) sp.max_tile_points = std::min(4000, std::max(64, atoi(e)));
         if (build_segs(p, sp) == EUT_OK) p->segmented = true;
         else order = EUT_ORDER_TILED;      // not lattice-like enough / tiles too large: first tiled kernel
     } else if (order == EUT_ORDER_SEGMENTS) order = EUT_ORDER_ROWBLOCK;

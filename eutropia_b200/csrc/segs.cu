@@ -225,16 +225,43 @@ int build_segs(eut_plan *p, const SegParams &sp)
     // cells per piece: s = 8).  Ragged tiles (polygon border: rows start and end anywhere) get gap
     // cells after each piece, 0..15 of them, and the step s that needs the fewest.  Gap cells are
     // never read as neighbours, hold 0, and cost their share of HBM traffic (n_padded vs n_points).
+    // Row colours: rows of one layer alternate (2-colouring of the row adjacency without the pair
+    // flag, i.e. the C / D relation).  A row and the row one of its streams reads then differ by a
+    // colour that is the same for all rows of its layer, as long as no raster row is missing inside
+    // the tile -- which is what "all streams move together" needs.
+    std::vector<int8_t> colour(NR, -1);
+    int64_t colour_clash = 0;
+    {
+        std::vector<int32_t> stack;
+        for (int32_t seed = 0; seed < NR; seed++) {
+            if (colour[seed] >= 0) continue;
+            colour[seed] = 0;
+            stack.push_back(seed);
+            while (!stack.empty()) {
+                const int32_t r = stack.back();
+                stack.pop_back();
+                for (int64_t a = ra.adj_ptr[r]; a < ra.adj_ptr[r + 1]; a++) {
+                    if (ra.adj_pair[a]) continue;
+                    const int32_t rr = ra.adj_row[a];
+                    if (colour[rr] < 0) { colour[rr] = (int8_t)(1 - colour[r]); stack.push_back(rr); }
+                    else if (colour[rr] == colour[r]) colour_clash++;
+                }
+            }
+        }
+    }
     S.tile_start.assign(1, 0);
+    std::vector<int32_t> tile_t0;        // first cell of every tile (tile t ends at tile_start[t + 1])
     {
         int32_t pos = 0;
         std::vector<int32_t> gap;
+        int64_t total_gap = 0;
         for (int32_t t = 0; t < n_tiles; t++) {
             std::sort(ord.begin() + tile_piece0[t], ord.begin() + tile_piece0[t + 1],
                       [&](int32_t a, int32_t b) { return pieces[a].first < pieces[b].first; });
             const int32_t k0 = tile_piece0[t], k1 = tile_piece0[t + 1];
             gap.assign(k1 - k0, 0);
-            if (sp.pad_rows && k1 - k0 > 1) {
+            if (sp.pad_rows == 1 && k1 - k0 > 1) {
+                // chain rule: rho advances by the same step s from piece to piece
                 int64_t best_total = INT64_MAX;
                 int best_s = 8;
                 for (int s = 1; s < 16; s++) {
@@ -250,13 +277,34 @@ int build_segs(eut_plan *p, const SegParams &sp)
                     gap[k - k0] = (((best_s + u_of(b.first) - u_of(a.first) - a.count) % 16) + 16) % 16;
                 }
             }
+            if (sp.pad_rows == 3) {
+                // global rule: position - u == 8 * colour(row) (mod 16) for every piece of the field, so
+                // that the rows of OTHER tiles (halo) keep the same relation; the image keeps
+                // cell == position (mod 16).  The gap sits in front of a piece.
+                for (int32_t k = k0; k < k1; k++) {
+                    const Piece &pc = pieces[ord[k]];
+                    const int32_t want = ((u_of(pc.first) + 8 * std::max<int>(colour[ra.row_of[pc.first]], 0)) % 16 + 16) % 16;
+                    const int32_t g = (((want - pos) % 16) + 16) % 16;
+                    pos += g; total_gap += g;
+                    if (k == k0) tile_t0.push_back(pos);
+                    for (int32_t q = 0; q < pc.count; q++) p->perm[pc.first + q] = pos + q;
+                    pos += pc.count;
+                }
+                S.tile_start.push_back(pos);
+                continue;
+            }
+            tile_t0.push_back(pos);
             for (int32_t k = k0; k < k1; k++) {
                 const Piece &pc = pieces[ord[k]];
                 for (int32_t q = 0; q < pc.count; q++) p->perm[pc.first + q] = pos + q;
                 pos += pc.count + gap[k - k0];
+                total_gap += gap[k - k0];
             }
             S.tile_start.push_back(pos);
         }
+        if (getenv("EUT_TRACE"))
+            fprintf(stderr, "[eut] segment planner: %lld gap cells (%.2f %%), %lld colour clashes\n", (long long)total_gap,
+                    100.0 * (double)total_gap / (double)N, (long long)colour_clash);
     }
     p->Np = (((int64_t)S.tile_start.back() + kPadPoints - 1) / kPadPoints) * kPadPoints;
     p->iperm.assign(p->Np, -1);
@@ -289,7 +337,7 @@ int build_segs(eut_plan *p, const SegParams &sp)
     };
     const int kGap = 6;          // halo runs closer than this are merged (the cells between come along)
     for (int32_t t = 0; t < n_tiles; t++) {
-        const int32_t t0 = S.tile_start[t], t1 = S.tile_start[t + 1];
+        const int32_t t0 = tile_t0[t], t1 = S.tile_start[t + 1];
         halo.clear(); bulk.clear(); single.clear(); recs.clear(); tgens.clear();
         for (int32_t q = t0; q < t1; q++) {
             const int32_t i = p->iperm[q];
@@ -301,7 +349,10 @@ int build_segs(eut_plan *p, const SegParams &sp)
         }
         std::sort(halo.begin(), halo.end());
         halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
-        const int32_t own_off = ZH + ((t0 ^ ZH) & 1);
+        // pad_rows 3: image cell == internal position (mod 16) everywhere, which carries the global
+        // residue rule into the image (and implies the 16-byte parity rule of the bulk copies)
+        const bool keep_res = sp.pad_rows == 3;
+        const int32_t own_off = keep_res ? ZH + (((t0 - ZH) % 16) + 16) % 16 : ZH + ((t0 ^ ZH) & 1);
         emit(t0, own_off, t1 - t0);
         int32_t next = own_off + (t1 - t0);
         halo_off.assign(halo.size(), -1);
@@ -310,7 +361,8 @@ int build_segs(eut_plan *p, const SegParams &sp)
             while (e < halo.size() && halo[e] - halo[e - 1] <= kGap) e++;
             const int32_t span = halo[e - 1] - halo[h] + 1;
             if (span >= 3) {
-                if ((next & 1) != (halo[h] & 1)) next++;
+                if (keep_res) next += (((halo[h] - next) % 16) + 16) % 16;
+                else if ((next & 1) != (halo[h] & 1)) next++;
                 for (size_t k = h; k < e; k++) halo_off[k] = next + (halo[k] - halo[h]);
                 emit(halo[h], next, span);
                 halo_total += span;

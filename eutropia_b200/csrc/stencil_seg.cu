@@ -333,7 +333,7 @@ static int launch_seg_t(eut_field *f, int n_act, int substep)
     const int img_bytes = ((S.img_points * 8 + 127) / 128) * 128;
     const int out_bytes = (((S.max_tile_points + 2) * 8 + 127) / 128) * 128;
     const size_t smem = (size_t)NBUF * img_bytes + (size_t)OB * out_bytes;
-    if (smem > 220 * 1024) {
+    if (smem > 225 * 1024) {
         set_error("segment kernel: %zu bytes of shared memory per CTA", smem);
         return EUT_ERR_UNSUPPORTED;
     }
@@ -347,7 +347,7 @@ static int launch_seg_t(eut_field *f, int n_act, int substep)
     auto kern = k_substep_seg<R, SPT, CWARPS, NBUF, OB, MINB>;
     static bool attr_set[64] = {false};
     if (!attr_set[p->device & 63]) {
-        EUT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        EUT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
         attr_set[p->device & 63] = true;
     }
     kern<<<grid, (CWARPS + 1) * 32, smem, f->stream>>>(f->d_buf, p->Np, f->C * p->Np, p->d_seg_meta, p->d_copies,
@@ -368,14 +368,13 @@ int launch_seg(eut_field *f, int n_act, int substep)
             if (shape == 1) return launch_seg_t<7, 1, 7, 3, 2, 2>(f, n_act, substep);
             if (nb == 2) return launch_seg_t<7, 1, 7, 2, 2, 2>(f, n_act, substep);
             if (nb == 4) return launch_seg_t<7, 1, 7, 4, 2, 2>(f, n_act, substep);
-            if (shape == 2) return launch_seg_t<7, 1, 7, 5, 2, 2>(f, n_act, substep);
-            if (shape == 3) return launch_seg_t<7, 1, 7, 2, 2, 3>(f, n_act, substep);
             return launch_seg_t<7, 1, 7, 3, 3, 2>(f, n_act, substep);
         }
-        if (S.max_tile_segs <= 448) {
+        if (S.max_tile_segs <= 448) {      // EUT_SEG_TILE=448: one CTA per SM, 14 consumer warps
             if (shape == 1) return launch_seg_t<7, 1, 14, 3, 2, 1>(f, n_act, substep);
-            if (nb == 2) return launch_seg_t<7, 2, 7, 2, 2, 1>(f, n_act, substep);
-            return launch_seg_t<7, 2, 7, 3, 2, 1>(f, n_act, substep);
+            if (shape == 2) return launch_seg_t<7, 1, 14, 4, 2, 1>(f, n_act, substep);
+            if (shape == 4) return launch_seg_t<7, 1, 14, 3, 3, 1>(f, n_act, substep);
+            return launch_seg_t<7, 1, 14, 4, 3, 1>(f, n_act, substep);
         }
     }
     if (S.R == 5 && S.max_tile_segs <= 224) return launch_seg_t<5, 1, 7, 3, 2, 2>(f, n_act, substep);

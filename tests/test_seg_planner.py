@@ -33,7 +33,7 @@ def replay(m, plan, check_alignment=True, max_growth=1.6):
     npad = inf.n_padded
     assert np.unique(perm).size == n and perm.min() >= 0 and perm.max() < npad    # injective; gaps allowed
     meta, copies, segs, gens = plan.segs()
-    assert meta[0, 0] == 0 and np.array_equal(meta[1:, 0], np.cumsum(meta[:-1, 1]))
+    assert meta[0, 0] >= 0 and np.all(meta[1:, 0] >= meta[:-1, 0] + meta[:-1, 1])      # disjoint, ascending
     assert n <= meta[:, 1].sum() <= npad and meta[:, 1].sum() <= max_growth * n + 64
     assert meta[:, 3].max() <= 128 and meta[:, 5].max() <= 512 and meta[:, 9].max() <= 448
     value = np.random.default_rng(0).uniform(1, 2, n)     # by reference id; sums depend on the order
