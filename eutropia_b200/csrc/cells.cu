@@ -290,61 +290,68 @@ static int finish_lists(eut_cells *c, cudaStream_t s)
 }
 
 // ---- gather ------------------------------------------------------------------------------------
-// One warp per (cell, group of G compound columns).  Lanes stride over the cell's entries in the
-// order of their internal field position (g_idx: sorted once per cell map), so the 32 loads of a
-// warp request fall on a few runs of consecutive addresses (x-neighbours of one raster row) instead
-// of 32 different sectors; a lane keeps its (position, acc.prop) pairs in registers and reuses
-// them for the G columns, whose loads are all independent.  Sums are hi+lo pairs, so the walking
-// order does not show in the rounded result.
+// One warp per cell, cells in the order of their position in the field.  Lanes stride over the
+// cell's entries in the order of their internal field position (g_idx: sorted once per cell map), so
+// the 32 loads of a warp request fall on a few runs of consecutive addresses (x-neighbours of one
+// raster row) instead of 32 different sectors.  A lane loads its (position, acc.prop) pairs ONCE and
+// reuses them for all compound columns (G at a time, all loads independent); warps that run together
+// belong to neighbouring cells, whose field points overlap, so the columns are read from HBM about
+// once (the first version walked column groups in the outer loop and re-read the entry lists and the
+// field 8x: 10 GB of DRAM reads per call, profiles/r01_cells_ncu.csv).  Sums are hi+lo pairs, so the
+// walking order does not show in the rounded result.
 template <int G, int EPL>
 __global__ void __launch_bounds__(256)
 k_gather(const double *__restrict__ buf, const int64_t col_stride, const int64_t buf_stride,
          const int32_t *__restrict__ cur, const int64_t *__restrict__ cell_ptr,
          const int32_t *__restrict__ g_idx, const int32_t *__restrict__ fq,
          const double *__restrict__ acc, const double field_vol, double *__restrict__ fmol,
-         const int n_cells, const int n_cols, const int n_groups, const int32_t *__restrict__ cell_order)
+         const int n_cells, const int n_cols, const int32_t *__restrict__ cell_order)
 {
-    // column group major, cells in the order of their position in the field: the G columns of a
-    // group (G x 8 MB at 1 M points) stay in L2 while every cell reads them, and neighbouring
-    // warps touch neighbouring sectors
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (w >= (int64_t)n_cells * n_groups) return;
-    const int i = cell_order[(int)(w % n_cells)], c0 = (int)(w / n_cells) * G;
-    dd s[G];
-#pragma unroll
-    for (int u = 0; u < G; u++) s[u] = dd{0.0, 0.0};
+    if (w >= (int64_t)n_cells) return;
+    const int i = cell_order[(int)w];
     const int64_t k0 = cell_ptr[i], k1 = cell_ptr[i + 1];
-    for (int64_t kb = k0; kb < k1; kb += 32 * EPL) {
-        int q[EPL];
-        double a[EPL];
+    const bool one_pass = (k1 - k0) <= 32 * EPL;           // the usual case: the whole list sits in registers
+    int q[EPL];
+    double a[EPL];
+    auto load_entries = [&](int64_t kb) {
 #pragma unroll
         for (int m = 0; m < EPL; m++) {
             const int64_t k = kb + lane + 32 * m;
             q[m] = -1; a[m] = 0.0;
             if (k < k1) { const int e = g_idx[k]; q[m] = fq[e]; a[m] = acc[e]; }
         }
+    };
+    if (one_pass) load_entries(k0);
+    for (int c0 = 0; c0 < n_cols; c0 += G) {
+        dd s[G];
+#pragma unroll
+        for (int u = 0; u < G; u++) s[u] = dd{0.0, 0.0};
+        for (int64_t kb = k0; kb < k1; kb += 32 * EPL) {
+            if (!one_pass) load_entries(kb);
+#pragma unroll
+            for (int u = 0; u < G; u++) {
+                const int c = min(c0 + u, n_cols - 1);
+                const double *__restrict__ col = buf + (int64_t)cur[c] * buf_stride + (int64_t)c * col_stride;
+                double v[EPL];
+#pragma unroll
+                for (int m = 0; m < EPL; m++) v[m] = q[m] >= 0 ? __ldg(col + q[m]) : 0.0;
+                // sum_k ((conc_k / 1000) * fieldVol) * acc_k  (R/scavenge_compounds.R:17-22) is evaluated
+                // as ((sum_k conc_k * acc_k) / 1000) * fieldVol: all terms are non-negative, the two
+                // forms differ by a few ulp (<< the 1e-12 bar; R's own long double sum is not
+                // reproducible to the last bit either) and the per-term division leaves the hot loop.
+#pragma unroll
+                for (int m = 0; m < EPL; m++)
+                    if (q[m] >= 0) dd_add(s[u], __dmul_rn(v[m], a[m]));
+            }
+        }
 #pragma unroll
         for (int u = 0; u < G; u++) {
-            const int c = min(c0 + u, n_cols - 1);
-            const double *__restrict__ col = buf + (int64_t)cur[c] * buf_stride + (int64_t)c * col_stride;
-            double v[EPL];
-#pragma unroll
-            for (int m = 0; m < EPL; m++) v[m] = q[m] >= 0 ? __ldg(col + q[m]) : 0.0;
-            // sum_k ((conc_k / 1000) * fieldVol) * acc_k  (R/scavenge_compounds.R:17-22) is evaluated
-            // as ((sum_k conc_k * acc_k) / 1000) * fieldVol: all terms are non-negative, the two
-            // forms differ by a few ulp (<< the 1e-12 bar; R's own long double sum is not
-            // reproducible to the last bit either) and the per-term division leaves the hot loop.
-#pragma unroll
-            for (int m = 0; m < EPL; m++)
-                if (q[m] >= 0) dd_add(s[u], __dmul_rn(v[m], a[m]));
+            const dd r = dd_warp_sum(s[u]);
+            if (lane == 0 && c0 + u < n_cols)
+                fmol[(int64_t)(c0 + u) * n_cells + i] = __dmul_rn(__ddiv_rn(dd_value(r), 1000.0), field_vol);
         }
-    }
-#pragma unroll
-    for (int u = 0; u < G; u++) {
-        const dd r = dd_warp_sum(s[u]);
-        if (lane == 0 && c0 + u < n_cols)
-            fmol[(int64_t)(c0 + u) * n_cells + i] = __dmul_rn(__ddiv_rn(dd_value(r), 1000.0), field_vol);
     }
 }
 
@@ -452,13 +459,14 @@ k_ex_colsum(const double *__restrict__ buf, const int64_t col_stride, const int6
 // One warp per touched field point.  The warp walks the (cell, entry) pairs of its field in cell
 // order; the exchanges of one cell are evaluated in parallel (lane = exchange: compound, flux,
 // colSum and -- for an uptake -- the field's own concentration are one coalesced / gathered load
-// each), then handed one by one (warp shuffles) to the lane that owns the compound's accumulator
-// (lane = column mod 32, CPL columns per lane, all in registers).  Every (field, compound) sum is
-// thus taken in cell order, like the reference's by-group sum over the concatenated per-cell
-// tables (R/run_simulation.R:309-310).  A cell lists a compound at most once (checked on the
-// host), so the reference's "I.up rows, then I.pd rows" order inside one cell cannot matter.
-// Finally: NaN -> 0, add, clamp (:315-319).
-template <int CPL>
+// each) and added by that lane to the warp's per-column accumulators in shared memory.  A cell lists
+// a compound at most once (checked on the host), so the lanes of one step hit different columns, and
+// the steps are separated by __syncwarp: every (field, compound) sum is taken in cell order, like the
+// reference's by-group sum over the concatenated per-cell tables (R/run_simulation.R:309-310); the
+// reference's "I.up rows, then I.pd rows" order inside one cell cannot matter for the same reason.
+// Finally: NaN -> 0, add, clamp (:315-319).  (The first version kept the accumulators in registers
+// and routed every contribution to its owner lane by shuffle: 1 600 instructions per field point.)
+template <int COLS>
 __global__ void __launch_bounds__(256)
 k_scatter(double *__restrict__ buf, const int64_t col_stride, const int64_t buf_stride,
           const int32_t *__restrict__ cur, const int32_t *__restrict__ seg_start,
@@ -473,74 +481,62 @@ k_scatter(double *__restrict__ buf, const int64_t col_stride, const int64_t buf_
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (t >= n_seg) return;
     const unsigned full = 0xffffffffu;
-    // routing table of this warp: slot = column relative to c0, value = (stamp << 5) | source lane
-    __shared__ int s_route[8][32 * CPL];
-    int *route = s_route[threadIdx.x >> 5];
+    __shared__ double s_sum[8][COLS];
+    __shared__ uint8_t s_hit[8][COLS];
+    double *sum = s_sum[threadIdx.x >> 5];
+    uint8_t *hit = s_hit[threadIdx.x >> 5];
 #pragma unroll
-    for (int u = 0; u < CPL; u++) route[lane + 32 * u] = -1;
+    for (int u = lane; u < COLS; u += 32) { sum[u] = 0.0; hit[u] = 0; }
     __syncwarp();
-    double sum[CPL];
-    unsigned touched = 0;
-#pragma unroll
-    for (int u = 0; u < CPL; u++) sum[u] = 0.0;
     const int q = seg_fq[t];
-    int stamp = 0;
     const int r_begin = seg_start[t], r_end = seg_start[t + 1];
     for (int rb = r_begin; rb < r_end; rb += 32) {
-    // the per-cell quantities of up to 32 incident cells are fetched by the lanes in parallel (one
-    // chain of dependent loads for all of them instead of one per cell), then handed out by shuffle
-    double l_ak = 0.0, l_frac = 0.0;
-    long long l_e0 = 0;
-    int l_ne = 0;
-    if (rb + lane < r_end) {
-        const int k = t_entry[rb + lane];
-        const int i = ecell[k];
-        l_ak = acc[k];
-        l_frac = __ddiv_rn(__dsub_rn(dmax[i], dist[k]), fsum[i]);   // :729-730
-        l_e0 = ex_ptr[i];
-        l_ne = (int)(ex_ptr[i + 1] - l_e0);
-    }
-    const int nr = min(32, r_end - rb);
-    for (int rr = 0; rr < nr; rr++) {
-        const double ak = __shfl_sync(full, l_ak, rr);
-        const double frac = __shfl_sync(full, l_frac, rr);
-        const int64_t e0 = __shfl_sync(full, l_e0, rr);
-        const int ne = __shfl_sync(full, l_ne, rr);
-        for (int base = 0; base < ne; base += 32, stamp++) {
-            const int m = min(32, ne - base);
-            double d = 0.0;
-            if (lane < m) {
-                const int64_t e = e0 + base + lane;
-                const int c = ex_cpd[e] - 1;
-                const double ex = ex_flx[e];
-                if (c >= c0 && c < c0 + 32 * CPL && c < n_cols && ex != 0.0 && ex == ex) {
-                    if (ex < 0) {
-                        const double cv = buf[(int64_t)cur[c] * buf_stride + (int64_t)c * col_stride + q];
-                        const double fpf = __dmul_rn(__dmul_rn(__ddiv_rn(cv, 1000.0), field_vol), ak);
-                        const double am = __ddiv_rn(fpf, ex_cs[e]);                    // :696
-                        d = __ddiv_rn(__ddiv_rn(__dmul_rn(am, ex), 1e12), vol_l);      // :707-708
-                    } else {
-                        d = __dmul_rn(frac, ex_cs[e]);                                 // :732-734
+        // the per-cell quantities of up to 32 incident cells are fetched by the lanes in parallel (one
+        // chain of dependent loads for all of them instead of one per cell), then handed out by shuffle
+        double l_ak = 0.0, l_frac = 0.0;
+        long long l_e0 = 0;
+        int l_ne = 0;
+        if (rb + lane < r_end) {
+            const int k = t_entry[rb + lane];
+            const int i = ecell[k];
+            l_ak = acc[k];
+            l_frac = __ddiv_rn(__dsub_rn(dmax[i], dist[k]), fsum[i]);   // :729-730
+            l_e0 = ex_ptr[i];
+            l_ne = (int)(ex_ptr[i + 1] - l_e0);
+        }
+        const int nr = min(32, r_end - rb);
+        for (int rr = 0; rr < nr; rr++) {
+            const double ak = __shfl_sync(full, l_ak, rr);
+            const double frac = __shfl_sync(full, l_frac, rr);
+            const int64_t e0 = __shfl_sync(full, l_e0, rr);
+            const int ne = __shfl_sync(full, l_ne, rr);
+            for (int base = 0; base < ne; base += 32) {
+                if (base + lane < ne) {
+                    const int64_t e = e0 + base + lane;
+                    const int c = ex_cpd[e] - 1;
+                    const double ex = ex_flx[e];
+                    if (c >= c0 && c < c0 + COLS && c < n_cols && ex != 0.0 && ex == ex) {
+                        double d;
+                        if (ex < 0) {
+                            const double cv = buf[(int64_t)cur[c] * buf_stride + (int64_t)c * col_stride + q];
+                            const double fpf = __dmul_rn(__dmul_rn(__ddiv_rn(cv, 1000.0), field_vol), ak);
+                            const double am = __ddiv_rn(fpf, ex_cs[e]);                    // :696
+                            d = __ddiv_rn(__ddiv_rn(__dmul_rn(am, ex), 1e12), vol_l);      // :707-708
+                        } else {
+                            d = __dmul_rn(frac, ex_cs[e]);                                 // :732-734
+                        }
+                        sum[c - c0] = __dadd_rn(sum[c - c0], d);
+                        hit[c - c0] = 1;
                     }
-                    route[c - c0] = (stamp << 5) | lane;
                 }
+                __syncwarp();
             }
-            __syncwarp();
-#pragma unroll
-            for (int u = 0; u < CPL; u++) {
-                const int rt = route[lane + 32 * u];
-                const bool hit = rt >= 0 && (rt >> 5) == stamp;
-                const double dx = __shfl_sync(full, d, hit ? (rt & 31) : 0);
-                if (hit) { sum[u] = __dadd_rn(sum[u], dx); touched |= 1u << u; }
-            }
-            __syncwarp();
         }
     }
-    }
 #pragma unroll
-    for (int u = 0; u < CPL; u++) {
-        const int c = c0 + lane + 32 * u;
-        if (!((touched >> u) & 1u) || c >= n_cols) continue;
+    for (int u = lane; u < COLS; u += 32) {
+        const int c = c0 + u;
+        if (!hit[u] || c >= n_cols) continue;
         if (is_const && is_const[c]) continue;                          // :311-312
         double d = sum[u];
         if (d != d) d = 0.0;                                             // :315
@@ -843,11 +839,10 @@ int eut_cells_gather(eut_cells *c, eut_field *f, double field_vol, double *fmol_
     EUT_TRY(build_gather_order(c, 0));
     EUT_CUDA(cudaStreamSynchronize(0));  // list construction runs on the legacy stream
     constexpr int G = 8, EPL = 5;
-    const int n_groups = (int)((f->C + G - 1) / G);
-    const int64_t n_warps = c->M * n_groups;
+    const int64_t n_warps = c->M;
     k_gather<G, EPL><<<(unsigned)((n_warps * 32 + 255) / 256), 256, 0, f->stream>>>(
         f->d_buf, c->plan->Np, f->C * c->plan->Np, f->d_cur, c->d_cell_ptr, c->d_g_idx, c->d_fq, c->d_acc,
-        field_vol, c->d_fmol, (int)c->M, (int)f->C, n_groups, c->d_cell_order);
+        field_vol, c->d_fmol, (int)c->M, (int)f->C, c->d_cell_order);
     f->launches++;
     EUT_CUDA(cudaGetLastError());
     if (fmol_host) {
@@ -908,10 +903,10 @@ int eut_cells_scatter(eut_cells *c, eut_field *f, double field_vol, const uint8_
                                                                 c->d_ex_cpd, c->d_ex_flx, c->d_ex_cs, (int)M,
                                                                 field_vol / 1e15);
     f->launches++;
-    constexpr int CPL = 2;
+    constexpr int COLS = 128;             // compound columns per pass (per-warp accumulators: 8 x 128 x 9 B)
     const double vol_l = field_vol / 1e15;
-    for (int c0 = 0; c0 < f->C; c0 += 32 * CPL) {
-        k_scatter<CPL><<<(unsigned)((c->n_seg * 32 + 255) / 256), 256, 0, s>>>(
+    for (int c0 = 0; c0 < f->C; c0 += COLS) {
+        k_scatter<COLS><<<(unsigned)((c->n_seg * 32 + 255) / 256), 256, 0, s>>>(
             f->d_buf, c->plan->Np, bs, f->d_cur, c->d_seg_start, c->d_seg_fq, c->d_t_entry, c->d_ecell,
             c->d_dist, c->d_acc, c->d_dmax, c->d_fsum, field_vol, vol_l, c->d_ex_ptr, c->d_ex_cpd,
             c->d_ex_flx, c->d_ex_cs, d_const, (int)c->n_seg, c0, (int)f->C);

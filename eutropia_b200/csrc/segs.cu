@@ -225,17 +225,17 @@ int build_segs(eut_plan *p, const SegParams &sp)
     // cells per piece: s = 8).  Ragged tiles (polygon border: rows start and end anywhere) get gap
     // cells after each piece, 0..15 of them, and the step s that needs the fewest.  Gap cells are
     // never read as neighbours, hold 0, and cost their share of HBM traffic (n_padded vs n_points).
-    // Row colours: rows of one layer alternate (2-colouring of the row adjacency without the pair
-    // flag, i.e. the C / D relation).  A row and the row one of its streams reads then differ by a
-    // colour that is the same for all rows of its layer, as long as no raster row is missing inside
-    // the tile -- which is what "all streams move together" needs.
-    std::vector<int8_t> colour(NR, -1);
-    int64_t colour_clash = 0;
+    // Row index inside its layer: rows linked by the C / D relation (row adjacency without the pair
+    // flag) are one apart, the one with the higher ids above.  A row and the row one of its streams
+    // reads then differ by an index offset that is the same for all rows of its layer, as long as no
+    // raster row is missing inside the tile -- which is what "all streams move together" needs.
+    std::vector<int32_t> krow(NR, INT32_MIN);
+    int64_t krow_clash = 0;
     {
         std::vector<int32_t> stack;
         for (int32_t seed = 0; seed < NR; seed++) {
-            if (colour[seed] >= 0) continue;
-            colour[seed] = 0;
+            if (krow[seed] != INT32_MIN) continue;
+            krow[seed] = 0;
             stack.push_back(seed);
             while (!stack.empty()) {
                 const int32_t r = stack.back();
@@ -243,10 +243,25 @@ int build_segs(eut_plan *p, const SegParams &sp)
                 for (int64_t a = ra.adj_ptr[r]; a < ra.adj_ptr[r + 1]; a++) {
                     if (ra.adj_pair[a]) continue;
                     const int32_t rr = ra.adj_row[a];
-                    if (colour[rr] < 0) { colour[rr] = (int8_t)(1 - colour[r]); stack.push_back(rr); }
-                    else if (colour[rr] == colour[r]) colour_clash++;
+                    const int32_t want = krow[r] + (rr > r ? 1 : -1);
+                    if (krow[rr] == INT32_MIN) { krow[rr] = want; stack.push_back(rr); }
+                    else if (krow[rr] != want) krow_clash++;
                 }
             }
+        }
+    }
+    // Residue step per strip (pad_rows 3): position - u == step * krow (mod 16).  Full-width pieces
+    // (8 segments) pack two rows per half warp with step 8 and need no gaps; narrow strips (polygon
+    // border) need more distinct row residues to fill 16 lanes with distinct bank pairs: step 4 / 2 / 1.
+    std::vector<int8_t> strip_step(P, 8);
+    if (sp.pad_rows == 3) {
+        std::vector<std::vector<int32_t>> widths(P);
+        for (int32_t a = 0; a < P; a++) widths[pieces[a].strip].push_back((pieces[a].count + R - 1) / R);
+        for (int32_t st = 0; st < P; st++) {
+            if (widths[st].empty()) continue;
+            std::nth_element(widths[st].begin(), widths[st].begin() + widths[st].size() / 2, widths[st].end());
+            const int32_t med = widths[st][widths[st].size() / 2];
+            strip_step[st] = med >= 8 ? 8 : (med >= 4 ? 4 : (med >= 2 ? 2 : 1));
         }
     }
     S.tile_start.assign(1, 0);
@@ -278,12 +293,12 @@ int build_segs(eut_plan *p, const SegParams &sp)
                 }
             }
             if (sp.pad_rows == 3) {
-                // global rule: position - u == 8 * colour(row) (mod 16) for every piece of the field, so
-                // that the rows of OTHER tiles (halo) keep the same relation; the image keeps
+                // global rule: position - u == step * krow (mod 16) for every piece of the strip, so that
+                // the rows of OTHER tiles (halo) keep the same relation; the image keeps
                 // cell == position (mod 16).  The gap sits in front of a piece.
                 for (int32_t k = k0; k < k1; k++) {
                     const Piece &pc = pieces[ord[k]];
-                    const int32_t want = ((u_of(pc.first) + 8 * std::max<int>(colour[ra.row_of[pc.first]], 0)) % 16 + 16) % 16;
+                    const int32_t want = (int32_t)((((int64_t)u_of(pc.first) + (int64_t)strip_step[pc.strip] * krow[ra.row_of[pc.first]]) % 16 + 16) % 16);
                     const int32_t g = (((want - pos) % 16) + 16) % 16;
                     pos += g; total_gap += g;
                     if (k == k0) tile_t0.push_back(pos);
@@ -303,8 +318,8 @@ int build_segs(eut_plan *p, const SegParams &sp)
             S.tile_start.push_back(pos);
         }
         if (getenv("EUT_TRACE"))
-            fprintf(stderr, "[eut] segment planner: %lld gap cells (%.2f %%), %lld colour clashes\n", (long long)total_gap,
-                    100.0 * (double)total_gap / (double)N, (long long)colour_clash);
+            fprintf(stderr, "[eut] segment planner: %lld gap cells (%.2f %%), %lld row index clashes\n", (long long)total_gap,
+                    100.0 * (double)total_gap / (double)N, (long long)krow_clash);
     }
     p->Np = (((int64_t)S.tile_start.back() + kPadPoints - 1) / kPadPoints) * kPadPoints;
     p->iperm.assign(p->Np, -1);
@@ -370,8 +385,21 @@ int build_segs(eut_plan *p, const SegParams &sp)
             }
             h = e;
         }
-        for (size_t h = 0; h < halo.size(); h++)
-            if (halo_off[h] < 0) { halo_off[h] = next++; single.push_back({halo[h], halo_off[h]}); halo_total++; }
+        {
+            // lone points (row-end neighbours from the next tile column).  Under the global residue
+            // rule they keep cell == position (mod 16) too -- a 16-column grid, column = residue -- so
+            // that the end-cell loads of a half warp stay on distinct bank pairs.
+            int32_t fill[16] = {0};
+            if (keep_res) next = (next + 15) / 16 * 16;
+            for (size_t h = 0; h < halo.size(); h++) {
+                if (halo_off[h] >= 0) continue;
+                if (keep_res) { const int32_t r = halo[h] & 15; halo_off[h] = next + 16 * fill[r] + r; fill[r]++; }
+                else halo_off[h] = next++;
+                single.push_back({halo[h], halo_off[h]});
+                halo_total++;
+            }
+            if (keep_res) next += 16 * *std::max_element(fill, fill + 16);
+        }
         next += R + 2;                              // masked lanes of short segments read past their stream
         if (next > sp.max_img_points || next * 8 > 65535) {
             if (getenv("EUT_TRACE"))

@@ -366,6 +366,8 @@ int launch_seg(eut_field *f, int n_act, int substep)
     if (S.R == 7) {
         if (S.max_tile_segs <= 224) {
             if (shape == 1) return launch_seg_t<7, 1, 7, 3, 2, 2>(f, n_act, substep);
+            if (shape == 5) return launch_seg_t<7, 1, 7, 6, 3, 1>(f, n_act, substep);
+            if (shape == 6) return launch_seg_t<7, 1, 7, 4, 4, 1>(f, n_act, substep);
             if (nb == 2) return launch_seg_t<7, 1, 7, 2, 2, 2>(f, n_act, substep);
             if (nb == 4) return launch_seg_t<7, 1, 7, 4, 2, 2>(f, n_act, substep);
             return launch_seg_t<7, 1, 7, 3, 3, 2>(f, n_act, substep);
