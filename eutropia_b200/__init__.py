@@ -3,7 +3,9 @@ cell<->field exchange path, behind the reference's own call surface.
 
   rcpp_api     diffChange / diffChangePar           (one-shot tier; R/RcppExports.R:4-10)
   session      Plan / Field / Cells                 (resident tier over the C ABI)
-  environment  GrowthEnvironment.diffuse_compoundsPar (R/growthEnvironment.R:367-437)
+  environment  GrowthEnvironment.diffuse_compoundsPar / diffuse_compounds / exoenzyme_activity
+               (R/growthEnvironment.R:280-437, R/run_simulation.R:337-371)
+  exchange     scavenge_compounds / adjust_uptake   (R/scavenge_compounds.R, R/adjust_uptake.R)
   mesh         field points + mat.in / mat.out in the reference's format (setup, host)
   synth        synthetic inputs for tests and the bench
 
@@ -13,9 +15,10 @@ from . import _lib
 from ._lib import EutropiaError, EutropiaIndexError
 from .rcpp_api import diffChange, diffChangePar
 from .session import Cells, Field, Plan
-from .environment import GrowthEnvironment, diffusion_niter
+from .environment import Exoenzyme, GrowthEnvironment, diffusion_niter
+from .exchange import adjust_uptake, scavenge_compounds
 from . import mesh, synth
 
-__all__ = ["diffChange", "diffChangePar", "Plan", "Field", "Cells", "GrowthEnvironment",
-           "diffusion_niter", "mesh", "synth", "EutropiaError", "EutropiaIndexError"]
+__all__ = ["diffChange", "diffChangePar", "Plan", "Field", "Cells", "GrowthEnvironment", "Exoenzyme",
+           "diffusion_niter", "adjust_uptake", "scavenge_compounds", "mesh", "synth", "EutropiaError", "EutropiaIndexError"]
 __version__ = "0.1.0"

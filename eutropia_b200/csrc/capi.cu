@@ -243,6 +243,36 @@ int eut_field_fill_column(eut_field *f, int32_t col, double value)
     return launch_fill_column(f, col - 1, value);
 }
 
+int eut_field_exoenzyme_catalysis(eut_field *conc, eut_field *exo, int32_t exo_col, double kcat, double km,
+                                  const int32_t *met_cols, const double *stoich, int32_t n_mets,
+                                  const uint8_t *is_constant, double delta_time)
+{
+    clear_error();
+    if (!conc || !exo || conc->plan != exo->plan || !met_cols || !stoich) {
+        set_error("eut_field_exoenzyme_catalysis: NULL argument, or the two fields do not share a plan");
+        return EUT_ERR_ARG;
+    }
+    if (exo_col < 1 || exo_col > exo->C) { set_error("index out of bounds: exoenzyme column %d of %lld", exo_col, (long long)exo->C); return EUT_ERR_INDEX; }
+    if (n_mets < 1 || n_mets > max_exo_mets()) { set_error("eut_field_exoenzyme_catalysis: %d metabolites (1..%d supported)", n_mets, max_exo_mets()); return EUT_ERR_UNSUPPORTED; }
+    for (int32_t i = 0; i < n_mets; i++)
+        if (met_cols[i] < 1 || met_cols[i] > conc->C) {
+            // match(exec@mets, compounds) = NA in the reference -> subscript error
+            set_error("index out of bounds: metabolite column %d of %lld", met_cols[i], (long long)conc->C);
+            return EUT_ERR_INDEX;
+        }
+    EUT_TRY(ensure_device(conc->plan->device));
+    return field_exoenzyme_catalysis(conc, exo, exo_col, kcat, km, met_cols, stoich, n_mets, is_constant, delta_time);
+}
+
+int eut_field_scale_column(eut_field *f, int32_t col, double factor)
+{
+    clear_error();
+    if (!f) return EUT_ERR_ARG;
+    if (col < 1 || col > f->C) { set_error("eut_field_scale_column: column %d out of bounds", col); return EUT_ERR_INDEX; }
+    EUT_TRY(ensure_device(f->plan->device));
+    return field_scale_column(f, col - 1, factor);
+}
+
 // ---- one-shot tier ---------------------------------------------------------------------------
 namespace {
 

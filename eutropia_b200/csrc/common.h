@@ -235,4 +235,10 @@ int launch_permute_out(eut_field *f, double *d_stage, int64_t ld, const int32_t 
 int launch_column_stats(eut_field *f, const int32_t *d_cur);
 const char *last_error_cstr();
 int launch_fill_column(eut_field *f, int32_t col0, double value);
+// round.cu
+int field_exoenzyme_catalysis(eut_field *cf, eut_field *ef, int32_t exo_col, double kcat, double km,
+                              const int32_t *met_cols, const double *stoich, int32_t n_mets,
+                              const uint8_t *is_constant, double delta_time);
+int field_scale_column(eut_field *f, int32_t col0, double factor);
+int max_exo_mets();
 }  // namespace eut

@@ -178,6 +178,20 @@ class Field:
         check(_lib.lib().eut_field_fill_column(self._h, int(col), float(value)))
 
     # -- halo support for slab sharding (eutropia_b200/slab.py) ---------------------------------
+    def scale_column(self, col: int, factor: float):
+        """column *= factor (exoenzyme decay, R/run_simulation.R:367-371)."""
+        check(_lib.lib().eut_field_scale_column(self._h, int(col), float(factor)))
+
+    def exoenzyme_catalysis(self, exo: "Field", exo_col: int, kcat: float, km: float, met_cols, stoich,
+                            is_constant, delta_time: float):
+        """R/run_simulation.R:343-364 on the device; `self` is the concentration field."""
+        mets = _i32(met_cols)
+        st = _f64c(stoich)
+        isc = None if is_constant is None else np.ascontiguousarray(is_constant, dtype=np.uint8)
+        check(_lib.lib().eut_field_exoenzyme_catalysis(self._h, exo._h, int(exo_col), float(kcat), float(km),
+                                                       ptr(mets), ptr(st), mets.shape[0], ptr(isc),
+                                                       float(delta_time)))
+
     def halo_set(self, send_ids, recv_ids):
         s, r = _i32(send_ids), _i32(recv_ids)
         check(_lib.lib().eut_field_halo_set(self._h, ptr(s), s.shape[0], ptr(r), r.shape[0]))

@@ -211,6 +211,17 @@ EUT_API int eut_field_set_option(eut_field *field, const char *name, int64_t val
  * R/growthEnvironment.R:372, :393-401): writes min, max, mean of every column (arrays of n_cols). */
 EUT_API int eut_field_column_stats(eut_field *field, double *col_min, double *col_max,
                                    double *col_mean);
+/* Exoenzyme catalysis on the device (R/run_simulation.R:343-364), point by point:
+ *   vmax = kcat * E / 1e6;  S_t = km * W0( S_0/km * exp((S_0 - vmax * delta_time * 60 * 60) / km) );
+ *   conc[, met_cols[i]] += stoich[i] * (S_0 - S_t)   for every i whose column is not constant,
+ * E = column `exo_col` of `exo` (exoenzymes.conc, nM), S_0 = column met_cols[0] of `conc` (read
+ * before any update).  Both fields must share a plan.  is_constant: n_cols(conc) flags or NULL. */
+EUT_API int eut_field_exoenzyme_catalysis(eut_field *conc, eut_field *exo, int32_t exo_col, double kcat,
+                                          double km, const int32_t *met_cols, const double *stoich,
+                                          int32_t n_mets, const uint8_t *is_constant, double delta_time);
+/* column *= factor (exoenzyme decay, E * exp(-lambda * deltaTime), R/run_simulation.R:367-371; the
+ * factor is evaluated by the caller in binary64 like R does). */
+EUT_API int eut_field_scale_column(eut_field *field, int32_t col, double factor);
 /* Overwrite a column with one value (D = Inf -> column mean, R/growthEnvironment.R:393-401). */
 EUT_API int eut_field_fill_column(eut_field *field, int32_t col, double value);
 

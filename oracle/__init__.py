@@ -19,7 +19,7 @@ _lib = None
 
 def build(force: bool = False) -> str:
     """Compile the oracle with gcc (see oracle/Makefile)."""
-    srcs = [os.path.join(_HERE, f) for f in ("diffchange_oracle.c", "cellfield_oracle.c", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("diffchange_oracle.c", "cellfield_oracle.c", "exoenzyme_oracle.c", "Makefile")]
     stale = (not os.path.exists(_LIB_PATH)) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
     if force or stale:
@@ -48,6 +48,13 @@ def lib() -> C.CDLL:
         L.eut_oracle_scatter.argtypes = [dp, sz, sz, C.c_void_p, lp, ip, dp, dp, sz, C.c_double,
                                          lp, ip, dp]
         L.eut_oracle_scatter.restype = C.c_int
+        L.oracle_lambert_w0.argtypes = [C.c_double]
+        L.oracle_lambert_w0.restype = C.c_double
+        L.oracle_exoenzyme_catalysis.argtypes = [dp, C.c_int64, C.c_int64, dp, C.c_int64, C.c_int32, C.c_double,
+                                                 C.c_double, ip, dp, C.c_int32, C.c_void_p, C.c_double]
+        L.oracle_exoenzyme_catalysis.restype = C.c_int
+        L.oracle_exoenzyme_decay.argtypes = [dp, C.c_int64, C.c_int32, C.c_double, C.c_double]
+        L.oracle_exoenzyme_decay.restype = None
         _lib = L
     return _lib
 
@@ -164,4 +171,32 @@ def scatter(conc, is_constant, cell_ptr, field_id, field_dist, acc_prop, field_v
     _check(lib().eut_oracle_scatter(_p(out), out.shape[0], out.shape[1], _p(isc), _p(ptr), _p(fid),
                                     _p(fd), _p(acc), ptr.shape[0] - 1, float(field_vol),
                                     _p(exp_), _p(exc), _p(exf)))
+    return out
+
+
+def lambertW0(x):
+    """Principal branch of the Lambert W function (lamW::lambertW0), long double Halley iteration."""
+    x = np.asarray(x, dtype=np.float64)
+    f = lib().oracle_lambert_w0
+    return np.vectorize(lambda v: f(float(v)), otypes=[np.float64])(x)
+
+
+def exoenzyme_catalysis(conc, exo_conc, k, kcat, km, mets, stoich, is_constant, delta_time):
+    """R/run_simulation.R:343-364 for exoenzyme `k` (1-based column of exo_conc); returns the new
+    concentration matrix."""
+    out = np.array(conc, dtype=np.float64, order="F", copy=True)
+    exo = _f64(exo_conc)
+    mets = np.ascontiguousarray(mets, dtype=np.int32)
+    st = np.ascontiguousarray(stoich, dtype=np.float64)
+    isc = None if is_constant is None else np.ascontiguousarray(is_constant, dtype=np.uint8)
+    _check(lib().oracle_exoenzyme_catalysis(_p(out), out.shape[0], out.shape[1], _p(exo), exo.shape[1],
+                                            int(k), float(kcat), float(km), _p(mets), _p(st),
+                                            mets.shape[0], _p(isc), float(delta_time)))
+    return out
+
+
+def exoenzyme_decay(exo_conc, k, lam, delta_time):
+    """R/run_simulation.R:367-371 for column `k` (1-based); returns the new exoenzyme matrix."""
+    out = np.array(exo_conc, dtype=np.float64, order="F", copy=True)
+    lib().oracle_exoenzyme_decay(_p(out), out.shape[0], int(k), float(lam), float(delta_time))
     return out
