@@ -5,6 +5,9 @@
 #include <memory>
 #include <mutex>
 
+#include <functional>
+#include <future>
+
 #include "common.h"
 
 using namespace eut;
@@ -284,6 +287,7 @@ struct CachedPlan {
     eut_field *field = nullptr;
     int64_t field_cols = 0;
     uint64_t stamp = 0;
+    const void *last_adj = nullptr, *last_nn = nullptr;   // the arrays of the last call (a hint, never trusted)
 };
 
 std::mutex g_mu;
@@ -300,15 +304,24 @@ void drop(CachedPlan &c)
 
 // R calls diffChangePar every round with the same mat.in / mat.out (R/growthEnvironment.R:385-390);
 // the graph analysis and its device tables are kept and recognised by content hash.
-int get_cached(const int32_t *adj, int64_t n_edges, const int32_t *nn, int64_t n_nn, int64_t n_rows,
-               int device, CachedPlan **out)
+struct GraphHash { uint64_t he = 0, hn = 0; };
+
+GraphHash hash_graph(const int32_t *adj, int64_t n_edges, const int32_t *nn, int64_t n_nn)
 {
-    const uint64_t he = hash_bytes(adj, (size_t)n_edges * 2 * sizeof(int32_t), 0x5eedull);
-    const uint64_t hn = hash_bytes(nn, (size_t)n_nn * 2 * sizeof(int32_t), 0xfeedull);
+    GraphHash h;
+    h.he = hash_bytes(adj, (size_t)n_edges * 2 * sizeof(int32_t), 0x5eedull);
+    h.hn = hash_bytes(nn, (size_t)n_nn * 2 * sizeof(int32_t), 0xfeedull);
+    return h;
+}
+
+int get_cached(const GraphHash &h, const int32_t *adj, int64_t n_edges, const int32_t *nn, int64_t n_nn,
+               int64_t n_rows, int device, CachedPlan **out)
+{
     for (auto &c : g_cache)
-        if (c.h_edges == he && c.h_nn == hn && c.n_edges == n_edges && c.n_nn == n_nn &&
+        if (c.h_edges == h.he && c.h_nn == h.hn && c.n_edges == n_edges && c.n_nn == n_nn &&
             c.n_rows == n_rows && c.device == device) {
             c.stamp = ++g_stamp;
+            c.last_adj = adj; c.last_nn = nn;
             *out = &c;
             return EUT_OK;
         }
@@ -319,8 +332,9 @@ int get_cached(const int32_t *adj, int64_t n_edges, const int32_t *nn, int64_t n
         g_cache.erase(it);
     }
     CachedPlan c;
-    c.h_edges = he; c.h_nn = hn; c.n_edges = n_edges; c.n_nn = n_nn; c.n_rows = n_rows;
+    c.h_edges = h.he; c.h_nn = h.hn; c.n_edges = n_edges; c.n_nn = n_nn; c.n_rows = n_rows;
     c.device = device; c.stamp = ++g_stamp;
+    c.last_adj = adj; c.last_nn = nn;
     c.plan = new eut_plan();
     int rc = plan_build(c.plan, adj, adj + n_edges, n_edges, nn, nn + n_nn, n_nn, n_rows, device,
                         EUT_ORDER_AUTO);
@@ -331,6 +345,92 @@ int get_cached(const int32_t *adj, int64_t n_edges, const int32_t *nn, int64_t n
     }
     g_cache.push_back(c);
     *out = &g_cache.back();
+    return EUT_OK;
+}
+
+constexpr int kRetry = -1000;   // internal: the speculated plan was not the right one
+
+// The column pipeline on the plan / field of `cp`.  `verify` (may be empty) is called once, after the
+// first chunks have been queued and before anything is written to conc_out; when it returns false
+// the streams are drained and kRetry is returned (nothing has been written to conc_out).
+int run_pipeline(CachedPlan *cp, const double *conc_in, int64_t n_rows, int64_t n_cols, const int32_t *niter,
+                 const int32_t *indvar, const std::vector<int64_t> &act, double *conc_out,
+                 const std::function<bool()> &verify)
+{
+    if (!cp->field || cp->field_cols != n_cols) {
+        if (cp->field) field_destroy(cp->field);
+        cp->field = nullptr;
+        EUT_TRY(field_create(&cp->field, cp->plan, n_cols));
+        cp->field_cols = n_cols;
+    }
+    eut_field *f = cp->field;
+    // Pipeline over chunks of active columns: H2D(g+1) | substeps(g) | D2H(g-1) on three streams.
+    // The call lasts  H2D(first chunk) + all substeps + D2H(last chunk), and a launch over few columns
+    // is less efficient than one over many (tools/cols_scaling.py): the chunks ramp up 1/8, 3/8, 1, ...
+    // of the staging buffer and down again, so that the ends are short and the bulk runs wide.
+    const int64_t chunk = f->stage_cols;
+    std::vector<size_t> cuts;
+    {
+        const size_t n = act.size();
+        const size_t h1 = (size_t)std::max<int64_t>(1, chunk / 8), h2 = (size_t)std::max<int64_t>(1, 3 * chunk / 8);
+        std::vector<size_t> sizes;
+        auto middle = [&](size_t m) {
+            if (m == 0) return;
+            const size_t parts = (m + (size_t)chunk - 1) / (size_t)chunk;
+            for (size_t k = 0; k < parts; k++) sizes.push_back(m / parts + (k < m % parts ? 1 : 0));
+        };
+        if (n > 2 * (h1 + h2)) { sizes.push_back(h1); sizes.push_back(h2); middle(n - 2 * (h1 + h2)); sizes.push_back(h2); sizes.push_back(h1); }
+        else if (n > 2 * h1) { sizes.push_back(h1); middle(n - 2 * h1); sizes.push_back(h1); }
+        else middle(n);
+        cuts.push_back(0);
+        for (size_t sz : sizes) cuts.push_back(cuts.back() + sz);
+    }
+    struct Pending { std::vector<int32_t> cols; bool contiguous; };
+    std::vector<Pending> pending;
+    bool verified = !verify;
+    auto download = [&](const Pending &pd) -> int {
+        if (pd.contiguous) {
+            EUT_TRY(field_download_async(f, conc_out + (size_t)(pd.cols[0] - 1) * n_rows, n_rows, pd.cols.data(), (int64_t)pd.cols.size()));
+        } else {
+            for (size_t j = 0; j < pd.cols.size(); j++)
+                EUT_TRY(field_download_async(f, conc_out + (size_t)(pd.cols[j] - 1) * n_rows, n_rows, &pd.cols[j], 1));
+        }
+        return EUT_OK;
+    };
+    auto check_now = [&]() -> int {
+        if (verified) return EUT_OK;
+        if (!verify()) {
+            cudaStreamSynchronize(f->copy_stream); cudaStreamSynchronize(f->stream); cudaStreamSynchronize(f->down_stream);
+            return kRetry;
+        }
+        verified = true;
+        for (const Pending &pd : pending) EUT_TRY(download(pd));
+        pending.clear();
+        return EUT_OK;
+    };
+    std::vector<int32_t> nit;
+    for (size_t ci = 0; ci + 1 < cuts.size(); ci++) {
+        const size_t a0 = cuts[ci], a1 = cuts[ci + 1];
+        if (a1 <= a0) continue;
+        Pending pd;
+        nit.clear();
+        for (size_t a = a0; a < a1; a++) { pd.cols.push_back(indvar[act[a]]); nit.push_back(niter[act[a]]); }
+        // host column j of this chunk is conc_in column cols[j]-1: upload one column at a time when
+        // they are not contiguous, as one 2-D copy when they are
+        pd.contiguous = true;
+        for (size_t j = 1; j < pd.cols.size(); j++) pd.contiguous &= (pd.cols[j] == pd.cols[j - 1] + 1);
+        if (pd.contiguous) {
+            EUT_TRY(field_upload(f, conc_in + (size_t)(pd.cols[0] - 1) * n_rows, n_rows, pd.cols.data(), (int64_t)pd.cols.size()));
+        } else {
+            for (size_t j = 0; j < pd.cols.size(); j++)
+                EUT_TRY(field_upload(f, conc_in + (size_t)(pd.cols[j] - 1) * n_rows, n_rows, &pd.cols[j], 1));
+        }
+        EUT_TRY(field_diffuse(f, nit.data(), pd.cols.data(), (int64_t)pd.cols.size()));
+        if (!verified && ci >= 1) EUT_TRY(check_now());      // the hash has had two chunks' worth of time
+        if (verified) EUT_TRY(download(pd));
+        else pending.push_back(std::move(pd));
+    }
+    EUT_TRY(check_now());
     return EUT_OK;
 }
 
@@ -353,17 +453,6 @@ int oneshot_run(const int32_t *adj, int64_t n_edges, const int32_t *nn, int64_t 
     static const bool trace = getenv("EUT_TRACE") != nullptr;
     const double t_begin = now_ms();
     EUT_TRY(ensure_device(device));
-    CachedPlan *cp = nullptr;
-    EUT_TRY(get_cached(adj, n_edges, nn, n_nn, n_rows, device, &cp));
-    const double t_plan = now_ms();
-    if (!cp->field || cp->field_cols != n_cols) {
-        if (cp->field) field_destroy(cp->field);
-        cp->field = nullptr;
-        EUT_TRY(field_create(&cp->field, cp->plan, n_cols));
-        cp->field_cols = n_cols;
-    }
-    eut_field *f = cp->field;
-
     // active columns (validated by field_diffuse's rules before any work is queued)
     std::vector<int64_t> act;
     std::vector<uint8_t> is_act(std::max<int64_t>(n_cols, 1), 0);
@@ -380,49 +469,37 @@ int oneshot_run(const int32_t *adj, int64_t n_edges, const int32_t *nn, int64_t 
         is_act[indvar[i] - 1] = 1;
         act.push_back(i);
     }
-    // Pipeline over chunks of active columns: H2D(g+1) | substeps(g) | D2H(g-1) on three streams.
-    // The call lasts  H2D(first chunk) + all substeps + D2H(last chunk):  the first and the last
-    // chunk are kept small (a quarter of the staging buffer), the ones in between full size.
-    const int64_t chunk = f->stage_cols;
-    const int64_t small = std::max<int64_t>(1, chunk / 4);
-    std::vector<size_t> cuts;
-    {
-        const size_t n = act.size();
-        size_t a = 0;
-        cuts.push_back(0);
-        if (n > (size_t)(2 * small + chunk / 2)) {
-            a = (size_t)small; cuts.push_back(a);
-            while (n - a > (size_t)(chunk + small)) { a += (size_t)chunk; cuts.push_back(a); }
-            if (n - a > (size_t)small) { a = n - (size_t)small; cuts.push_back(a); }
-        } else {
-            while (n - a > (size_t)chunk) { a += (size_t)chunk; cuts.push_back(a); }
-        }
-        cuts.push_back(n);
+    // Which plan?  Decided by the content hash of the graph (83 MB at 1 M points: ~3 ms).  When the
+    // caller hands over the same arrays as last time -- R does, every round -- the hash is taken on
+    // another thread while the first chunks are already uploaded and diffused on the plan used last
+    // time; conc_out is not touched before the hash has confirmed the guess.
+    CachedPlan *guess = nullptr;
+    for (auto &c : g_cache)
+        if (c.last_adj == adj && c.last_nn == nn && c.n_edges == n_edges && c.n_nn == n_nn && c.n_rows == n_rows &&
+            c.device == device && c.field && c.field_cols == n_cols && (!guess || c.stamp > guess->stamp))
+            guess = &c;
+    int rc = kRetry;
+    GraphHash h;
+    bool have_hash = false;
+    if (guess && act.size() > 1 && !getenv("EUT_NO_SPECULATION")) {
+        std::future<GraphHash> fut = std::async(std::launch::async, hash_graph, adj, n_edges, nn, n_nn);
+        const uint64_t want_e = guess->h_edges, want_n = guess->h_nn;
+        rc = run_pipeline(guess, conc_in, n_rows, n_cols, niter, indvar, act, conc_out, [&]() {
+            h = fut.get(); have_hash = true;
+            return h.he == want_e && h.hn == want_n;
+        });
+        if (!have_hash) { h = fut.get(); have_hash = true; }      // error paths: never leave the thread behind
+        if (rc == EUT_OK) guess->stamp = ++g_stamp;
     }
-    std::vector<int32_t> cols, nit;
-    for (size_t ci = 0; ci + 1 < cuts.size(); ci++) {
-        const size_t a0 = cuts[ci], a1 = cuts[ci + 1];
-        if (a1 <= a0) continue;
-        cols.clear(); nit.clear();
-        for (size_t a = a0; a < a1; a++) { cols.push_back(indvar[act[a]]); nit.push_back(niter[act[a]]); }
-        // host column j of this chunk is conc_in column cols[j]-1: upload one column at a time when
-        // they are not contiguous, as one 2-D copy when they are
-        bool contiguous = true;
-        for (size_t j = 1; j < cols.size(); j++) contiguous &= (cols[j] == cols[j - 1] + 1);
-        if (contiguous) {
-            EUT_TRY(field_upload(f, conc_in + (size_t)(cols[0] - 1) * n_rows, n_rows, cols.data(), (int64_t)cols.size()));
-        } else {
-            for (size_t j = 0; j < cols.size(); j++)
-                EUT_TRY(field_upload(f, conc_in + (size_t)(cols[j] - 1) * n_rows, n_rows, &cols[j], 1));
-        }
-        EUT_TRY(field_diffuse(f, nit.data(), cols.data(), (int64_t)cols.size()));
-        if (contiguous) {
-            EUT_TRY(field_download_async(f, conc_out + (size_t)(cols[0] - 1) * n_rows, n_rows, cols.data(), (int64_t)cols.size()));
-        } else {
-            for (size_t j = 0; j < cols.size(); j++)
-                EUT_TRY(field_download_async(f, conc_out + (size_t)(cols[j] - 1) * n_rows, n_rows, &cols[j], 1));
-        }
+    const double t_plan = now_ms();
+    CachedPlan *cp = guess;
+    if (rc == kRetry) {
+        if (!have_hash) h = hash_graph(adj, n_edges, nn, n_nn);
+        EUT_TRY(get_cached(h, adj, n_edges, nn, n_nn, n_rows, device, &cp));
+        rc = run_pipeline(cp, conc_in, n_rows, n_cols, niter, indvar, act, conc_out, std::function<bool()>());
     }
+    if (rc != EUT_OK) return rc;
+    eut_field *f = cp->field;
     // columns the call does not touch are returned as they came (src/diffChange.cpp:34, :68)
     for (int64_t c = 0; c < n_cols; c++)
         if (!is_act[c] && n_rows > 0)
@@ -432,8 +509,8 @@ int oneshot_run(const int32_t *adj, int64_t n_edges, const int32_t *nn, int64_t 
     EUT_CUDA(cudaStreamSynchronize(f->stream));
     EUT_CUDA(cudaStreamSynchronize(f->down_stream));
     if (trace)
-        fprintf(stderr, "[eut] one-shot: plan lookup %.2f ms, enqueue %.2f ms, drain %.2f ms\n",
-                t_plan - t_begin, t_enq - t_plan, now_ms() - t_enq);
+        fprintf(stderr, "[eut] one-shot: plan lookup%s + first chunks %.2f ms, enqueue %.2f ms, drain %.2f ms\n",
+                guess && cp == guess ? " (speculated)" : "", t_plan - t_begin, t_enq - t_plan, now_ms() - t_enq);
     return EUT_OK;
 }
 

@@ -7,7 +7,7 @@
 
 namespace eut {
 
-static constexpr int64_t kStageBytes = 128ll << 20;  // per staging slot
+static constexpr int64_t kStageBytes = 256ll << 20;  // per staging slot (two up, two down)
 
 static int field_alloc(eut_field *f)
 {

@@ -204,3 +204,28 @@ def test_dispatcher_diffuse_compoundsPar(harbor_mesh):
     ref[:, 4] = conc[:, 4].mean()
     assert np.array_equal(got[:, [0, 1, 2, 3, 5]], ref[:, [0, 1, 2, 3, 5]])
     assert np.allclose(got[:, 4], ref[:, 4], rtol=1e-12)
+
+
+def test_one_shot_speculation_is_verified(small_mesh):
+    """The one-shot tier starts the first column chunks on the plan of the previous call while the
+    graph hash is still being taken (same array addresses as last time).  A graph that changed IN
+    PLACE must still be detected: the guess is discarded and the result follows the new graph."""
+    m = small_mesh
+    adj = np.require(m.mat_in.reshape(-1, 2), dtype=np.int32, requirements=["F", "A", "W", "O"]).copy(order="F")
+    nn = np.require(m.mat_out.reshape(-1, 2), dtype=np.int32, requirements=["F", "A"]).copy(order="F")
+    conc = synth.synthetic_concentrations(m.field_pts, 9, seed=11)
+    niter = [7] * 9
+    indvar = list(range(1, 10))
+    a = eb.diffChangePar(adj, nn, conc, niter, indvar)          # builds and caches the plan
+    b = eb.diffChangePar(adj, nn, conc, niter, indvar)          # same addresses: speculated
+    ref = oracle.diffChangePar(adj, nn, conc, niter, indvar, 2)
+    assert np.array_equal(a, ref) and np.array_equal(b, ref)
+    # rewire a handful of edges in place (same buffers, same sizes): drop them onto other sources
+    rng = np.random.default_rng(1)
+    rows = rng.choice(adj.shape[0], 40, replace=False)
+    adj[rows, 0] = rng.integers(1, m.nfields + 1, rows.size)
+    c = eb.diffChangePar(adj, nn, conc, niter, indvar)          # guess is wrong -> must fall back
+    ref2 = oracle.diffChangePar(adj, nn, conc, niter, indvar, 2)
+    assert np.array_equal(c, ref2) and not np.array_equal(c, ref)
+    d = eb.diffChangePar(adj, nn, conc, niter, indvar)          # and the new graph is now the guess
+    assert np.array_equal(d, ref2)
