@@ -162,3 +162,53 @@ def test_properties_at_scale():
     assert np.allclose(moved, want, rtol=1e-6, atol=1e-9)
     ref = oracle.scatter(conc, None, ptr, fid, fd, acc2, m.field_vol, ex_ptr, ex_cpd, ex_flx)
     assert close(after, ref, absol=1e-12 * np.abs(conc).max())
+
+
+def test_vignette_like_rounds():
+    """BASELINE.json configs[0] in shape: the Crossfeeding vignette's environment (`Petri_80`, field
+    size 1, 6 layers, vignettes/Crossfeeding.Rmd:31-33: 124 k points; 171 compound columns of which
+    19 are constant medium components, inst/extdata/medium.csv:2-20; 30 cells; D = 75, deltaTime
+    1/6 h -> 60 substeps), three rounds of  cell map -> claim -> gather -> (synthetic fluxes instead
+    of the FBA) -> scatter + clamp -> diffuse_compoundsPar  on the resident field, against the same
+    rounds composed from the oracle."""
+    from eutropia_b200 import environment, mesh as mesh_mod
+    m = mesh_mod.make_mesh("Petri_80", 1.0, 6)
+    assert 100_000 < m.nfields < 150_000
+    n_cols, n_const, n_cells = 171, 19, 30
+    rng = np.random.default_rng(80)
+    conc = np.zeros((m.nfields, n_cols))
+    conc[:, :n_const] = 1000.0                                   # constant medium components
+    conc[:, n_const:n_const + 7] = rng.uniform(0.5, 25.0, 7)     # the non-constant medium, uniform at t = 0
+    is_const = np.zeros(n_cols, dtype=bool); is_const[:n_const] = True
+    D = np.full(n_cols, 75.0)
+    env = environment.GrowthEnvironment(m, [f"cpd{i}" for i in range(n_cols)], conc, D, is_const)
+    vol, dt = m.field_vol, 1 / 6
+    ref = conc.copy()
+    cx, cy, size, scv = synth.place_cells(m, n_cells, seed=7)
+    for rnd in range(3):
+        cx = cx + rng.normal(0, 0.4, n_cells); cy = cy + rng.normal(0, 0.4, n_cells)      # cells drift
+        ex_ptr, ex_cpd, ex_flx = synth.synthetic_exchanges(n_cells, n_cols, 12, seed=100 + rnd)
+        ex_flx = ex_flx * 1e-3
+        # device
+        env.cells.build_lists(m.field_pts, cx, cy, size, scv)
+        env.cells.claim_rescale()
+        fmol = env.cells.gather(env.field, vol)
+        env.cells.scatter(env.field, vol, is_const, ex_ptr, ex_cpd, ex_flx)
+        env.diffuse_compoundsPar(dt, n_cores=4)
+        # oracle
+        ptr, fid, fd, acc = oracle.cellmap(m.field_pts, cx, cy, size, scv)
+        acc = oracle.claim(fid, acc, m.nfields)
+        d_ptr, d_fid, d_fd, d_acc = env.cells.get_lists()
+        assert np.array_equal(d_ptr, ptr) and np.array_equal(d_fid, fid)                     # index maps: bit-exact
+        rfmol = oracle.gather(ref, ptr, fid, acc, vol)
+        assert close(fmol, rfmol, rel=1e-11, absol=1e-12 * max(np.abs(rfmol).max(), 1e-300))
+        ref = oracle.scatter(ref, is_const, ptr, fid, fd, acc, vol, ex_ptr, ex_cpd, ex_flx)
+        sd_pos = (ref.max(0) > ref.min(0)) & ~is_const
+        ind = np.flatnonzero(sd_pos) + 1
+        niter = environment.diffusion_niter(D[ind - 1], dt, m.field_size)
+        assert np.all(niter == 60)
+        ref = oracle.diffChangePar(m.mat_in, m.mat_out, ref, niter.astype(np.int32), ind.astype(np.int32), 8)
+        got = env.concentrations
+        assert np.array_equal(got[:, :n_const], conc[:, :n_const])                           # constants never move
+        assert close(got, ref, absol=REL * 25.0), float(np.abs(got - ref).max())
+    assert ind.size > 12                                          # the diffusing set grows with the exchanges
