@@ -46,6 +46,18 @@ int eut_plan_create(eut_plan **out, const int32_t *from, const int32_t *to, int6
     return EUT_OK;
 }
 
+int eut_build_dcm(const double *pts, int64_t ld, int64_t n_points, double field_size, int device,
+                  int32_t *mat_in, int64_t cap, int64_t *n_edges, int32_t *mat_out)
+{
+    clear_error();
+    if (n_points < 0 || cap < 0 || !n_edges || (n_points > 0 && (!pts || !mat_out || ld < n_points)) || (cap > 0 && !mat_in) ||
+        !(field_size > 0)) {
+        set_error("eut_build_dcm: NULL pointer, negative size or non-positive field size");
+        return EUT_ERR_ARG;
+    }
+    return mesh_build_dcm(pts, ld, n_points, field_size, device, mat_in, cap, n_edges, mat_out);
+}
+
 int eut_plan_destroy(eut_plan *plan)
 {
     if (!plan) return EUT_OK;

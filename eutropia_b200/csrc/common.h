@@ -241,4 +241,7 @@ int field_exoenzyme_catalysis(eut_field *cf, eut_field *ef, int32_t exo_col, dou
                               const uint8_t *is_constant, double delta_time);
 int field_scale_column(eut_field *f, int32_t col0, double factor);
 int max_exo_mets();
+// meshgen.cu
+int mesh_build_dcm(const double *pts, int64_t ld, int64_t n, double fs, int device, int32_t *mat_in, int64_t cap,
+                   int64_t *n_edges_out, int32_t *mat_out);
 }  // namespace eut

@@ -213,6 +213,24 @@ def build_dcm(pts: np.ndarray, field_size: float) -> tuple[np.ndarray, np.ndarra
     return mat_in, mat_out
 
 
+def build_dcm_gpu(pts: np.ndarray, field_size: float, device: int = 0) -> tuple[np.ndarray, np.ndarray]:
+    """`build_dcm` on the B200 (eut_build_dcm: sort / search joins, csrc/meshgen.cu); same rules, same
+    integer output, bit for bit."""
+    import ctypes as C
+
+    from . import _lib
+    p = np.require(np.asarray(pts, dtype=np.float64), requirements=["F", "A"])
+    n = p.shape[0]
+    cap = 12 * n
+    buf = np.zeros((max(cap, 1), 2), dtype=np.int32, order="F")
+    mat_out = np.zeros((max(n, 1), 2), dtype=np.int32, order="F")
+    n_edges = C.c_int64(0)
+    _lib.check(_lib.lib().eut_build_dcm(_lib.ptr(p), n, n, float(field_size), int(device), _lib.ptr(buf), cap,
+                                        C.byref(n_edges), _lib.ptr(mat_out)))
+    e = int(n_edges.value)
+    return np.ascontiguousarray(buf[:e]), np.ascontiguousarray(mat_out[:n])
+
+
 @dataclass
 class FieldMesh:
     """The slots of `growthEnvironment` that the hot path reads (R/growthEnvironment.R:37-58)."""
@@ -229,13 +247,13 @@ class FieldMesh:
         return int(self.field_pts.shape[0])
 
 
-def make_mesh(polygon, field_size: float = 1.0, field_layers: int = 3) -> FieldMesh:
+def make_mesh(polygon, field_size: float = 1.0, field_layers: int = 3, on_device: bool = False, device: int = 0) -> FieldMesh:
     """`new("growthEnvironment", polygon.coords, field.size, field.layers)` restricted to the mesh
     slots (R/growthEnvironment.R:68-153)."""
     if isinstance(polygon, str):
         polygon = universe_polygon_preset(polygon)
     polygon = _close(polygon)
     pts = make_field_points(polygon, field_size, field_layers)
-    mat_in, mat_out = build_dcm(pts, field_size)
+    mat_in, mat_out = build_dcm_gpu(pts, field_size, device) if on_device else build_dcm(pts, field_size)
     return FieldMesh(pts, mat_in, mat_out, float(field_size), int(field_layers),
                      field_volume(field_size), polygon)

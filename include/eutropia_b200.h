@@ -181,6 +181,14 @@ EUT_API int eut_plan_get_segs(const eut_plan *plan, int32_t *seg_meta, int32_t *
 /* Internal position (0-based) of every reference point id: perm[N]. */
 EUT_API int eut_plan_get_perm(const eut_plan *plan, int32_t *perm);
 
+/* Neighbour index maps from field points on the device: `build.DCM` and the emit step of
+ * `initialize` (R/growthEnvironment.R:164-273, :138-149).  pts: n x 3 column-major (x, y, z), leading
+ * dimension ld.  mat_in: caller-provided cap x 2 column-major int32 (from | to), cap >= number of
+ * edges (12 n always suffices); rows [0, *n_edges) are filled, ordered by (to, from).  mat_out: n x 2
+ * column-major (id | n_neighbors = out-degree + 1).  1-based ids like the R slots. */
+EUT_API int eut_build_dcm(const double *pts, int64_t ld, int64_t n_points, double field_size, int device,
+                          int32_t *mat_in, int64_t cap, int64_t *n_edges, int32_t *mat_out);
+
 /* ---- session tier: field = N x C concentrations resident in HBM -------------------------------
  * Mirrors growthEnvironment@concentrations (R/growthEnvironment.R:44) / @exoenzymes.conc (:56). */
 typedef struct eut_field eut_field;
