@@ -11,7 +11,7 @@
 //   (:141-142);  n_neighbors = out-degree + 1 for the diagonal (:143).
 //
 // Integer output, so the parity bar is bit-exact equality with the host mirror (mesh.build_dcm),
-// which tests/test_oracle.py pins against hand-built meshes.  Floating-point inputs are only shifted
+// which the CPU test-suite pins against hand-built meshes.  Floating-point inputs are only shifted
 // and compared; --fmad=false keeps `x + d * fs` the two IEEE operations the reference performs.
 #include <cub/cub.cuh>
 
