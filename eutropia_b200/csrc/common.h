@@ -6,6 +6,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -191,6 +193,9 @@ struct eut_field {
     int64_t up_chunks = 0, down_chunks = 0;
     double *d_stats = nullptr;         // [3][C]
     int64_t launches = 0;
+    // substep loops seen before, captured as CUDA graphs (key: substep counts + options)
+    std::map<uint64_t, cudaGraphExec_t> graphs;
+    std::set<uint64_t> graph_seen;
     // options
     int opt_cpt = 0;      // compounds per thread (0 = auto)
     int opt_block = 256;

@@ -79,6 +79,8 @@ int field_destroy(eut_field *f)
         if (f->ev_dstage_free[i]) cudaEventDestroy(f->ev_dstage_free[i]);
         if (f->ev_dstage_ready[i]) cudaEventDestroy(f->ev_dstage_ready[i]);
     }
+    for (auto &g : f->graphs)
+        if (g.second) cudaGraphExecDestroy(g.second);
     if (f->own_stream && f->stream) cudaStreamDestroy(f->stream);
     if (f->copy_stream) cudaStreamDestroy(f->copy_stream);
     if (f->down_stream) cudaStreamDestroy(f->down_stream);
@@ -222,10 +224,49 @@ int field_diffuse(eut_field *f, const int32_t *niter, const int32_t *indvar, int
     EUT_CUDA(cudaMemcpyAsync(f->d_act + f->act_cap, f->h_act.data() + f->act_cap,
                              n_tot * sizeof(int32_t), cudaMemcpyHostToDevice, f->stream));
     const int max_it = niter[order[0]];
-    int n_act = n_tot;
-    for (int s = 0; s < max_it; s++) {
-        while (n_act > 0 && niter[order[n_act - 1]] <= s) n_act--;
-        EUT_TRY(launch_substep(f, n_act, s));
+    auto run_loop = [&]() -> int {
+        int n_act = n_tot;
+        for (int s = 0; s < max_it; s++) {
+            while (n_act > 0 && niter[order[n_act - 1]] <= s) n_act--;
+            EUT_TRY(launch_substep(f, n_act, s));
+        }
+        return EUT_OK;
+    };
+    // The loop is launch-bound when few columns diffuse (a 4-column launch lasts 35 us): a loop shape
+    // that comes back -- R calls with the same columns every round, the one-shot tier with the same
+    // chunk sizes -- is captured as a CUDA graph the second time it is seen and replayed from then on.
+    // Which columns (and which buffer each is in) is read from d_act, so the graph only depends on the
+    // substep counts and the kernel options.
+    static const bool no_graphs = getenv("EUT_NO_GRAPHS") != nullptr;
+    uint64_t key = 0xcbf29ce484222325ull;
+    auto mix = [&](uint64_t v) { key = (key ^ v) * 0x100000001b3ull; };
+    for (int a = 0; a < n_tot; a++) mix((uint64_t)niter[order[a]]);
+    mix((uint64_t)f->opt_cpt); mix((uint64_t)f->opt_variant); mix((uint64_t)f->opt_nbuf); mix((uint64_t)f->opt_debug);
+    mix((uint64_t)f->opt_ppt); mix((uint64_t)f->opt_shape); mix((uint64_t)f->opt_group_cols);
+    const auto hit = f->graphs.find(key);
+    if (hit != f->graphs.end()) {
+        if (hit->second) { EUT_CUDA(cudaGraphLaunch(hit->second, f->stream)); f->launches += max_it; }
+        else EUT_TRY(run_loop());                       // capture failed once: plain launches
+    } else if (!no_graphs && max_it >= 4 && f->graph_seen.count(key) && f->graphs.size() < 64) {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        EUT_CUDA(cudaStreamBeginCapture(f->stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = run_loop();
+        const cudaError_t ce = cudaStreamEndCapture(f->stream, &graph);
+        if (rc != EUT_OK || ce != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            (void)cudaGetLastError();
+            f->graphs[key] = nullptr;                   // do not try again
+            EUT_TRY(run_loop());
+        } else {
+            const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ie != cudaSuccess || !exec) { (void)cudaGetLastError(); f->graphs[key] = nullptr; EUT_TRY(run_loop()); }
+            else { f->graphs[key] = exec; EUT_CUDA(cudaGraphLaunch(exec, f->stream)); }
+        }
+    } else {
+        f->graph_seen.insert(key);
+        EUT_TRY(run_loop());
     }
     for (int a = 0; a < n_tot; a++) {
         const int c = indvar[order[a]] - 1;

@@ -264,6 +264,29 @@ int build_segs(eut_plan *p, const SegParams &sp)
             strip_step[st] = med >= 8 ? 8 : (med >= 4 ? 4 : (med >= 2 ? 2 : 1));
         }
     }
+    // Storage order inside a tile: level by level (as the strips were cut) or reference order.  Level
+    // major keeps the rows a tile reads from the tiles above / below it in its strip contiguous -- two
+    // halo runs instead of one per layer and side, i.e. 3 instead of 7 bulk copies per tile-column,
+    // which the single issuing thread of the producer warp feels.  The price: rows of one layer are a
+    // whole level group apart, (pieces per level) x 56 cells, which is 8 (mod 16) only for an odd
+    // number of layers; with an even number the two rows of a half warp would collide, so reference
+    // order is kept there.
+    bool level_major = false;
+    {
+        std::vector<int32_t> per_level;
+        for (size_t i = 0; i < ord.size();) {
+            size_t e = i;
+            while (e < ord.size() && pieces[ord[e]].strip == pieces[ord[i]].strip && pieces[ord[e]].level == pieces[ord[i]].level) e++;
+            per_level.push_back((int32_t)(e - i));
+            i = e;
+        }
+        if (!per_level.empty()) {
+            std::nth_element(per_level.begin(), per_level.begin() + per_level.size() / 2, per_level.end());
+            level_major = (per_level[per_level.size() / 2] % 2) == 1;
+        }
+        if (const char *e = getenv("EUT_SEG_ORDER")) level_major = atoi(e) != 0;
+        if (sp.pad_rows == 3) level_major = false;      // the global rule is written for reference order
+    }
     S.tile_start.assign(1, 0);
     std::vector<int32_t> tile_t0;        // first cell of every tile (tile t ends at tile_start[t + 1])
     {
@@ -271,8 +294,9 @@ int build_segs(eut_plan *p, const SegParams &sp)
         std::vector<int32_t> gap;
         int64_t total_gap = 0;
         for (int32_t t = 0; t < n_tiles; t++) {
-            std::sort(ord.begin() + tile_piece0[t], ord.begin() + tile_piece0[t + 1],
-                      [&](int32_t a, int32_t b) { return pieces[a].first < pieces[b].first; });
+            if (!level_major)
+                std::sort(ord.begin() + tile_piece0[t], ord.begin() + tile_piece0[t + 1],
+                          [&](int32_t a, int32_t b) { return pieces[a].first < pieces[b].first; });
             const int32_t k0 = tile_piece0[t], k1 = tile_piece0[t + 1];
             gap.assign(k1 - k0, 0);
             if (sp.pad_rows == 1 && k1 - k0 > 1) {

@@ -55,6 +55,15 @@ __device__ __forceinline__ void s_mbar_wait(uint32_t bar, uint32_t parity)
                  " bra WAIT_%=;\n"
                  "DONE_%=:\n}\n" ::"r"(bar), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void s_mbar_spin(uint32_t bar, uint32_t parity)
+{
+    asm volatile("{\n .reg .pred p;\n"
+                 "SPIN_%=:\n"
+                 " mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 " @p bra SDONE_%=;\n"
+                 " bra SPIN_%=;\n"
+                 "SDONE_%=:\n}\n" ::"r"(bar), "r"(parity) : "memory");
+}
 __device__ __forceinline__ void s_bulk_g2s(uint32_t saddr, const void *g, uint32_t bytes, uint32_t bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
@@ -156,23 +165,29 @@ k_substep_seg(double *__restrict__ buf, const int64_t col_stride, const int64_t 
         __syncwarp();
         const int head = t0 & 1;                           // first point sits at an odd global index
         const int body = (cnt - head) & ~1;
+        const int nb_iter = (m0.w + 31) / 32, ns_iter = (m1.y + 31) / 32;
         auto issue = [&](int c) {
             const int slot = c % NBUF;
-            if (c >= NBUF) s_mbar_wait(bar_empty + 8u * slot, (uint32_t)((c / NBUF) - 1) & 1u);
+            if (c >= NBUF) { if (dbg & 256) s_mbar_spin(bar_empty + 8u * slot, (uint32_t)((c / NBUF) - 1) & 1u); else s_mbar_wait(bar_empty + 8u * slot, (uint32_t)((c / NBUF) - 1) & 1u); }
             const double *__restrict__ src = buf + s_src[c];
             const uint32_t sb = s_base + (uint32_t)slot * (uint32_t)img_bytes;
             const uint32_t bar = bar_full + 8u * slot;
             if (lane == 0) s_mbar_expect_tx_arrive(bar, (dbg & 2) ? 0u : (uint32_t)m1.z);
             __syncwarp();
+            // the producer shares its scheduler with consumer warps: keep its instruction count down
+            // (uniform trip counts instead of BE + SE predicated iterations)
 #pragma unroll
             for (int e = 0; e < BE; e++) {
+                if (e >= nb_iter) break;
                 const uint32_t n = bs[e] >> 16;
                 if (n && !(dbg & 2)) s_bulk_g2s(sb + (bs[e] & 0xffffu) * 8u, src + bg[e], n * 8u, bar);
             }
 #pragma unroll
-            for (int e = 0; e < SE; e++)
+            for (int e = 0; e < SE; e++) {
+                if (e >= ns_iter) break;
                 if (sg[e] >= 0 && !(dbg & 8)) s_cp_async_8(sb + ss[e], src + sg[e]);
-            s_cp_async_arrive_noinc(bar);
+            }
+            if (dbg & 64) s_mbar_arrive(bar); else s_cp_async_arrive_noinc(bar);
         };
         // Column j is finished when all consumer warps have arrived on out_full[j] (they release the
         // image slot at the same moment).  First refill the freed slot -- the loads are what the
@@ -182,7 +197,7 @@ k_substep_seg(double *__restrict__ buf, const int64_t col_stride, const int64_t 
         for (int c = 0; c < pre; c++) issue(c);
         for (int j = 0; j < n_cols; j++) {
             const int ob_i = j % OB;
-            s_mbar_wait(bar_ofull + 8u * ob_i, (uint32_t)(j / OB) & 1u);
+            { if (dbg & 256) s_mbar_spin(bar_ofull + 8u * ob_i, (uint32_t)(j / OB) & 1u); else s_mbar_wait(bar_ofull + 8u * ob_i, (uint32_t)(j / OB) & 1u); }
             if (j + NBUF < n_cols) issue(j + NBUF);
             double *__restrict__ dst = buf + s_dst[j];
             const uint32_t ob = out_base + (uint32_t)ob_i * (uint32_t)out_bytes;
@@ -194,7 +209,7 @@ k_substep_seg(double *__restrict__ buf, const int64_t col_stride, const int64_t 
             if (lane == 1 && head) dst[0] = res[1];
             if (lane == 2 && head + body < cnt) dst[cnt - 1] = res[head + cnt - 1];
             if (j > 0) {
-                if (lane == 0) s_bulk_wait_read<1>();      // the store of column j-1 has drained its buffer
+                if (lane == 0 && !(dbg & 128)) s_bulk_wait_read<1>();      // the store of column j-1 has drained its buffer
                 __syncwarp();
                 if (lane == 0) s_mbar_arrive(bar_oempty + 8u * ((j - 1) % OB));
             }
@@ -233,7 +248,7 @@ k_substep_seg(double *__restrict__ buf, const int64_t col_stride, const int64_t 
     auto s_sts = [](unsigned char *a, double v) { *reinterpret_cast<double *>(a) = v; };
     for (int j = 0; j < n_cols; j++) {
         const int slot = j % NBUF, ob_i = j % OB;
-        s_mbar_wait(bar_full + 8u * slot, (uint32_t)(j / NBUF) & 1u);
+        { if (dbg & 256) s_mbar_spin(bar_full + 8u * slot, (uint32_t)(j / NBUF) & 1u); else s_mbar_wait(bar_full + 8u * slot, (uint32_t)(j / NBUF) & 1u); }
         const unsigned char *img = smem_raw + (size_t)slot * img_bytes;
         unsigned char *ob = smem_raw + (size_t)NBUF * img_bytes + (size_t)ob_i * out_bytes;
         double res[SPT][R];
@@ -289,7 +304,7 @@ k_substep_seg(double *__restrict__ buf, const int64_t col_stride, const int64_t 
                 res[s][i] = __dadd_rn(o[i + 1], y);
             }
         }
-        if (j >= OB) s_mbar_wait(bar_oempty + 8u * ob_i, (uint32_t)((j / OB) - 1) & 1u);
+        if (j >= OB) { if (dbg & 256) s_mbar_spin(bar_oempty + 8u * ob_i, (uint32_t)((j / OB) - 1) & 1u); else s_mbar_wait(bar_oempty + 8u * ob_i, (uint32_t)((j / OB) - 1) & 1u); }
 #pragma unroll
         for (int s = 0; s < SPT; s++)
 #pragma unroll
@@ -311,7 +326,7 @@ k_substep_seg(double *__restrict__ buf, const int64_t col_stride, const int64_t 
             y = __dsub_rn(y, __dmul_rn(cq, __ldg(wout + t0 + (int)oc - head)));
             s_sts(ob + oc * 8u, __dadd_rn(cq, y));
         }
-        s_fence_async();        // results (generic proxy) before the producer's bulk store (async proxy)
+        if (!(dbg & 32)) s_fence_async();        // results (generic proxy) before the producer's bulk store (async proxy)
         __syncwarp();
         if (lane == 0) {
             s_mbar_arrive(bar_empty + 8u * slot);          // this warp is done reading the image slot
