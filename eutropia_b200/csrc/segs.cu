@@ -410,19 +410,31 @@ int build_segs(eut_plan *p, const SegParams &sp)
             h = e;
         }
         {
-            // lone points (row-end neighbours from the next tile column).  Under the global residue
-            // rule they keep cell == position (mod 16) too -- a 16-column grid, column = residue -- so
-            // that the end-cell loads of a half warp stay on distinct bank pairs.
+            // Lone points: mostly the left / right neighbour of a row piece, which lives in the next tile
+            // column.  A lane reads it in place of the cell before / after its row, so it is placed at
+            // the residue (mod 16 cells) that cell would have had -- a 16-column grid, column = residue --
+            // and the end-cell loads of a half warp stay on distinct bank pairs like the in-line ones.
             int32_t fill[16] = {0};
-            if (keep_res) next = (next + 15) / 16 * 16;
+            next = (next + 15) / 16 * 16;
+            int32_t rr = 0;
             for (size_t h = 0; h < halo.size(); h++) {
                 if (halo_off[h] >= 0) continue;
-                if (keep_res) { const int32_t r = halo[h] & 15; halo_off[h] = next + 16 * fill[r] + r; fill[r]++; }
-                else halo_off[h] = next++;
+                int32_t r = -1;
+                if (keep_res) r = halo[h] & 15;
+                else {
+                    const int32_t i = p->iperm[halo[h]];
+                    if (i + 1 < (int32_t)N && ra.row_of[i + 1] == ra.row_of[i] && p->perm[i + 1] >= t0 && p->perm[i + 1] < t1)
+                        r = (own_off + (p->perm[i + 1] - t0) - 1) & 15;
+                    else if (i > 0 && ra.row_of[i - 1] == ra.row_of[i] && p->perm[i - 1] >= t0 && p->perm[i - 1] < t1)
+                        r = (own_off + (p->perm[i - 1] - t0) + 1) & 15;
+                    else r = (rr++) & 15;
+                }
+                halo_off[h] = next + 16 * fill[r] + r;
+                fill[r]++;
                 single.push_back({halo[h], halo_off[h]});
                 halo_total++;
             }
-            if (keep_res) next += 16 * *std::max_element(fill, fill + 16);
+            next += 16 * *std::max_element(fill, fill + 16);
         }
         next += R + 2;                              // masked lanes of short segments read past their stream
         if (next > sp.max_img_points || next * 8 > 65535) {

@@ -129,12 +129,16 @@ k_substep_seg(double *__restrict__ buf, const int64_t col_stride, const int64_t 
         s_src[j] = (long long)b * buf_stride + (long long)c * col_stride;
         s_dst[j] = (long long)(b ^ 1) * buf_stride + (long long)c * col_stride + t0;
     }
-    // holes and the zero header of every staging buffer are +0.0 for the whole kernel: the copies
-    // only ever write cells that exist
+    // the zero header of every staging buffer (absent streams, unused slots, idle lanes read it) stays
+    // +0.0 for the whole kernel: the copies never write it.  The result buffers are cleared once as
+    // well: their gap cells are never written by a lane and are stored with every column.
     {
         uint4 *z = reinterpret_cast<uint4 *>(smem_raw);
-        const int n16 = (NBUF * img_bytes + OB * out_bytes) / 16;   // result buffers too: gap cells store 0
-        for (int i = tid; i < n16; i += THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        constexpr int H16 = 8;                              // 128 bytes >= the zero header (R + 3 cells)
+        for (int i = tid; i < NBUF * H16; i += THREADS) z[(i / H16) * (img_bytes / 16) + (i % H16)] = make_uint4(0u, 0u, 0u, 0u);
+        uint4 *zo = reinterpret_cast<uint4 *>(smem_raw + (size_t)NBUF * img_bytes);
+        const int n16 = OB * out_bytes / 16;
+        for (int i = tid; i < n16; i += THREADS) zo[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     if (tid == 0) {
         for (int i = 0; i < NBUF; i++) { s_mbar_init(bar_full + 8u * i, 1 + 32); s_mbar_init(bar_empty + 8u * i, CWARPS); }
