@@ -258,6 +258,9 @@ int plan_build(eut_plan *p, const int32_t *from, const int32_t *to, int64_t n_ed
         if (const char *e = getenv("EUT_SEG_R")) sp.R = atoi(e);
         sp.tile_cols = 8 * sp.R;
         if (const char *e = getenv("EUT_SEG_COLS")) sp.tile_cols = atoi(e);
+        // tile capacity: 448 segments (one CTA of 14 consumer warps per SM) once the field is large enough
+        // to give every SM several such tiles; 224 (two CTAs of 7 per SM) below that
+        sp.max_tile_segs = N >= 400000 ? 448 : 224;
         if (const char *e = getenv("EUT_SEG_TILE")) sp.max_tile_segs = std::min(448, std::max(8, atoi(e)));
         if (const char *e = getenv("EUT_TILE_BAND")) sp.band_levels = atoi(e);
         if (const char *e = getenv("EUT_SEG_PAD")) sp.pad_rows = atoi(e);

@@ -357,7 +357,7 @@ static int launch_seg_t(eut_field *f, int n_act, int substep)
         return EUT_ERR_UNSUPPORTED;
     }
     int slices = 1;
-    const int64_t want = 4ll * 148 * MINB;
+    const int64_t want = 6ll * 148 * MINB;          // ~6 waves: the tail of the last wave stays small
     while ((int64_t)p->n_tiles * slices < want && slices < n_act) slices++;
     if (f->opt_cpt > 0) slices = (n_act + f->opt_cpt - 1) / f->opt_cpt;
     slices = std::max(slices, (n_act + kTileMaxCols - 1) / kTileMaxCols);
@@ -391,11 +391,12 @@ int launch_seg(eut_field *f, int n_act, int substep)
             if (nb == 4) return launch_seg_t<7, 1, 7, 4, 2, 2>(f, n_act, substep);
             return launch_seg_t<7, 1, 7, 3, 3, 2>(f, n_act, substep);
         }
-        if (S.max_tile_segs <= 448) {      // EUT_SEG_TILE=448: one CTA per SM, 14 consumer warps
+        if (S.max_tile_segs <= 448) {      // large fields: one CTA per SM, 14 consumer warps (halo / own 0.18)
             if (shape == 1) return launch_seg_t<7, 1, 14, 3, 2, 1>(f, n_act, substep);
             if (shape == 2) return launch_seg_t<7, 1, 14, 4, 2, 1>(f, n_act, substep);
-            if (shape == 4) return launch_seg_t<7, 1, 14, 3, 3, 1>(f, n_act, substep);
-            return launch_seg_t<7, 1, 14, 4, 3, 1>(f, n_act, substep);
+            if (shape == 3) return launch_seg_t<7, 1, 14, 4, 3, 1>(f, n_act, substep);
+            if (shape == 5) return launch_seg_t<7, 1, 14, 3, 4, 1>(f, n_act, substep);
+            return launch_seg_t<7, 1, 14, 3, 3, 1>(f, n_act, substep);
         }
     }
     if (S.R == 5 && S.max_tile_segs <= 224) return launch_seg_t<5, 1, 7, 3, 2, 2>(f, n_act, substep);
