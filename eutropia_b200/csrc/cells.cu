@@ -62,6 +62,8 @@ struct eut_cells {
     size_t tmp_bytes = 0;
     double *d_fmol = nullptr;   // [M x C]
     int64_t fmol_cap = 0;
+    double *d_tfield = nullptr; // [Np x ldc] point-major copy of the field for the gather
+    int64_t tfield_cap = 0;
     int64_t *d_ex_ptr = nullptr;
     int32_t *d_ex_cpd = nullptr;
     double *d_ex_flx = nullptr, *d_ex_cs = nullptr;
@@ -355,6 +357,79 @@ k_gather(const double *__restrict__ buf, const int64_t col_stride, const int64_t
     }
 }
 
+// ---- gather, second generation ------------------------------------------------------------------
+// The field is compound-major (one column = one contiguous vector: what the stencil and the column
+// transfers want), so a cell's ~133 points of one column are ~21 short runs and every 8-byte load of
+// the kernel above pulls a 32-byte sector: 366 M sectors from L2 per call, which is what bounds it.
+// Here the field is first copied point-major (one pass over HBM, 0.16 ms at 1 M x 64), then a warp
+// takes a cell and its lanes take the COLUMNS: the 64 values of one field point are 512 contiguous
+// bytes, every sector is used in full, and neighbouring cells hit the same lines in L1 / L2.  Each
+// lane adds its column's terms in the cell's position order as a hi+lo pair: no warp reduction, and
+// the result does not depend on the launch shape.
+__global__ void __launch_bounds__(256)
+k_field_transpose(const double *__restrict__ buf, const int64_t col_stride, const int64_t buf_stride,
+                  const int32_t *__restrict__ cur, double *__restrict__ tf, const int n_padded,
+                  const int n_cols, const int ldc)
+{
+    __shared__ double tile[32][33];
+    const int q0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) {
+        const int c = c0 + j, q = q0 + tx;
+        double v = 0.0;
+        if (c < n_cols && q < n_padded) v = buf[(int64_t)cur[c] * buf_stride + (int64_t)c * col_stride + q];
+        tile[j][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) {
+        const int q = q0 + j, c = c0 + tx;
+        if (q < n_padded && c < ldc) tf[(int64_t)q * ldc + c] = tile[tx][j];
+    }
+}
+
+template <int CPL>
+__global__ void __launch_bounds__(256)
+k_gather_t(const double *__restrict__ tf, const int ldc, const int64_t *__restrict__ cell_ptr,
+           const int32_t *__restrict__ g_idx, const int32_t *__restrict__ fq, const double *__restrict__ acc,
+           const double field_vol, double *__restrict__ fmol, const int n_cells, const int n_cols,
+           const int32_t *__restrict__ cell_order)
+{
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= (int64_t)n_cells) return;
+    const unsigned full = 0xffffffffu;
+    const int i = cell_order[(int)w];
+    const int64_t k0 = cell_ptr[i], k1 = cell_ptr[i + 1];
+    for (int c0 = 0; c0 < n_cols; c0 += 32 * CPL) {
+        dd s[CPL];
+#pragma unroll
+        for (int u = 0; u < CPL; u++) s[u] = dd{0.0, 0.0};
+        for (int64_t kb = k0; kb < k1; kb += 32) {
+            int ql = 0;
+            double al = 0.0;
+            if (kb + lane < k1) { const int e = g_idx[kb + lane]; ql = fq[e]; al = acc[e]; }
+            const int nr = (int)min((int64_t)32, k1 - kb);
+#pragma unroll 4
+            for (int r = 0; r < nr; r++) {
+                const int q = __shfl_sync(full, ql, r);
+                const double a = __shfl_sync(full, al, r);
+                const double *__restrict__ row = tf + (int64_t)q * ldc + c0 + lane;
+#pragma unroll
+                for (int u = 0; u < CPL; u++)
+                    if (c0 + lane + 32 * u < n_cols) dd_add(s[u], __dmul_rn(__ldg(row + 32 * u), a));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < CPL; u++) {
+            const int c = c0 + lane + 32 * u;
+            // ((sum_k conc_k * acc_k) / 1000) * fieldVol, see k_gather
+            if (c < n_cols) fmol[(int64_t)c * n_cells + i] = __dmul_rn(__ddiv_rn(dd_value(s[u]), 1000.0), field_vol);
+        }
+    }
+}
+
 // key of the per-cell position sort: (cell << 32) | internal position
 __global__ void __launch_bounds__(256)
 k_gather_keys(const int32_t *__restrict__ ecell, const int32_t *__restrict__ fq,
@@ -452,7 +527,19 @@ k_ex_colsum(const double *__restrict__ buf, const int64_t col_stride, const int6
         for (int64_t k = cell_ptr[i] + lane; k < cell_ptr[i + 1]; k += 32)
             dd_add(s, __dmul_rn(col[fq[k]], acc[k]));   // same form as the gather
         s = dd_warp_sum(s);
-        if (lane == 0) ex_cs[e] = __dmul_rn(__ddiv_rn(dd_value(s), 1000.0), field_vol);
+        // The reference evaluates, per field, am = fmolPerField / colSum and Delta = am * ex / 1e12 /
+        // (fieldVol / 1e15) (R/run_simulation.R:696, :707-708) with fmolPerField = conc / 1000 * fieldVol
+        // * acc.prop.  Everything that does not depend on the field is folded into one factor per
+        // exchange here, so that the scatter kernel needs two multiplications per contribution instead
+        // of four divisions (a division is ~25 instructions; the scatter was bound by instruction
+        // issue): Delta = conc * acc.prop * g,  g = ex / colSum / 1e12 / vol_l * fieldVol / 1000.
+        // A few ulp from the reference's operation order, far inside 1e-12; colSum = 0 gives
+        // g = -Inf and 0 * -Inf = NaN, the reference's 0 / 0.
+        if (lane == 0) {
+            const double cs = __dmul_rn(__ddiv_rn(dd_value(s), 1000.0), field_vol);
+            const double g = __ddiv_rn(__ddiv_rn(__ddiv_rn(ex, cs), 1e12), vol_l);
+            ex_cs[e] = __ddiv_rn(__dmul_rn(g, field_vol), 1000.0);
+        }
     }
 }
 
@@ -519,9 +606,7 @@ k_scatter(double *__restrict__ buf, const int64_t col_stride, const int64_t buf_
                         double d;
                         if (ex < 0) {
                             const double cv = buf[(int64_t)cur[c] * buf_stride + (int64_t)c * col_stride + q];
-                            const double fpf = __dmul_rn(__dmul_rn(__ddiv_rn(cv, 1000.0), field_vol), ak);
-                            const double am = __ddiv_rn(fpf, ex_cs[e]);                    // :696
-                            d = __ddiv_rn(__ddiv_rn(__dmul_rn(am, ex), 1e12), vol_l);      // :707-708
+                            d = __dmul_rn(__dmul_rn(cv, ak), ex_cs[e]);                    // :696, :707-708 (see k_ex_colsum)
                         } else {
                             d = __dmul_rn(frac, ex_cs[e]);                                 // :732-734
                         }
@@ -666,7 +751,7 @@ int eut_cells_destroy(eut_cells *c)
     cudaFree(c->d_t_entry); cudaFree(c->d_t_key); cudaFree(c->d_seg_start); cudaFree(c->d_seg_fq);
     cudaFree(c->d_gx); cudaFree(c->d_gy); cudaFree(c->d_gfield); cudaFree(c->d_col_start);
     cudaFree(c->d_col_x); cudaFree(c->d_layer_col); cudaFree(c->d_layer_z); cudaFree(c->d_tmp);
-    cudaFree(c->d_fmol); cudaFree(c->d_ex_ptr); cudaFree(c->d_ex_cpd); cudaFree(c->d_ex_flx);
+    cudaFree(c->d_fmol); cudaFree(c->d_tfield); cudaFree(c->d_ex_ptr); cudaFree(c->d_ex_cpd); cudaFree(c->d_ex_flx);
     cudaFree(c->d_ex_cs); cudaFree(c->d_const); cudaFree(c->d_g_idx); cudaFree(c->d_cell_order);
     delete c;
     return EUT_OK;
@@ -838,12 +923,25 @@ int eut_cells_gather(eut_cells *c, eut_field *f, double field_vol, double *fmol_
     EUT_TRY(grow(&c->d_fmol, &c->fmol_cap, n));
     EUT_TRY(build_gather_order(c, 0));
     EUT_CUDA(cudaStreamSynchronize(0));  // list construction runs on the legacy stream
-    constexpr int G = 8, EPL = 5;
     const int64_t n_warps = c->M;
-    k_gather<G, EPL><<<(unsigned)((n_warps * 32 + 255) / 256), 256, 0, f->stream>>>(
-        f->d_buf, c->plan->Np, f->C * c->plan->Np, f->d_cur, c->d_cell_ptr, c->d_g_idx, c->d_fq, c->d_acc,
-        field_vol, c->d_fmol, (int)c->M, (int)f->C, c->d_cell_order);
-    f->launches++;
+    static const bool old_gather = getenv("EUT_GATHER_V1") != nullptr;
+    if (old_gather) {
+        constexpr int G = 8, EPL = 5;
+        k_gather<G, EPL><<<(unsigned)((n_warps * 32 + 255) / 256), 256, 0, f->stream>>>(
+            f->d_buf, c->plan->Np, f->C * c->plan->Np, f->d_cur, c->d_cell_ptr, c->d_g_idx, c->d_fq, c->d_acc,
+            field_vol, c->d_fmol, (int)c->M, (int)f->C, c->d_cell_order);
+        f->launches++;
+    } else {
+        const int ldc = (int)((f->C + 31) / 32 * 32);
+        EUT_TRY(grow(&c->d_tfield, &c->tfield_cap, c->plan->Np * (int64_t)ldc));
+        dim3 tg((unsigned)((c->plan->Np + 31) / 32), (unsigned)(ldc / 32), 1);
+        k_field_transpose<<<tg, 256, 0, f->stream>>>(f->d_buf, c->plan->Np, f->C * c->plan->Np, f->d_cur, c->d_tfield,
+                                                     (int)c->plan->Np, (int)f->C, ldc);
+        k_gather_t<2><<<(unsigned)((n_warps * 32 + 255) / 256), 256, 0, f->stream>>>(
+            c->d_tfield, ldc, c->d_cell_ptr, c->d_g_idx, c->d_fq, c->d_acc, field_vol, c->d_fmol, (int)c->M, (int)f->C,
+            c->d_cell_order);
+        f->launches += 2;
+    }
     EUT_CUDA(cudaGetLastError());
     if (fmol_host) {
         EUT_CUDA(cudaMemcpyAsync(fmol_host, c->d_fmol, n * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
