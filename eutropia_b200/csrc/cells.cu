@@ -64,6 +64,10 @@ struct eut_cells {
     int64_t fmol_cap = 0;
     double *d_tfield = nullptr; // [Np x ldc] point-major copy of the field for the gather
     int64_t tfield_cap = 0;
+    double *d_exd = nullptr;    // [M x ldc] dense exchange factors per cell (scatter, second generation)
+    int64_t exd_cap = 0;
+    unsigned long long *d_exmask = nullptr;   // [M x ldc/64 x 2] bit c: the cell takes up / produces column c
+    int64_t exmask_cap = 0;
     int64_t *d_ex_ptr = nullptr;
     int32_t *d_ex_cpd = nullptr;
     double *d_ex_flx = nullptr, *d_ex_cs = nullptr;
@@ -632,6 +636,106 @@ k_scatter(double *__restrict__ buf, const int64_t col_stride, const int64_t buf_
     }
 }
 
+// ---- scatter, second generation --------------------------------------------------------------------
+// Lanes = compound columns, like the second gather.  The sparse exchange list of every cell is first
+// spread into a dense row of factors (k_ex_dense: 8 bytes per cell and column, L2 resident) with two
+// bit masks per 64 columns (uptake / production); the warp of a field point then walks its incident
+// cells in cell order and every lane adds what the cell does to ITS columns:
+//     uptake      Delta = conc[q, c] * acc.prop * g          (g folded per exchange, see k_ex_colsum)
+//     production  Delta = (dmax - dist) / fsum * ex'          (R/run_simulation.R:729-734)
+// into a register.  Same terms, same (cell) order per (field, compound) sum as the first version --
+// bit-identical results -- but no exchange-list walk, no shared-memory accumulators and a third of
+// the instructions.  Finally NaN -> 0, add, clamp (:315-319).
+__global__ void __launch_bounds__(256)
+k_ex_dense(const int64_t *__restrict__ ex_ptr, const int32_t *__restrict__ ex_cpd, const double *__restrict__ ex_flx,
+           const double *__restrict__ ex_cs, double *__restrict__ exd, unsigned long long *__restrict__ exmask,
+           const int n_cells, const int n_cols, const int ldc)
+{
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= n_cells) return;
+    for (int64_t e = ex_ptr[i] + lane; e < ex_ptr[i + 1]; e += 32) {
+        const int c = ex_cpd[e] - 1;
+        const double ex = ex_flx[e];
+        if (c < 0 || c >= n_cols || ex == 0.0 || ex != ex) continue;
+        exd[(int64_t)i * ldc + c] = ex_cs[e];
+        atomicOr(exmask + ((int64_t)i * (ldc / 64) + c / 64) * 2 + (ex < 0 ? 0 : 1), 1ull << (c & 63));
+    }
+}
+
+template <int CPL>
+__global__ void __launch_bounds__(256)
+k_scatter_t(double *__restrict__ buf, const int64_t col_stride, const int64_t buf_stride,
+            const int32_t *__restrict__ cur, const int32_t *__restrict__ seg_start,
+            const int32_t *__restrict__ seg_fq, const int32_t *__restrict__ t_entry,
+            const int32_t *__restrict__ ecell, const double *__restrict__ dist,
+            const double *__restrict__ acc, const double *__restrict__ dmax,
+            const double *__restrict__ fsum, const double *__restrict__ exd,
+            const unsigned long long *__restrict__ exmask, const int ldc,
+            const uint8_t *__restrict__ is_const, const int n_seg, const int n_cols)
+{
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (t >= n_seg) return;
+    const unsigned full = 0xffffffffu;
+    const int q = seg_fq[t];
+    const int r_begin = seg_start[t], r_end = seg_start[t + 1];
+    for (int c0 = 0; c0 < n_cols; c0 += 64) {              // 64 columns per pass: one mask pair per cell
+        double sum[2] = {0.0, 0.0}, cv[2] = {0.0, 0.0};
+        double *pc[2];
+        unsigned hit = 0;
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int c = min(c0 + lane + 32 * u, n_cols - 1);
+            pc[u] = buf + (int64_t)cur[c] * buf_stride + (int64_t)c * col_stride + q;
+            cv[u] = *pc[u];
+        }
+        for (int rb = r_begin; rb < r_end; rb += 32) {
+            // the per-cell quantities of up to 32 incident cells are fetched by the lanes in parallel
+            double l_ak = 0.0, l_frac = 0.0;
+            int l_i = 0;
+            unsigned long long l_mu = 0, l_mp = 0;
+            if (rb + lane < r_end) {
+                const int k = t_entry[rb + lane];
+                l_i = ecell[k];
+                l_ak = acc[k];
+                l_frac = __ddiv_rn(__dsub_rn(dmax[l_i], dist[k]), fsum[l_i]);   // :729-730
+                const unsigned long long *m = exmask + ((int64_t)l_i * (ldc / 64) + c0 / 64) * 2;
+                l_mu = m[0]; l_mp = m[1];
+            }
+            const int nr = min(32, r_end - rb);
+            for (int rr = 0; rr < nr; rr++) {
+                const unsigned long long mu = __shfl_sync(full, l_mu, rr), mp = __shfl_sync(full, l_mp, rr);
+                if ((mu | mp) == 0ull) continue;                                  // warp-uniform
+                const int i = __shfl_sync(full, l_i, rr);
+                const double ak = __shfl_sync(full, l_ak, rr);
+                const double frac = __shfl_sync(full, l_frac, rr);
+                const double *__restrict__ row = exd + (int64_t)i * ldc + c0 + lane;
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const int b = lane + 32 * u;
+                    const bool up = (mu >> b) & 1ull, pd = (mp >> b) & 1ull;
+                    if (up | pd) {
+                        const double f = __ldg(row + 32 * u);
+                        const double d = up ? __dmul_rn(__dmul_rn(cv[u], ak), f) : __dmul_rn(frac, f);
+                        sum[u] = __dadd_rn(sum[u], d);
+                        hit |= 1u << u;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int c = c0 + lane + 32 * u;
+            if (!((hit >> u) & 1u) || c >= n_cols) continue;
+            if (is_const && is_const[c]) continue;                          // :311-312
+            double d = sum[u];
+            if (d != d) d = 0.0;                                             // :315
+            double v = __dadd_rn(cv[u], d);                                  // :318
+            if (v < 1e-12) v = 0.0;                                          // :319
+            *pc[u] = v;
+        }
+    }
+}
+
 // ---- claim rescale (R/run_simulation.R:236-241) ------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_claim(const int32_t *__restrict__ seg_start, const int32_t *__restrict__ t_entry,
@@ -751,7 +855,7 @@ int eut_cells_destroy(eut_cells *c)
     cudaFree(c->d_t_entry); cudaFree(c->d_t_key); cudaFree(c->d_seg_start); cudaFree(c->d_seg_fq);
     cudaFree(c->d_gx); cudaFree(c->d_gy); cudaFree(c->d_gfield); cudaFree(c->d_col_start);
     cudaFree(c->d_col_x); cudaFree(c->d_layer_col); cudaFree(c->d_layer_z); cudaFree(c->d_tmp);
-    cudaFree(c->d_fmol); cudaFree(c->d_tfield); cudaFree(c->d_ex_ptr); cudaFree(c->d_ex_cpd); cudaFree(c->d_ex_flx);
+    cudaFree(c->d_fmol); cudaFree(c->d_tfield); cudaFree(c->d_exd); cudaFree(c->d_exmask); cudaFree(c->d_ex_ptr); cudaFree(c->d_ex_cpd); cudaFree(c->d_ex_flx);
     cudaFree(c->d_ex_cs); cudaFree(c->d_const); cudaFree(c->d_g_idx); cudaFree(c->d_cell_order);
     delete c;
     return EUT_OK;
@@ -1001,6 +1105,21 @@ int eut_cells_scatter(eut_cells *c, eut_field *f, double field_vol, const uint8_
                                                                 c->d_ex_cpd, c->d_ex_flx, c->d_ex_cs, (int)M,
                                                                 field_vol / 1e15);
     f->launches++;
+    static const bool old_scatter = getenv("EUT_SCATTER_V1") != nullptr;
+    if (!old_scatter) {
+        const int ldc = (int)((f->C + 63) / 64 * 64);
+        EUT_TRY(grow(&c->d_exd, &c->exd_cap, M * (int64_t)ldc));
+        EUT_TRY(grow(&c->d_exmask, &c->exmask_cap, M * (int64_t)(ldc / 64) * 2));
+        EUT_CUDA(cudaMemsetAsync(c->d_exmask, 0, (size_t)M * (ldc / 64) * 2 * sizeof(unsigned long long), s));
+        k_ex_dense<<<(unsigned)((M * 32 + 255) / 256), 256, 0, s>>>(c->d_ex_ptr, c->d_ex_cpd, c->d_ex_flx, c->d_ex_cs, c->d_exd,
+                                                                   c->d_exmask, (int)M, (int)f->C, ldc);
+        k_scatter_t<2><<<(unsigned)((c->n_seg * 32 + 255) / 256), 256, 0, s>>>(
+            f->d_buf, c->plan->Np, bs, f->d_cur, c->d_seg_start, c->d_seg_fq, c->d_t_entry, c->d_ecell, c->d_dist,
+            c->d_acc, c->d_dmax, c->d_fsum, c->d_exd, c->d_exmask, ldc, d_const, (int)c->n_seg, (int)f->C);
+        f->launches += 2;
+        EUT_CUDA(cudaGetLastError());
+        return EUT_OK;
+    }
     constexpr int COLS = 128;             // compound columns per pass (per-warp accumulators: 8 x 128 x 9 B)
     const double vol_l = field_vol / 1e15;
     for (int c0 = 0; c0 < f->C; c0 += COLS) {
