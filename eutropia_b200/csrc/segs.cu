@@ -80,11 +80,19 @@ int build_segs(eut_plan *p, const SegParams &sp)
             }
             if (len - kend > 0 && len - kend < X / 2) kend = len;
             for (int32_t i = k; i < kend; i++) piece_of[ra.row_start[r] + i] = (int32_t)pieces.size();
+            // the column label is taken at the centre of the piece: a head that is one cell shorter or
+            // longer than the neighbouring row's (the half-cell shift between layers along a ragged
+            // boundary) must not relabel it, or the strips would fall apart into single rows
+            ucol = (u0 + (k + kend) / 2) / X;
             pieces.push_back({ucol, ra.level[r], ra.row_start[r] + k, kend - k, 0});
             k = kend;
         }
     }
     const int32_t P = (int32_t)pieces.size();
+    if (getenv("EUT_TRACE_PIECES"))
+        for (int32_t a = 0; a < std::min(P, 60); a++)
+            fprintf(stderr, "[eut] piece %d: row %d level %d u %d count %d ucol %d\n", a, ra.row_of[pieces[a].first],
+                    pieces[a].level, u_of(pieces[a].first) - ra.xmin, pieces[a].count, pieces[a].ucol);
     {
         Dsu dsu(P);
         for (int64_t i = 0; i < N; i++) {
@@ -92,6 +100,27 @@ int build_segs(eut_plan *p, const SegParams &sp)
             for (int64_t k = p->row_ptr[i]; k < p->row_ptr[i + 1]; k++) {
                 const int32_t b = piece_of[p->col[k]];
                 if (a != b && pieces[a].ucol == pieces[b].ucol) dsu.unite(a, b);
+            }
+        }
+        // Tiny strips join a neighbour, whatever its column label.  The ghost points of a slab (halo.cu)
+        // are the typical case: they have no in-edges of their own, so each is a one-point row at the end
+        // of a raster row with a column label of its own, and would otherwise become a tile of its own.
+        {
+            std::vector<int32_t> strip_pts(P, 0);
+            for (int32_t a = 0; a < P; a++) strip_pts[dsu.find(a)] += pieces[a].count;
+            const int32_t tiny = 4 * X;
+            for (int64_t i = 0; i < N; i++) {
+                const int32_t a = piece_of[i];
+                for (int64_t k = p->row_ptr[i]; k < p->row_ptr[i + 1]; k++) {
+                    const int32_t b = piece_of[p->col[k]];
+                    const int32_t ra_ = dsu.find(a), rb_ = dsu.find(b);
+                    if (ra_ == rb_) continue;
+                    if (strip_pts[ra_] < tiny || strip_pts[rb_] < tiny) {
+                        const int32_t tot = strip_pts[ra_] + strip_pts[rb_];
+                        dsu.unite(ra_, rb_);
+                        strip_pts[dsu.find(ra_)] = tot;
+                    }
+                }
             }
         }
         for (int32_t a = 0; a < P; a++) pieces[a].strip = dsu.find(a);
@@ -215,6 +244,15 @@ int build_segs(eut_plan *p, const SegParams &sp)
         tile_piece0.push_back((int32_t)ord.size());
     }
     const int32_t n_tiles = (int32_t)tile_piece0.size() - 1;
+    if (getenv("EUT_TRACE")) {
+        std::vector<int32_t> st;
+        for (int32_t a = 0; a < P; a++) st.push_back(pieces[a].strip);
+        std::sort(st.begin(), st.end());
+        const size_t n_strips = std::unique(st.begin(), st.end()) - st.begin();
+        int32_t max_level = 0;
+        for (int32_t r = 0; r < NR; r++) max_level = std::max(max_level, ra.level[r]);
+        fprintf(stderr, "[eut] segment planner: %d rows, %d pieces, %zu strips, %d levels, %d tiles\n", NR, P, n_strips, max_level + 1, n_tiles);
+    }
     // Storage inside a tile.  Pieces follow the reference order (layer by layer, row by row), so the
     // rows a segment's streams read are a fixed number of pieces away from its own row: the previous
     // / next piece for C / D, a constant piece count for the other layers.  The own block of a tile

@@ -32,8 +32,16 @@ def harbor_width_for(n_points: int, layers: int = 3, field_size: float = 1.0) ->
     return math.sqrt(n_points / layers * field_size ** 2 / area)
 
 
-def config_mesh(name: str):
-    """The BASELINE.json configs as meshes."""
+def config_mesh(name: str, on_device: bool = False, device: int = 0):
+    """The BASELINE.json configs as meshes (`on_device`: neighbour maps by eut_build_dcm)."""
+    if on_device:
+        import functools
+        real = _mesh.make_mesh
+        _mesh.make_mesh = functools.partial(real, on_device=True, device=device)
+        try:
+            return config_mesh(name)
+        finally:
+            _mesh.make_mesh = real
     if name == "square100k":      # config 2: 183 x 183 x 3 = 100 467 points
         return _mesh.make_mesh("Rectangle_181_181", 1.0, 3)
     if name == "harbor1m":        # config 3/4: non-convex polygon, ~1e6 points, 3 layers

@@ -20,7 +20,7 @@ substeps = int(sys.argv[3]) if len(sys.argv) > 3 else 60
 rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-mesh = synth.config_mesh(f"square:{ppg * world}")
+mesh = synth.config_mesh(f"square:{ppg * world}", on_device=True, device=local)   # neighbour maps on this rank's GPU
 part = SlabPartition(mesh.mat_in, mesh.mat_out, mesh.nfields, world, rank)
 rng = np.random.default_rng(5)
 be = GpuSlabBackend(part, cols, local)
