@@ -87,6 +87,7 @@ def lib() -> C.CDLL:
         "eut_field_exoenzyme_catalysis": (C.c_int, [vp, vp, i32, dbl, dbl, vp, vp, i32, vp, dbl]),
         "eut_field_scale_column": (C.c_int, [vp, i32, dbl]),
         "eut_field_halo_set": (C.c_int, [vp, vp, i64, vp, i64]),
+        "eut_field_set_halo_stream": (C.c_int, [vp, vp]),
         "eut_field_halo_pack": (C.c_int, [vp, vp, i64, vp]),
         "eut_field_halo_unpack": (C.c_int, [vp, vp, i64, vp]),
         "eut_cells_create": (C.c_int, [C.POINTER(vp), vp]),
@@ -114,7 +115,7 @@ EXPORTS = (
     "eut_field_diffuse eut_field_sync eut_field_stream eut_field_set_stream "
     "eut_field_launch_count eut_field_set_option eut_field_column_stats eut_field_fill_column "
     "eut_field_exoenzyme_catalysis eut_field_scale_column "
-    "eut_field_halo_set eut_field_halo_pack eut_field_halo_unpack "
+    "eut_field_halo_set eut_field_set_halo_stream eut_field_halo_pack eut_field_halo_unpack "
     "eut_cells_create eut_cells_destroy eut_cells_set_lists eut_cells_build_lists "
     "eut_cells_claim_rescale eut_cells_num_entries eut_cells_get_lists eut_cells_gather "
     "eut_cells_scatter"

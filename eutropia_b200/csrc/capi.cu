@@ -227,6 +227,7 @@ int eut_field_set_option(eut_field *f, const char *name, int64_t value)
     else if (n == "ppt") f->opt_ppt = (int)value;
     else if (n == "debug") f->opt_debug = (int)value;
     else if (n == "shape") f->opt_shape = (int)value;
+    else if (n == "phase") f->opt_phase = (int)value;
     else { set_error("eut_field_set_option: unknown option '%s'", name); return EUT_ERR_ARG; }
     return EUT_OK;
 }

@@ -209,6 +209,11 @@ struct eut_field {
     int32_t *d_halo_send = nullptr, *d_halo_recv = nullptr, *d_halo_cols = nullptr;
     std::vector<int32_t> h_halo_cols;
     int64_t n_halo_send = 0, n_halo_recv = 0;
+    cudaStream_t halo_stream = nullptr;   // pack / unpack run here when set (overlap with interior tiles)
+    // slab overlap: tiles that hold points a neighbour reads (boundary) and the rest (interior)
+    int32_t *d_tiles_b = nullptr, *d_tiles_i = nullptr;
+    int n_tiles_b = 0, n_tiles_i = 0;
+    int opt_phase = 0;       // 0: all tiles; 1: boundary tiles, then flip; 2: interior tiles of the substep just flipped
 };
 
 namespace eut {

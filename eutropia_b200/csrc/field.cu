@@ -72,7 +72,7 @@ int field_destroy(eut_field *f)
     if (f->down_stream) cudaStreamSynchronize(f->down_stream);
     cudaFree(f->d_buf); cudaFree(f->d_cur); cudaFree(f->d_act); cudaFree(f->d_cols);
     cudaFree(f->d_stats); cudaFree(f->d_stage); cudaFree(f->d_stage2);
-    cudaFree(f->d_halo_send); cudaFree(f->d_halo_recv); cudaFree(f->d_halo_cols);
+    cudaFree(f->d_halo_send); cudaFree(f->d_halo_recv); cudaFree(f->d_halo_cols); cudaFree(f->d_tiles_b); cudaFree(f->d_tiles_i);
     for (int i = 0; i < 2; i++) {
         if (f->ev_stage_free[i]) cudaEventDestroy(f->ev_stage_free[i]);
         if (f->ev_stage_ready[i]) cudaEventDestroy(f->ev_stage_ready[i]);
@@ -214,10 +214,17 @@ int field_diffuse(eut_field *f, const int32_t *niter, const int32_t *indvar, int
     std::stable_sort(order.begin(), order.end(),
                      [&](int64_t a, int64_t b) { return niter[a] > niter[b]; });
     const int n_tot = (int)order.size();
+    // phase 1 / 2 (slab overlap): one substep in two launches, boundary tiles first; phase 2 completes
+    // the substep phase 1 has already flipped, so it reads the buffer the column was in before
+    const int phase = (f->plan->segmented && f->opt_variant != 1 && f->d_tiles_b) ? f->opt_phase : 0;
+    if (f->opt_phase != 0 && (phase == 0 || niter[order[0]] != 1)) {
+        set_error("eut_field_diffuse: phase %d needs a segment plan with halo lists and exactly one substep", f->opt_phase);
+        return EUT_ERR_ARG;
+    }
     for (int a = 0; a < n_tot; a++) {
         const int c = indvar[order[a]] - 1;
         f->h_act[a] = c;
-        f->h_act[f->act_cap + a] = f->cur[c];
+        f->h_act[f->act_cap + a] = phase == 2 ? (f->cur[c] ^ 1) : f->cur[c];
     }
     EUT_CUDA(cudaMemcpyAsync(f->d_act, f->h_act.data(), n_tot * sizeof(int32_t),
                              cudaMemcpyHostToDevice, f->stream));
@@ -244,7 +251,10 @@ int field_diffuse(eut_field *f, const int32_t *niter, const int32_t *indvar, int
     mix((uint64_t)f->opt_cpt); mix((uint64_t)f->opt_variant); mix((uint64_t)f->opt_nbuf); mix((uint64_t)f->opt_debug);
     mix((uint64_t)f->opt_ppt); mix((uint64_t)f->opt_shape); mix((uint64_t)f->opt_group_cols);
     const auto hit = f->graphs.find(key);
-    if (hit != f->graphs.end()) {
+    if (phase != 0) {
+        EUT_TRY(run_loop());
+        if (phase == 2) return EUT_OK;                  // the flip happened in phase 1
+    } else if (hit != f->graphs.end()) {
         if (hit->second) { EUT_CUDA(cudaGraphLaunch(hit->second, f->stream)); f->launches += max_it; }
         else EUT_TRY(run_loop());                       // capture failed once: plain launches
     } else if (!no_graphs && max_it >= 4 && f->graph_seen.count(key) && f->graphs.size() < 64) {

@@ -51,7 +51,7 @@ static int upload_cols(eut_field *f, const int32_t *cols, int64_t n_cols, int32_
         if (cols[j] < 1 || cols[j] > f->C) { set_error("halo: column %d out of bounds", cols[j]); return EUT_ERR_INDEX; }
         hc[j] = cols[j] - 1;
     }
-    EUT_CUDA(cudaMemcpyAsync(f->d_halo_cols, hc, n_cols * sizeof(int32_t), cudaMemcpyHostToDevice, f->stream));
+    EUT_CUDA(cudaMemcpyAsync(f->d_halo_cols, hc, n_cols * sizeof(int32_t), cudaMemcpyHostToDevice, f->halo_stream ? f->halo_stream : f->stream));
     *d_cols = f->d_halo_cols;
     return EUT_OK;
 }
@@ -85,6 +85,41 @@ int eut_field_halo_set(eut_field *f, const int32_t *send_ids, int64_t n_send, co
     f->h_halo_cols.assign(std::max<size_t>(f->C, 1), 0);
     f->n_halo_send = n_send;
     f->n_halo_recv = n_recv;
+    // boundary / interior tile lists of the segment plan: a substep can then run the boundary tiles
+    // first, and the exchange of their results overlaps the interior tiles (eut_field_set_option
+    // "phase", eutropia_b200/slab.py)
+    cudaFree(f->d_tiles_b); cudaFree(f->d_tiles_i);
+    f->d_tiles_b = f->d_tiles_i = nullptr;
+    f->n_tiles_b = f->n_tiles_i = 0;
+    if (f->plan->segmented) {
+        const auto &meta = f->plan->segs.meta;
+        const int nt = f->plan->n_tiles;
+        std::vector<int32_t> t0(nt);
+        for (int t = 0; t < nt; t++) t0[t] = meta[(size_t)t * 12];
+        std::vector<uint8_t> is_b(nt, 0);
+        // tiles with points a neighbour reads, and tiles with ghost points: a substep copies a ghost's
+        // old value forward, which must happen before -- not while -- the unpack overwrites it
+        for (const std::vector<int32_t> *lst : {&ps, &pr})
+            for (int32_t q : *lst) {
+                const int t = (int)(std::upper_bound(t0.begin(), t0.end(), q) - t0.begin()) - 1;
+                if (t >= 0 && q < meta[(size_t)t * 12] + meta[(size_t)t * 12 + 1]) is_b[t] = 1;
+            }
+        std::vector<int32_t> tb, ti;
+        for (int t = 0; t < nt; t++) (is_b[t] ? tb : ti).push_back(t);
+        EUT_CUDA(cudaMalloc((void **)&f->d_tiles_b, std::max<size_t>(tb.size(), 1) * sizeof(int32_t)));
+        EUT_CUDA(cudaMalloc((void **)&f->d_tiles_i, std::max<size_t>(ti.size(), 1) * sizeof(int32_t)));
+        if (!tb.empty()) EUT_CUDA(cudaMemcpy(f->d_tiles_b, tb.data(), tb.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        if (!ti.empty()) EUT_CUDA(cudaMemcpy(f->d_tiles_i, ti.data(), ti.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        f->n_tiles_b = (int)tb.size(); f->n_tiles_i = (int)ti.size();
+    }
+    return EUT_OK;
+}
+
+int eut_field_set_halo_stream(eut_field *f, void *stream)
+{
+    clear_error();
+    if (!f) return EUT_ERR_ARG;
+    f->halo_stream = (cudaStream_t)stream;
     return EUT_OK;
 }
 
@@ -98,7 +133,7 @@ int eut_field_halo_pack(eut_field *f, const int32_t *cols, int64_t n_cols, void 
     int32_t *d_cols = nullptr;
     EUT_TRY(upload_cols(f, cols, n_cols, &d_cols));
     dim3 grid((unsigned)((f->n_halo_send + 255) / 256), (unsigned)n_cols, 1);
-    k_halo_pack<<<grid, 256, 0, f->stream>>>(f->d_buf, f->plan->Np, f->C * f->plan->Np, f->d_cur, d_cols,
+    k_halo_pack<<<grid, 256, 0, f->halo_stream ? f->halo_stream : f->stream>>>(f->d_buf, f->plan->Np, f->C * f->plan->Np, f->d_cur, d_cols,
                                              f->d_halo_send, (int)f->n_halo_send, (double *)dev_out);
     f->launches++;
     EUT_CUDA(cudaGetLastError());
@@ -115,7 +150,7 @@ int eut_field_halo_unpack(eut_field *f, const int32_t *cols, int64_t n_cols, con
     int32_t *d_cols = nullptr;
     EUT_TRY(upload_cols(f, cols, n_cols, &d_cols));
     dim3 grid((unsigned)((f->n_halo_recv + 255) / 256), (unsigned)n_cols, 1);
-    k_halo_unpack<<<grid, 256, 0, f->stream>>>(f->d_buf, f->plan->Np, f->C * f->plan->Np, f->d_cur, d_cols,
+    k_halo_unpack<<<grid, 256, 0, f->halo_stream ? f->halo_stream : f->stream>>>(f->d_buf, f->plan->Np, f->C * f->plan->Np, f->d_cur, d_cols,
                                                f->d_halo_recv, (int)f->n_halo_recv, (const double *)dev_in);
     f->launches++;
     EUT_CUDA(cudaGetLastError());

@@ -96,7 +96,8 @@ k_substep_seg(double *__restrict__ buf, const int64_t col_stride, const int64_t 
               const uint4 *__restrict__ segs, const uint4 *__restrict__ gens,
               const double *__restrict__ wout, const int32_t *__restrict__ act_col,
               const int32_t *__restrict__ act_par, const int n_act, const int substep,
-              const int img_bytes, const int out_bytes, const int cols_per_cta, const int dbg)
+              const int img_bytes, const int out_bytes, const int cols_per_cta, const int dbg,
+              const int32_t *__restrict__ tile_list)
 {
     constexpr int THREADS = (CWARPS + 1) * 32;
     constexpr int CTHREADS = CWARPS * 32;
@@ -108,7 +109,7 @@ k_substep_seg(double *__restrict__ buf, const int64_t col_stride, const int64_t 
     __shared__ long long s_src[kTileMaxCols], s_dst[kTileMaxCols];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const int tile = blockIdx.x;
+    const int tile = tile_list ? __ldg(tile_list + blockIdx.x) : (int)blockIdx.x;
     const int a_begin = blockIdx.y * cols_per_cta;
     const int n_cols = min(n_act, a_begin + cols_per_cta) - a_begin;
     if (n_cols <= 0) return;
@@ -356,13 +357,17 @@ static int launch_seg_t(eut_field *f, int n_act, int substep)
         set_error("segment kernel: %zu bytes of shared memory per CTA", smem);
         return EUT_ERR_UNSUPPORTED;
     }
+    // slab overlap (halo.cu): only the boundary or only the interior tiles
+    const int32_t *tile_list = f->opt_phase == 1 ? f->d_tiles_b : (f->opt_phase == 2 ? f->d_tiles_i : nullptr);
+    const int n_tiles = f->opt_phase == 1 ? f->n_tiles_b : (f->opt_phase == 2 ? f->n_tiles_i : p->n_tiles);
+    if (n_tiles == 0) return EUT_OK;
     int slices = 1;
     const int64_t want = 6ll * 148 * MINB;          // ~6 waves: the tail of the last wave stays small
-    while ((int64_t)p->n_tiles * slices < want && slices < n_act) slices++;
+    while ((int64_t)n_tiles * slices < want && slices < n_act) slices++;
     if (f->opt_cpt > 0) slices = (n_act + f->opt_cpt - 1) / f->opt_cpt;
     slices = std::max(slices, (n_act + kTileMaxCols - 1) / kTileMaxCols);
     const int cols_per_cta = (n_act + slices - 1) / slices;
-    dim3 grid((unsigned)p->n_tiles, (unsigned)((n_act + cols_per_cta - 1) / cols_per_cta), 1);
+    dim3 grid((unsigned)n_tiles, (unsigned)((n_act + cols_per_cta - 1) / cols_per_cta), 1);
     auto kern = k_substep_seg<R, SPT, CWARPS, NBUF, OB, MINB>;
     static bool attr_set[64] = {false};
     if (!attr_set[p->device & 63]) {
@@ -371,7 +376,7 @@ static int launch_seg_t(eut_field *f, int n_act, int substep)
     }
     kern<<<grid, (CWARPS + 1) * 32, smem, f->stream>>>(f->d_buf, p->Np, f->C * p->Np, p->d_seg_meta, p->d_copies,
                                                        p->d_segs, p->d_gens, p->d_w, f->d_act, f->d_act + f->act_cap,
-                                                       n_act, substep, img_bytes, out_bytes, cols_per_cta, f->opt_debug);
+                                                       n_act, substep, img_bytes, out_bytes, cols_per_cta, f->opt_debug, tile_list);
     return EUT_OK;
 }
 

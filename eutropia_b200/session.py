@@ -196,6 +196,9 @@ class Field:
         s, r = _i32(send_ids), _i32(recv_ids)
         check(_lib.lib().eut_field_halo_set(self._h, ptr(s), s.shape[0], ptr(r), r.shape[0]))
 
+    def set_halo_stream(self, stream_ptr):
+        check(_lib.lib().eut_field_set_halo_stream(self._h, C.c_void_p(stream_ptr) if stream_ptr else None))
+
     def halo_pack(self, cols, dev_ptr: int):
         c = _i32(cols)
         check(_lib.lib().eut_field_halo_pack(self._h, ptr(c), c.shape[0], C.c_void_p(dev_ptr)))

@@ -19,6 +19,8 @@ tests/test_slab_gloo.py, where a test backend stands in for the device).
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from . import _lib
@@ -121,6 +123,10 @@ class GpuSlabBackend:
             self.h_send = torch.zeros_like(self.send, device="cpu")
             self.h_recv = torch.zeros_like(self.recv, device="cpu")
         self.stream = torch.cuda.ExternalStream(self.field.stream, device=dev)
+        # overlap of the exchange with the interior tiles: boundary tiles first, their results travel on
+        # a second stream while the interior tiles run (needs the segment plan's tile lists)
+        self.overlap = (not self.host_staged) and bool(self.plan.info.segmented) and os.environ.get("EUT_SLAB_OVERLAP", "1") != "0"
+        self.comm_stream = torch.cuda.Stream(device=dev) if self.overlap else None
 
     def close(self):
         """Release device objects in a safe order (torch tensors first, then the field's stream)."""
@@ -135,6 +141,30 @@ class GpuSlabBackend:
 
     def substep(self, cols):
         self.field.diffuse(np.ones(len(cols), dtype=np.int32), cols)
+
+    def substep_overlapped(self, cols, exchange):
+        """One substep with the halo exchange hidden behind the interior tiles: boundary tiles (and the
+        buffer flip) on the field's stream; pack -> `exchange()` -> unpack on the comm stream; interior
+        tiles on the field's stream meanwhile; the field's stream finally waits for the unpack."""
+        torch = self.torch
+        ones = np.ones(len(cols), dtype=np.int32)
+        self.field.set_option("phase", 1)
+        self.field.diffuse(ones, cols)
+        ev = torch.cuda.Event()
+        ev.record(self.stream)
+        self.comm_stream.wait_event(ev)
+        self.field.set_halo_stream(self.comm_stream.cuda_stream)
+        with torch.cuda.stream(self.comm_stream):
+            self.field.halo_pack(cols, self.send.data_ptr())
+            exchange(self.send, self.recv)
+            self.field.halo_unpack(cols, self.recv.data_ptr())
+            done = torch.cuda.Event()
+            done.record(self.comm_stream)
+        self.field.set_halo_stream(None)
+        self.field.set_option("phase", 2)
+        self.field.diffuse(ones, cols)
+        self.field.set_option("phase", 0)
+        self.stream.wait_event(done)
 
     def pack(self, cols):
         self.field.halo_pack(cols, self.send.data_ptr())
@@ -192,6 +222,11 @@ class SlabDriver:
                 cols = indvar[niter > s]
                 if cols.size == 0:
                     break
+                if self.part.peers and getattr(self.backend, "overlap", False):
+                    n_c = int(cols.size)
+                    self.backend.substep_overlapped(
+                        cols, lambda send, recv: exchange_halo(self.part, send, recv, n_c, self.dist))
+                    continue
                 self.backend.substep(cols)
                 if self.part.peers:
                     send = self.backend.pack(cols)

@@ -233,6 +233,13 @@ EUT_API int eut_field_scale_column(eut_field *field, int32_t col, double factor)
 /* Overwrite a column with one value (D = Inf -> column mean, R/growthEnvironment.R:393-401). */
 EUT_API int eut_field_fill_column(eut_field *field, int32_t col, double value);
 
+/* Run eut_field_halo_pack / _unpack on `stream` (a cudaStream_t; NULL = the field's stream), so that
+ * the exchange of the boundary tiles' results overlaps the interior tiles of the same substep:
+ *   eut_field_set_option(f, "phase", 1); eut_field_diffuse(one substep)   -- boundary tiles, flip
+ *   [halo stream waits; pack -> send/recv -> unpack on the halo stream]
+ *   eut_field_set_option(f, "phase", 2); eut_field_diffuse(same call)      -- interior tiles, no flip
+ *   [field stream waits for the halo stream]; eut_field_set_option(f, "phase", 0) when done. */
+EUT_API int eut_field_set_halo_stream(eut_field *field, void *stream);
 /* Halo support for spatial slab sharding (one process per GPU, each with the plan of its slab: own
  * points + ghost copies of the remote in-neighbours; eutropia_b200/slab.py builds those).  The
  * reference has no counterpart (it runs on one host); the exchange itself is done by the caller
