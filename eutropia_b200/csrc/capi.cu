@@ -377,6 +377,16 @@ int run_pipeline(CachedPlan *cp, const double *conc_in, int64_t n_rows, int64_t 
         cp->field_cols = n_cols;
     }
     eut_field *f = cp->field;
+    // EUT_ONESHOT_STREAM=1: column streaming (field.cu: one launch at a time over all columns that have
+    // arrived).  Measured equal to the chunked pipeline below (157 vs 160 G updates/s): what both pay
+    // for is the fixed cost of a launch over few columns (~26 us), and the chunked one replays CUDA graphs.
+    static const bool streaming = getenv("EUT_ONESHOT_STREAM") != nullptr;
+    if (streaming && act.size() >= 2) {
+        std::vector<int32_t> scols(act.size()), snit(act.size());
+        for (size_t a = 0; a < act.size(); a++) { scols[a] = indvar[act[a]]; snit[a] = niter[act[a]]; }
+        const int rc = field_stream_columns(f, conc_in, conc_out, n_rows, scols.data(), snit.data(), (int64_t)act.size(), verify);
+        return rc == -1000 ? kRetry : rc;
+    }
     // Pipeline over chunks of active columns: H2D(g+1) | substeps(g) | D2H(g-1) on three streams.
     // The call lasts  H2D(first chunk) + all substeps + D2H(last chunk), and a launch over few columns
     // is less efficient than one over many (tools/cols_scaling.py): the chunks ramp up 1/8, 3/8, 1, ...

@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <set>
 #include <string>
@@ -179,6 +180,12 @@ struct eut_field {
     // active-column tables of the current diffuse call
     int32_t *d_act = nullptr;          // [2][cap]: column, starting buffer
     int64_t act_cap = 0;
+    // the tables the substep launch reads (default: d_act; the column-streaming pipeline points them
+    // at a ring of per-launch tables)
+    const int32_t *act_col = nullptr, *act_par = nullptr;
+    int32_t *d_ring = nullptr, *h_ring = nullptr;   // [kRing][2][cap] device / pinned host
+    int32_t *d_stream_cols = nullptr;                // [3][C]: column list, zeros, final buffer of each column
+    std::vector<cudaEvent_t> ev_pool;
     std::vector<int32_t> h_act;        // host mirror (kept alive for async copies)
     int32_t *d_cur = nullptr;          // [C] device mirror of cur
     std::vector<int32_t> h_cur32;
@@ -233,6 +240,11 @@ int field_upload(eut_field *f, const double *host, int64_t ld, const int32_t *co
 int field_download_async(eut_field *f, double *host, int64_t ld, const int32_t *cols, int64_t n_cols);
 int field_sync_down(eut_field *f);
 int field_diffuse(eut_field *f, const int32_t *niter, const int32_t *indvar, int64_t n_indvar);
+// one-shot tier, column streaming: upload, diffuse and download `n` columns (1-based `cols`) with the
+// substeps of a column starting as soon as it has arrived; `verify` is called before the first byte is
+// written to h_out (false -> returns -1000 after draining the streams)
+int field_stream_columns(eut_field *f, const double *h_in, double *h_out, int64_t ld, const int32_t *cols,
+                         const int32_t *niter, int64_t n, const std::function<bool()> &verify);
 
 // stencil.cu
 int launch_substep(eut_field *f, int n_act, int substep);

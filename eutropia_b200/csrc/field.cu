@@ -81,6 +81,9 @@ int field_destroy(eut_field *f)
     }
     for (auto &g : f->graphs)
         if (g.second) cudaGraphExecDestroy(g.second);
+    for (cudaEvent_t e : f->ev_pool) cudaEventDestroy(e);
+    cudaFree(f->d_ring); cudaFree(f->d_stream_cols);
+    if (f->h_ring) cudaFreeHost(f->h_ring);
     if (f->own_stream && f->stream) cudaStreamDestroy(f->stream);
     if (f->copy_stream) cudaStreamDestroy(f->copy_stream);
     if (f->down_stream) cudaStreamDestroy(f->down_stream);
@@ -226,6 +229,7 @@ int field_diffuse(eut_field *f, const int32_t *niter, const int32_t *indvar, int
         f->h_act[a] = c;
         f->h_act[f->act_cap + a] = phase == 2 ? (f->cur[c] ^ 1) : f->cur[c];
     }
+    f->act_col = f->d_act; f->act_par = f->d_act + f->act_cap;
     EUT_CUDA(cudaMemcpyAsync(f->d_act, f->h_act.data(), n_tot * sizeof(int32_t),
                              cudaMemcpyHostToDevice, f->stream));
     EUT_CUDA(cudaMemcpyAsync(f->d_act + f->act_cap, f->h_act.data() + f->act_cap,
@@ -285,6 +289,134 @@ int field_diffuse(eut_field *f, const int32_t *niter, const int32_t *indvar, int
     }
     EUT_CUDA(cudaMemcpyAsync(f->d_cur, f->h_cur32.data(), f->C * sizeof(int32_t),
                              cudaMemcpyHostToDevice, f->stream));
+    return EUT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Column streaming (one-shot tier).  The chunked pipeline lasts H2D(first chunk) + all substeps +
+// D2H(last chunk) and pays for narrow launches at both ends.  Here every group of `G` columns is
+// uploaded on the copy stream back to back, and the host feeds the compute stream ONE substep launch
+// at a time over "all columns that have arrived and are not finished": the set widens while the
+// upload runs (9 ms for 64 columns of 1 M points) and narrows as columns finish, each column keeps
+// its own buffer parity in the per-launch table, finished groups leave on the download stream
+// while the others go on.  The host keeps at most kInFlight launches queued so that a group that
+// has just arrived joins the next launch.
+// ---------------------------------------------------------------------------------------------
+int field_stream_columns(eut_field *f, const double *h_in, double *h_out, int64_t ld, const int32_t *cols,
+                         const int32_t *niter, int64_t n64, const std::function<bool()> &verify)
+{
+    const eut_plan *p = f->plan;
+    const int64_t N = p->N;
+    const int n = (int)n64;
+    if (n == 0 || N == 0) return EUT_OK;
+    constexpr int kRing = 16;
+    static const int kInFlight = [] { const char *e = getenv("EUT_STREAM_DEPTH"); return std::min(12, std::max(1, e ? atoi(e) : 6)); }();
+    static const int G = [] { const char *e = getenv("EUT_STREAM_GROUP"); return std::max(1, e ? atoi(e) : 4); }();
+    const int ng = (n + G - 1) / G;
+    const int64_t cap = f->act_cap;
+    if (!f->d_ring) {
+        EUT_CUDA(cudaMalloc((void **)&f->d_ring, (size_t)kRing * 2 * cap * sizeof(int32_t)));
+        EUT_CUDA(cudaHostAlloc((void **)&f->h_ring, (size_t)kRing * 2 * cap * sizeof(int32_t), cudaHostAllocDefault));
+        EUT_CUDA(cudaMalloc((void **)&f->d_stream_cols, (size_t)3 * cap * sizeof(int32_t)));
+    }
+    while ((int)f->ev_pool.size() < ng + kRing) {
+        cudaEvent_t e;
+        EUT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        f->ev_pool.push_back(e);
+    }
+    cudaEvent_t *up_ev = f->ev_pool.data(), *launch_ev = f->ev_pool.data() + ng;
+    // column list (act order), zeros (every column is uploaded into buffer 0), final buffer per column
+    std::vector<int32_t> h3((size_t)3 * cap, 0);
+    for (int i = 0; i < n; i++) { h3[i] = cols[i] - 1; h3[2 * cap + (cols[i] - 1)] = niter[i] & 1; }
+    EUT_CUDA(cudaMemcpyAsync(f->d_stream_cols, h3.data(), h3.size() * sizeof(int32_t), cudaMemcpyHostToDevice, f->copy_stream));
+    EUT_CUDA(cudaStreamSynchronize(f->copy_stream));          // h3 is pageable; also: previous calls are drained
+    const int32_t *d_list = f->d_stream_cols, *d_zero = f->d_stream_cols + cap, *d_final = f->d_stream_cols + 2 * cap;
+    // staging rings: slots of G columns inside the two halves of d_stage / d_stage2
+    const int64_t slots = std::max<int64_t>(1, 2 * f->stage_cols / G);
+    // ---- uploads: all groups, back to back, on the copy stream (H2D, then the permute kernel) -------
+    for (int g = 0; g < ng; g++) {
+        const int j0 = g * G, nc = std::min(G, n - j0);
+        double *stage = f->d_stage + (size_t)(g % slots) * G * N;
+        bool contiguous = true;
+        for (int j = 1; j < nc; j++) contiguous &= (cols[j0 + j] == cols[j0 + j - 1] + 1);
+        if (contiguous)
+            EUT_CUDA(cudaMemcpy2DAsync(stage, N * sizeof(double), h_in + (size_t)(cols[j0] - 1) * ld, ld * sizeof(double),
+                                       N * sizeof(double), nc, cudaMemcpyHostToDevice, f->copy_stream));
+        else
+            for (int j = 0; j < nc; j++)
+                EUT_CUDA(cudaMemcpyAsync(stage + (size_t)j * N, h_in + (size_t)(cols[j0 + j] - 1) * ld, N * sizeof(double),
+                                         cudaMemcpyHostToDevice, f->copy_stream));
+        EUT_TRY(launch_permute_in(f, stage, N, d_list + j0, d_zero, nc, f->copy_stream));
+        EUT_CUDA(cudaEventRecord(up_ev[g], f->copy_stream));
+    }
+    // ---- substeps ---------------------------------------------------------------------------------
+    std::vector<int> remaining(n), par(n, 0), group_left(ng, 0);
+    for (int i = 0; i < n; i++) { remaining[i] = niter[i]; group_left[i / G]++; }
+    std::vector<int> active;
+    int arrived = 0, n_done = 0, k = 0;
+    bool verified = !verify;
+    auto absorb = [&]() {
+        while (arrived < ng && cudaEventQuery(up_ev[arrived]) == cudaSuccess) {
+            for (int i = arrived * G; i < std::min(n, (arrived + 1) * G); i++) active.push_back(i);
+            arrived++;
+        }
+    };
+    int down_slot = 0;
+    while (n_done < n) {
+        absorb();
+        if (active.empty()) { EUT_CUDA(cudaEventSynchronize(up_ev[arrived])); continue; }
+        if (k >= kInFlight) {
+            while (cudaEventQuery(launch_ev[(k - kInFlight) % kRing]) == cudaErrorNotReady) absorb();
+        }
+        const int na = (int)active.size();
+        int32_t *hr = f->h_ring + (size_t)(k % kRing) * 2 * cap, *dr = f->d_ring + (size_t)(k % kRing) * 2 * cap;
+        for (int a = 0; a < na; a++) { hr[a] = cols[active[a]] - 1; hr[na + a] = par[active[a]]; }
+        EUT_CUDA(cudaMemcpyAsync(dr, hr, 2 * na * sizeof(int32_t), cudaMemcpyHostToDevice, f->stream));
+        f->act_col = dr; f->act_par = dr + na;
+        EUT_TRY(launch_substep(f, na, 0));
+        EUT_CUDA(cudaEventRecord(launch_ev[k % kRing], f->stream));
+        // bookkeeping; finished columns leave the set, finished groups leave the device
+        size_t w = 0;
+        for (size_t a = 0; a < active.size(); a++) {
+            const int i = active[a];
+            par[i] ^= 1;
+            if (--remaining[i] > 0) { active[w++] = i; continue; }
+            n_done++;
+            const int g = i / G;
+            if (--group_left[g] == 0) {
+                if (!verified) {
+                    if (!verify()) {
+                        cudaStreamSynchronize(f->copy_stream); cudaStreamSynchronize(f->stream); cudaStreamSynchronize(f->down_stream);
+                        f->act_col = f->d_act; f->act_par = f->d_act + f->act_cap;
+                        return -1000;
+                    }
+                    verified = true;
+                }
+                const int j0 = g * G, nc = std::min(G, n - j0);
+                double *stage = f->d_stage2 + (size_t)(down_slot++ % slots) * G * N;
+                EUT_CUDA(cudaStreamWaitEvent(f->down_stream, launch_ev[k % kRing], 0));
+                EUT_TRY(launch_permute_out(f, stage, N, d_list + j0, d_final, nc, f->down_stream));
+                bool contiguous = true;
+                for (int j = 1; j < nc; j++) contiguous &= (cols[j0 + j] == cols[j0 + j - 1] + 1);
+                if (contiguous)
+                    EUT_CUDA(cudaMemcpy2DAsync(h_out + (size_t)(cols[j0] - 1) * ld, ld * sizeof(double), stage, N * sizeof(double),
+                                               N * sizeof(double), nc, cudaMemcpyDeviceToHost, f->down_stream));
+                else
+                    for (int j = 0; j < nc; j++)
+                        EUT_CUDA(cudaMemcpyAsync(h_out + (size_t)(cols[j0 + j] - 1) * ld, stage + (size_t)j * N, N * sizeof(double),
+                                                 cudaMemcpyDeviceToHost, f->down_stream));
+            }
+        }
+        active.resize(w);
+        k++;
+    }
+    f->act_col = f->d_act; f->act_par = f->d_act + f->act_cap;
+    for (int i = 0; i < n; i++) {
+        const int c = cols[i] - 1;
+        f->cur[c] = (uint8_t)(niter[i] & 1);
+        f->h_cur32[c] = f->cur[c];
+    }
+    EUT_CUDA(cudaMemcpyAsync(f->d_cur, f->h_cur32.data(), f->C * sizeof(int32_t), cudaMemcpyHostToDevice, f->stream));
     return EUT_OK;
 }
 

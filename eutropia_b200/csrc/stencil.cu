@@ -310,7 +310,7 @@ static int launch_tile_t(eut_field *f, int n_act, int substep)
         attr_set[p->device & 63] = true;
     }
     kern<<<grid, THREADS, smem, f->stream>>>(f->d_buf, p->Np, f->C * p->Np, p->d_tile_meta, p->d_copies,
-                                             p->d_loc16, p->d_deg, p->d_w, f->d_act, f->d_act + f->act_cap,
+                                             p->d_loc16, p->d_deg, p->d_w, f->act_col, f->act_par,
                                              n_act, substep, img_bytes, cols_per_cta);
     return EUT_OK;
 }
@@ -339,7 +339,7 @@ static int launch_ell_w(eut_field *f, int n_act, int substep)
     // pieces); gap cells have degree 0 and weight 0 and keep their value
     dim3 grid((unsigned)((p->Np + block - 1) / block), 1, 1);
     const int64_t bs = f->C * p->Np;
-    const int32_t *act_col = f->d_act, *act_par = f->d_act + f->act_cap;
+    const int32_t *act_col = f->act_col, *act_par = f->act_par;
 #define EUT_LAUNCH_ELL(CPT)                                                                      \
     grid.y = (unsigned)((n_act + CPT - 1) / CPT);                                                \
     k_substep_ell<W, CPT><<<grid, block, 0, f->stream>>>(f->d_buf, p->Np, bs, p->d_nbr, p->d_deg, \
@@ -371,8 +371,8 @@ int launch_substep(eut_field *f, int n_act, int substep)
         const int block = 256;
         dim3 grid((unsigned)((p->N + block - 1) / block), (unsigned)n_act, 1);
         k_substep_csr<<<grid, block, 0, f->stream>>>(f->d_buf, p->Np, bs, p->d_row_ptr, p->d_col,
-                                                     p->d_out_ptr, p->d_out_w, f->d_act,
-                                                     f->d_act + f->act_cap, n_act, substep,
+                                                     p->d_out_ptr, p->d_out_w, f->act_col,
+                                                     f->act_par, n_act, substep,
                                                      (int)p->N);
     }
     f->launches++;

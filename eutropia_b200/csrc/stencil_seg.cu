@@ -375,7 +375,7 @@ static int launch_seg_t(eut_field *f, int n_act, int substep)
         attr_set[p->device & 63] = true;
     }
     kern<<<grid, (CWARPS + 1) * 32, smem, f->stream>>>(f->d_buf, p->Np, f->C * p->Np, p->d_seg_meta, p->d_copies,
-                                                       p->d_segs, p->d_gens, p->d_w, f->d_act, f->d_act + f->act_cap,
+                                                       p->d_segs, p->d_gens, p->d_w, f->act_col, f->act_par,
                                                        n_act, substep, img_bytes, out_bytes, cols_per_cta, f->opt_debug, tile_list);
     return EUT_OK;
 }

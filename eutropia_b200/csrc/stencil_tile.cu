@@ -203,7 +203,7 @@ static int launch_u(eut_field *f, int n_act, int substep)
         attr_set[p->device & 63] = true;
     }
     kern<<<grid, THREADS, smem, f->stream>>>(f->d_buf, p->Np, f->C * p->Np, p->d_tile_meta, p->d_copies,
-                                             p->d_loc16, p->d_deg, p->d_w, f->d_act, f->d_act + f->act_cap,
+                                             p->d_loc16, p->d_deg, p->d_w, f->act_col, f->act_par,
                                              n_act, substep, img_bytes, cols_per_cta);
     return EUT_OK;
 }
