@@ -361,9 +361,11 @@ static int launch_seg_t(eut_field *f, int n_act, int substep)
     const int32_t *tile_list = f->opt_phase == 1 ? f->d_tiles_b : (f->opt_phase == 2 ? f->d_tiles_i : nullptr);
     const int n_tiles = f->opt_phase == 1 ? f->n_tiles_b : (f->opt_phase == 2 ? f->n_tiles_i : p->n_tiles);
     if (n_tiles == 0) return EUT_OK;
+    // slices of columns per tile: ~6 waves of CTAs keep the tail of the last wave small, but a CTA
+    // costs ~4 us before its first column (tables, first image), so it should get at least 16 columns
     int slices = 1;
-    const int64_t want = 6ll * 148 * MINB;          // ~6 waves: the tail of the last wave stays small
-    while ((int64_t)n_tiles * slices < want && slices < n_act) slices++;
+    const int64_t want = 6ll * 148 * MINB;
+    while ((int64_t)n_tiles * slices < want && slices < n_act && (n_act + slices) / (slices + 1) >= 16) slices++;
     if (f->opt_cpt > 0) slices = (n_act + f->opt_cpt - 1) / f->opt_cpt;
     slices = std::max(slices, (n_act + kTileMaxCols - 1) / kTileMaxCols);
     const int cols_per_cta = (n_act + slices - 1) / slices;

@@ -229,3 +229,22 @@ def test_one_shot_speculation_is_verified(small_mesh):
     assert np.array_equal(c, ref2) and not np.array_equal(c, ref)
     d = eb.diffChangePar(adj, nn, conc, niter, indvar)          # and the new graph is now the guess
     assert np.array_equal(d, ref2)
+
+
+def test_one_shot_streaming_pipeline_option(small_mesh, tmp_path):
+    """EUT_ONESHOT_STREAM=1 selects the column-streaming pipeline of the one-shot tier (read once per
+    process, hence the subprocess): same bits as the oracle, mixed substep counts included."""
+    import subprocess
+    import sys
+    m = small_mesh
+    conc = synth.synthetic_concentrations(m.field_pts, 11, seed=23)
+    niter = [9, 3, 12, 1, 7, 7, 2, 30, 5, 4, 8]
+    indvar = [1, 3, 2, 5, 4, 6, 8, 7, 11, 9, 10]
+    inp, outp = tmp_path / "in.npz", tmp_path / "out.npy"
+    np.savez(inp, mat_in=m.mat_in, mat_out=m.mat_out, conc=conc, niter=niter, indvar=indvar)
+    code = ("import numpy as np, eutropia_b200 as eb; g = np.load(r'%s'); "
+            "np.save(r'%s', eb.diffChangePar(g['mat_in'], g['mat_out'], g['conc'], g['niter'], g['indvar']))" % (inp, outp))
+    env = dict(os.environ, EUT_ONESHOT_STREAM="1", PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=300)
+    ref = oracle.diffChangePar(m.mat_in, m.mat_out, conc, niter, indvar, 2)
+    assert_parity(np.load(outp), ref)
