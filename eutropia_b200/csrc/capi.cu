@@ -224,7 +224,6 @@ int eut_field_set_option(eut_field *f, const char *name, int64_t value)
     else if (n == "variant") f->opt_variant = (int)value;
     else if (n == "group_cols") f->opt_group_cols = (int)value;
     else if (n == "nbuf") f->opt_nbuf = (int)value;
-    else if (n == "ppt") f->opt_ppt = (int)value;
     else if (n == "debug") f->opt_debug = (int)value;
     else if (n == "shape") f->opt_shape = (int)value;
     else if (n == "phase") f->opt_phase = (int)value;

@@ -210,7 +210,6 @@ struct eut_field {
     int opt_group_cols = 0;  // 0: substep-major over all active columns; >0: column groups
     int opt_nbuf = 3;        // staging depth of the tiled kernel (3 or 4 columns)
     int opt_debug = 0;
-    int opt_ppt = 0;         // > 0: use the first-generation tiled kernel with this many points per thread
     int opt_shape = 0;       // thread shape of the lean tiled kernel (stencil_tile.cu)
     // halo lists of a slab field (halo.cu)
     int32_t *d_halo_send = nullptr, *d_halo_recv = nullptr, *d_halo_cols = nullptr;

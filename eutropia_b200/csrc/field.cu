@@ -253,7 +253,7 @@ int field_diffuse(eut_field *f, const int32_t *niter, const int32_t *indvar, int
     auto mix = [&](uint64_t v) { key = (key ^ v) * 0x100000001b3ull; };
     for (int a = 0; a < n_tot; a++) mix((uint64_t)niter[order[a]]);
     mix((uint64_t)f->opt_cpt); mix((uint64_t)f->opt_variant); mix((uint64_t)f->opt_nbuf); mix((uint64_t)f->opt_debug);
-    mix((uint64_t)f->opt_ppt); mix((uint64_t)f->opt_shape); mix((uint64_t)f->opt_group_cols);
+    mix((uint64_t)f->opt_shape); mix((uint64_t)f->opt_group_cols);
     const auto hit = f->graphs.find(key);
     if (phase != 0) {
         EUT_TRY(run_loop());

@@ -1,5 +1,9 @@
-// Tiled substep kernel, instruction-lean version (the default).  Same tables, same staging scheme
-// and the same arithmetic as k_substep_tile in stencil.cu; what changes is the per-thread code:
+// Tiled substep kernel (tables from tiles.cu): the fallback of the segment kernel (stencil_seg.cu) for
+// plans the segment planner declines, and EUT_ORDER_TILED.  One CTA = one compact tile of <= 256*PPT
+// points and a slice of the active compound columns.  For every column the tile's image -- own points
+// plus halo runs -- is staged into shared memory NBUF columns deep: 16-byte aligned runs by
+// cp.async.bulk (UBLKCP, issued by warp 0, completing on an mbarrier with a transaction count), odd
+// ends and lone halo points by 8-byte cp.async; one __syncthreads per column.  Per thread:
 //
 //   * the image offsets of the 12 neighbour slots are kept UNPACKED, one 32-bit register each, so a
 //     neighbour load is a single `LDS.64 R, [Roff + URimage]` (no unpack, no address add);
@@ -8,10 +12,8 @@
 //     not a per-load predicate; unused slots of a point read the zero cell, which is exact;
 //   * the staging slot is a rotating counter (no modulo), all column bookkeeping is uniform.
 //
-// ncu on the previous version showed 80 issued instructions per point update of which 30 were
-// LDS/DADD/DMUL/STG; with 4 warps per scheduler the kernel was bound by instruction issue plus
-// fixed-latency stalls, not by shared memory or HBM (profiles/r01_v4_tile_lockstep_ncu.csv and the
-// "debug" experiments described in DESIGN.md).  This version issues ~30.
+// 13 shared-memory loads per update: bound by the LSU data pipe (profiles/r01_v6_tile_lean_ncu.csv),
+// which is what the segment kernel's register reuse addresses.
 #include <algorithm>
 
 #include "common.h"

@@ -1,5 +1,5 @@
 """Sweep tile-planner / kernel options and time the diffusion substep with CUDA events.
-usage: python tools/sweep.py workload cols "TILE_POINTS,TILE_COLS,nbuf,cpt[,variant[,ppt]]" ..."""
+usage: python tools/sweep.py workload cols "TILE_POINTS,TILE_COLS,nbuf,cpt[,variant]" ..."""
 import os
 import sys
 
@@ -20,7 +20,6 @@ for spec in sys.argv[3:]:
     parts = [int(x) for x in spec.split(",")]
     tp, tc, nbuf, cpt = parts[:4]
     variant = parts[4] if len(parts) > 4 else 0
-    ppt = parts[5] if len(parts) > 5 else 0
     dbg = parts[6] if len(parts) > 6 else 0
     shape = parts[7] if len(parts) > 7 else 0
     os.environ["EUT_TILE_POINTS"] = str(tp)
@@ -30,7 +29,6 @@ for spec in sys.argv[3:]:
     f.set_option("nbuf", nbuf)
     f.set_option("cpt", cpt)
     f.set_option("variant", variant)
-    f.set_option("ppt", ppt)
     f.set_option("debug", dbg)
     f.set_option("shape", shape)
     f.upload(conc)
