@@ -89,7 +89,11 @@ uint64_t hash_bytes(const void *data, size_t n, uint64_t seed)
     if (n <= 2 * kSlice) return hash_span(p, n, seed);
     const size_t n_slices = (n + kSlice - 1) / kSlice;
     std::vector<uint64_t> part(n_slices);
-    const unsigned n_thr = std::min<unsigned>(16, std::max(1u, std::thread::hardware_concurrency()));
+    // up to 16 threads, but not more than this process's share of the host when several ranks of a
+    // launcher run on it (LOCAL_WORLD_SIZE is exported by torchrun)
+    unsigned share = std::max(1u, std::thread::hardware_concurrency());
+    if (const char *e = getenv("LOCAL_WORLD_SIZE")) share = std::max(2u, share / (unsigned)std::max(1, atoi(e)));
+    const unsigned n_thr = std::min<unsigned>(16, share);
     std::vector<std::thread> pool;
     for (unsigned t = 0; t < n_thr; t++)
         pool.emplace_back([&, t]() {
