@@ -99,6 +99,7 @@ def lib() -> C.CDLL:
         "eut_cells_get_lists": (C.c_int, [vp, vp, vp, vp, vp]),
         "eut_cells_gather": (C.c_int, [vp, vp, dbl, vp]),
         "eut_cells_scatter": (C.c_int, [vp, vp, dbl, vp, vp, vp, vp]),
+        "eut_cells_chemotaxis_moments": (C.c_int, [vp, vp, i32, vp, i64, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -118,7 +119,7 @@ EXPORTS = (
     "eut_field_halo_set eut_field_set_halo_stream eut_field_halo_pack eut_field_halo_unpack "
     "eut_cells_create eut_cells_destroy eut_cells_set_lists eut_cells_build_lists "
     "eut_cells_claim_rescale eut_cells_num_entries eut_cells_get_lists eut_cells_gather "
-    "eut_cells_scatter"
+    "eut_cells_scatter eut_cells_chemotaxis_moments"
 ).split()
 
 

@@ -64,6 +64,12 @@ struct eut_cells {
     int64_t fmol_cap = 0;
     double *d_tfield = nullptr; // [Np x ldc] point-major copy of the field for the gather
     int64_t tfield_cap = 0;
+    double *d_pxy = nullptr;    // [2][Np] x, y of the field points by internal position (chemotaxis moments)
+    uint64_t pxy_hash = 0;
+    double *d_mom = nullptr;    // [7 x M] result of eut_cells_chemotaxis_moments
+    int64_t mom_cap = 0;
+    double *d_cxy = nullptr;    // [3 x M] cell x, y, sensing radius
+    int64_t cxy_cap = 0;
     double *d_exd = nullptr;    // [M x ldc] dense exchange factors per cell (scatter, second generation)
     int64_t exd_cap = 0;
     unsigned long long *d_exmask = nullptr;   // [M x ldc/64 x 2] bit c: the cell takes up / produces column c
@@ -736,6 +742,38 @@ k_scatter_t(double *__restrict__ buf, const int64_t col_stride, const int64_t bu
     }
 }
 
+// ---- chemotaxis moments (R/run_simulation.R:260-291) -------------------------------------------------
+// Per cell and chemotaxis compound the reference takes, over the cell's field list, the weighted mean of
+// the normalised offsets (dx, dy) = (field.xy - cell.xy) / (size/2 + scavengeDist) with weights
+// conc / sum(conc) (uniform when the sum is 0), and the weighted mean of conc itself.  The kernel
+// returns the sums those means are made of -- sum c, sum c^2, sum dx c, sum dy c, sum dx, sum dy, n --
+// as hi+lo accumulations (one warp per cell); the Hill term and the scaling stay with the caller.
+__global__ void __launch_bounds__(256)
+k_chemo_moments(const double *__restrict__ col, const double *__restrict__ px, const double *__restrict__ py,
+                const int64_t *__restrict__ cell_ptr, const int32_t *__restrict__ fq, const double *__restrict__ cxy,
+                double *__restrict__ out, const int n_cells)
+{
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= n_cells) return;
+    const double cx = cxy[i], cy = cxy[n_cells + i], rr = cxy[2 * (int64_t)n_cells + i];
+    dd s0{0, 0}, s1{0, 0}, sx{0, 0}, sy{0, 0}, ux{0, 0}, uy{0, 0};
+    for (int64_t k = cell_ptr[i] + lane; k < cell_ptr[i + 1]; k += 32) {
+        const int q = fq[k];
+        const double c = col[q];
+        const double dx = __ddiv_rn(__dsub_rn(px[q], cx), rr), dy = __ddiv_rn(__dsub_rn(py[q], cy), rr);   // :268-272
+        dd_add(s0, c); dd_add(s1, __dmul_rn(c, c));
+        dd_add(sx, __dmul_rn(dx, c)); dd_add(sy, __dmul_rn(dy, c));
+        dd_add(ux, dx); dd_add(uy, dy);
+    }
+    s0 = dd_warp_sum(s0); s1 = dd_warp_sum(s1); sx = dd_warp_sum(sx); sy = dd_warp_sum(sy);
+    ux = dd_warp_sum(ux); uy = dd_warp_sum(uy);
+    if (lane == 0) {
+        const int64_t M = n_cells;
+        out[i] = dd_value(s0); out[M + i] = dd_value(s1); out[2 * M + i] = dd_value(sx); out[3 * M + i] = dd_value(sy);
+        out[4 * M + i] = dd_value(ux); out[5 * M + i] = dd_value(uy); out[6 * M + i] = (double)(cell_ptr[i + 1] - cell_ptr[i]);
+    }
+}
+
 // ---- claim rescale (R/run_simulation.R:236-241) ------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_claim(const int32_t *__restrict__ seg_start, const int32_t *__restrict__ t_entry,
@@ -855,7 +893,8 @@ int eut_cells_destroy(eut_cells *c)
     cudaFree(c->d_t_entry); cudaFree(c->d_t_key); cudaFree(c->d_seg_start); cudaFree(c->d_seg_fq);
     cudaFree(c->d_gx); cudaFree(c->d_gy); cudaFree(c->d_gfield); cudaFree(c->d_col_start);
     cudaFree(c->d_col_x); cudaFree(c->d_layer_col); cudaFree(c->d_layer_z); cudaFree(c->d_tmp);
-    cudaFree(c->d_fmol); cudaFree(c->d_tfield); cudaFree(c->d_exd); cudaFree(c->d_exmask); cudaFree(c->d_ex_ptr); cudaFree(c->d_ex_cpd); cudaFree(c->d_ex_flx);
+    cudaFree(c->d_fmol); cudaFree(c->d_tfield); cudaFree(c->d_exd); cudaFree(c->d_exmask);
+    cudaFree(c->d_pxy); cudaFree(c->d_mom); cudaFree(c->d_cxy); cudaFree(c->d_ex_ptr); cudaFree(c->d_ex_cpd); cudaFree(c->d_ex_flx);
     cudaFree(c->d_ex_cs); cudaFree(c->d_const); cudaFree(c->d_g_idx); cudaFree(c->d_cell_order);
     delete c;
     return EUT_OK;
@@ -1051,6 +1090,45 @@ int eut_cells_gather(eut_cells *c, eut_field *f, double field_vol, double *fmol_
         EUT_CUDA(cudaMemcpyAsync(fmol_host, c->d_fmol, n * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
         EUT_CUDA(cudaStreamSynchronize(f->stream));
     }
+    return EUT_OK;
+}
+
+int eut_cells_chemotaxis_moments(eut_cells *c, eut_field *f, int32_t col, const double *pts, int64_t n_pts,
+                                 const double *cell_x, const double *cell_y, const double *cell_r, double *out)
+{
+    clear_error();
+    if (!c || !f || f->plan != c->plan || !pts || !out || (c->M > 0 && (!cell_x || !cell_y || !cell_r))) {
+        set_error("eut_cells_chemotaxis_moments: bad argument");
+        return EUT_ERR_ARG;
+    }
+    if (n_pts != c->plan->N) { set_error("eut_cells_chemotaxis_moments: %lld field points, plan has %lld", (long long)n_pts, (long long)c->plan->N); return EUT_ERR_ARG; }
+    if (col < 1 || col > f->C) { set_error("index out of bounds: compound column %d of %lld", col, (long long)f->C); return EUT_ERR_INDEX; }
+    EUT_TRY(ensure_device(c->plan->device));
+    const int64_t M = c->M, Np = c->plan->Np, N = c->plan->N;
+    if (M == 0) return EUT_OK;
+    const uint64_t h = hash_bytes(pts, (size_t)N * 2 * sizeof(double), 0xc0ffeeull);
+    if (!c->d_pxy || h != c->pxy_hash) {
+        std::vector<double> xy((size_t)2 * Np, 0.0);
+        for (int64_t i = 0; i < N; i++) { xy[c->plan->perm[i]] = pts[i]; xy[Np + c->plan->perm[i]] = pts[N + i]; }
+        cudaFree(c->d_pxy); c->d_pxy = nullptr;
+        EUT_CUDA(cudaMalloc((void **)&c->d_pxy, xy.size() * sizeof(double)));
+        EUT_CUDA(cudaMemcpy(c->d_pxy, xy.data(), xy.size() * sizeof(double), cudaMemcpyHostToDevice));
+        c->pxy_hash = h;
+    }
+    EUT_TRY(grow(&c->d_mom, &c->mom_cap, 7 * M));
+    EUT_TRY(grow(&c->d_cxy, &c->cxy_cap, 3 * M));
+    EUT_CUDA(cudaStreamSynchronize(0));            // list construction runs on the legacy stream
+    cudaStream_t s = f->stream;
+    EUT_CUDA(cudaMemcpyAsync(c->d_cxy, cell_x, M * sizeof(double), cudaMemcpyHostToDevice, s));
+    EUT_CUDA(cudaMemcpyAsync(c->d_cxy + M, cell_y, M * sizeof(double), cudaMemcpyHostToDevice, s));
+    EUT_CUDA(cudaMemcpyAsync(c->d_cxy + 2 * M, cell_r, M * sizeof(double), cudaMemcpyHostToDevice, s));
+    const double *colp = f->d_buf + (int64_t)f->cur[col - 1] * f->C * Np + (int64_t)(col - 1) * Np;
+    k_chemo_moments<<<(unsigned)((M * 32 + 255) / 256), 256, 0, s>>>(colp, c->d_pxy, c->d_pxy + Np, c->d_cell_ptr, c->d_fq,
+                                                                    c->d_cxy, c->d_mom, (int)M);
+    f->launches++;
+    EUT_CUDA(cudaGetLastError());
+    EUT_CUDA(cudaMemcpyAsync(out, c->d_mom, 7 * M * sizeof(double), cudaMemcpyDeviceToHost, s));
+    EUT_CUDA(cudaStreamSynchronize(s));
     return EUT_OK;
 }
 

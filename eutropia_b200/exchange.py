@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["scavenge_compounds", "adjust_uptake"]
+__all__ = ["scavenge_compounds", "adjust_uptake", "chemotaxis_shift"]
 
 
 def scavenge_compounds(cells, field, env_cpds, env_fieldVol, cell_index=None):
@@ -40,3 +40,21 @@ def adjust_uptake(model_react_id, model_lowbnd, cMass, accCpdFMOL, deltaTime):
     lb1 = fmol * (1 / deltaTime) / cMass                       # fmol / (pg * hr) = mmol / (g * hr)
     lb2 = -np.asarray(model_lowbnd, dtype=np.float64)[model_ex_ind]
     return model_ex_ind + 1, -np.minimum(lb1, lb2)
+
+
+def chemotaxis_shift(cells, field, pts, compound_col, cell_x, cell_y, cell_size, scavenge_dist, hill_ka, hill_coef,
+                     strength, vmax, deltaTime):
+    """R/run_simulation.R:260-291 for one chemotaxis compound (1-based column): the (CT.x, CT.y)
+    contribution of every cell, from the moments the device takes over the cells' field lists.
+    `hill_ka`, `hill_coef`, `strength`, `vmax`, `scavenge_dist` may be scalars or per-cell arrays."""
+    cell_r = np.asarray(cell_size, dtype=np.float64) / 2 + scavenge_dist
+    m = cells.chemotaxis_moments(field, compound_col, pts, cell_x, cell_y, np.broadcast_to(cell_r, np.shape(cell_x)))
+    s0, s1, sxc, syc, sx1, sy1, n = (m[:, k] for k in range(7))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        uniform = s0 == 0                                     # sum(f_conc) == 0 -> weights 1 (:275-276)
+        centr_x = np.where(uniform, sx1 / n, sxc / s0)
+        centr_y = np.where(uniform, sy1 / n, syc / s0)
+        wmean = np.where(uniform, 0.0, s1 / s0)               # weighted.mean(f_conc_orig, f_conc)
+        sensing = 1 / (1 + (hill_ka / wmean) ** hill_coef)    # :286
+    scale = sensing * strength * vmax * 60 * deltaTime * 60
+    return centr_x * scale, centr_y * scale

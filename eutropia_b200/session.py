@@ -258,6 +258,15 @@ class Cells:
         check(_lib.lib().eut_cells_gather(self._h, field._h, float(field_vol), ptr(out)))
         return out
 
+    def chemotaxis_moments(self, field: Field, col: int, pts, cell_x, cell_y, cell_r):
+        """M x 7 sums per cell for compound column `col` (see eut_cells_chemotaxis_moments)."""
+        p = np.require(np.asarray(pts, dtype=np.float64), requirements=["F", "A"])
+        cx, cy, cr = _f64c(cell_x), _f64c(cell_y), _f64c(cell_r)
+        out = np.zeros((max(cx.shape[0], 1), 7), dtype=np.float64, order="F")
+        check(_lib.lib().eut_cells_chemotaxis_moments(self._h, field._h, int(col), ptr(p), p.shape[0], ptr(cx), ptr(cy),
+                                                      ptr(cr), ptr(out)))
+        return out[:cx.shape[0]]
+
     def scatter(self, field: Field, field_vol: float, is_constant, ex_ptr, ex_cpd, ex_flx):
         isc = None if is_constant is None else np.ascontiguousarray(is_constant, dtype=np.uint8)
         ep = np.ascontiguousarray(ex_ptr, dtype=np.int64)

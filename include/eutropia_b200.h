@@ -280,6 +280,14 @@ EUT_API int eut_cells_get_lists(const eut_cells *cells, int64_t *cell_ptr, int32
 /* Gather (R/run_simulation.R:249, R/scavenge_compounds.R:17-22): fmol[n_cells x n_cols]
  * column-major = accessible fmol per cell and compound. */
 EUT_API int eut_cells_gather(eut_cells *cells, eut_field *field, double field_vol, double *fmol_host);
+/* Chemotaxis (R/run_simulation.R:260-291): for compound column `col`, per cell over its field list the
+ * sums the reference's weighted means are made of.  pts: N x 3 column-major field points (x | y | z);
+ * cell_x, cell_y: cell positions; cell_r = size / 2 + scavengeDist.  out: M x 7 column-major:
+ * sum c | sum c^2 | sum dx c | sum dy c | sum dx | sum dy | n   with dx = (x - cell_x) / cell_r.
+ * centr_x = sum dx c / sum c (sum dx / n when sum c = 0), weighted.mean(conc) = sum c^2 / sum c. */
+EUT_API int eut_cells_chemotaxis_moments(eut_cells *cells, eut_field *field, int32_t col, const double *pts,
+                                         int64_t n_pts, const double *cell_x, const double *cell_y,
+                                         const double *cell_r, double *out);
 /* Scatter + clamp (R/run_simulation.R:689-740, :309-319).  Per cell i the exchanges
  * ex_ptr[i]..ex_ptr[i+1]: ex_cpd (1-based field column), ex_flx (fmol; <0 uptake, >0 production).
  * is_constant[n_cols] (may be NULL) marks buffered compounds, which are left untouched. */

@@ -200,3 +200,26 @@ def exoenzyme_decay(exo_conc, k, lam, delta_time):
     out = np.array(exo_conc, dtype=np.float64, order="F", copy=True)
     lib().oracle_exoenzyme_decay(_p(out), out.shape[0], int(k), float(lam), float(delta_time))
     return out
+
+
+def chemotaxis_shift(conc_col, pts, cell_ptr, field_id, cell_x, cell_y, cell_size, scavenge_dist, hill_ka, hill_coef,
+                     strength, vmax, delta_time):
+    """R/run_simulation.R:260-291, cell by cell and statement by statement (numpy; small cases)."""
+    m = len(cell_x)
+    ctx, cty = np.zeros(m), np.zeros(m)
+    for i in range(m):
+        fid = np.asarray(field_id[cell_ptr[i]:cell_ptr[i + 1]], dtype=np.int64) - 1
+        r = cell_size[i] / 2 + scavenge_dist
+        dx = (pts[fid, 0] - cell_x[i]) / r
+        dy = (pts[fid, 1] - cell_y[i]) / r
+        f_orig = conc_col[fid]
+        f = f_orig.copy()
+        if f.sum() == 0:
+            f = np.ones_like(f)
+        f = f / f.sum()
+        cx, cy = (dx * f).sum() / f.sum(), (dy * f).sum() / f.sum()
+        with np.errstate(divide="ignore"):
+            sens = 1 / (1 + (hill_ka / ((f_orig * f).sum() / f.sum())) ** hill_coef)
+        ctx[i] = cx * sens * strength * vmax * 60 * delta_time * 60
+        cty[i] = cy * sens * strength * vmax * 60 * delta_time * 60
+    return ctx, cty

@@ -212,3 +212,26 @@ def test_vignette_like_rounds():
         assert np.array_equal(got[:, :n_const], conc[:, :n_const])                           # constants never move
         assert close(got, ref, absol=REL * 25.0), float(np.abs(got - ref).max())
     assert ind.size > 12                                          # the diffusing set grows with the exchanges
+
+
+def test_chemotaxis_shift_matches_oracle(small_mesh):
+    """Chemotaxis vector of every cell (R/run_simulation.R:260-291) from the device moments, against the
+    statement-by-statement numpy restatement; includes cells whose neighbourhood holds none of the
+    compound (uniform weights, zero sensing)."""
+    m = small_mesh
+    rng = np.random.default_rng(12)
+    conc = rng.uniform(0, 5, (m.nfields, 3))
+    conc[m.field_pts[:, 0] < 0, 1] = 0.0                    # the left half holds nothing of compound 2
+    plan = eb.Plan(m.mat_in, m.mat_out)
+    field = eb.Field(plan, 3)
+    field.upload(conc)
+    cx, cy, size, scv = synth.place_cells(m, 40, seed=3)
+    cells = eb.Cells(plan)
+    cells.build_lists(m.field_pts, cx, cy, size, scv)
+    ptr, fid, _, _ = cells.get_lists()
+    from eutropia_b200 import exchange
+    got = exchange.chemotaxis_shift(cells, field, m.field_pts, 2, cx, cy, size, float(scv[0]), 0.1, 1.2, 0.01, 11.0, 1 / 6)
+    ref = oracle.chemotaxis_shift(conc[:, 1], m.field_pts, ptr, fid, cx, cy, size, float(scv[0]), 0.1, 1.2, 0.01, 11.0, 1 / 6)
+    scale = max(np.abs(ref[0]).max(), np.abs(ref[1]).max(), 1e-300)
+    assert np.all(np.abs(got[0] - ref[0]) <= REL * scale) and np.all(np.abs(got[1] - ref[1]) <= REL * scale)
+    assert np.any(ref[0] != 0) and np.any(ref[0] == 0)       # both branches are exercised
