@@ -113,17 +113,23 @@ def host_threads() -> int:
 
 
 def cpu_sample(mesh, substeps_full, n_cols_full, threads, target_s=12.0):
-    """Time the CPU oracle (restatement of diffChangePar, OpenMP over compounds like the reference)
-    on a bounded sample of the workload: same mesh, `threads` columns (one per thread, at most the
-    workload's columns), as many substeps as fit in about target_s."""
+    """Time the reference's CPU implementation of diffChangePar -- its own src/diffChange.cpp from
+    oracle/_ref (kind "reference") when that library was built, else the oracle's restatement (kind
+    "port"); both run OpenMP over compounds -- on a bounded sample of the workload: same mesh,
+    `threads` columns (one per thread, at most the workload's columns), as many substeps as fit in
+    about target_s."""
     import oracle
+    if oracle.ref_available():
+        run, kind, what = oracle.ref_diffChangePar, "reference", "src/diffChange.cpp via oracle/_ref"
+    else:
+        run, kind, what = oracle.diffChangePar, "port", "oracle/diffchange_oracle.c"
     n = mesh.nfields
     rng = np.random.default_rng(99)
     # calibration: one substep on one column per thread
     c1 = int(max(1, min(n_cols_full, threads)))
     conc = np.asfortranarray(rng.uniform(0.0, 25.0, (n, c1)))
     t0 = time.perf_counter()
-    oracle.diffChangePar(mesh.mat_in, mesh.mat_out, conc, np.ones(c1, np.int32), np.arange(1, c1 + 1), threads)
+    run(mesh.mat_in, mesh.mat_out, conc, np.ones(c1, np.int32), np.arange(1, c1 + 1), threads)
     t1 = max(time.perf_counter() - t0, 1e-6)
     # sample: full substep count if it fits, on as many column waves (threads columns each) as fit
     s = int(max(1, min(substeps_full, target_s / t1)))
@@ -132,16 +138,17 @@ def cpu_sample(mesh, substeps_full, n_cols_full, threads, target_s=12.0):
     conc = np.asfortranarray(rng.uniform(0.0, 25.0, (n, cols)))
     iv = np.arange(1, cols + 1, dtype=np.int32)
     t0 = time.perf_counter()
-    oracle.diffChangePar(mesh.mat_in, mesh.mat_out, conc, np.full(cols, s, np.int32), iv, threads)
+    run(mesh.mat_in, mesh.mat_out, conc, np.full(cols, s, np.int32), iv, threads)
     dt = time.perf_counter() - t0
-    return {"value": n * cols * s / dt, "unit": UNIT, "cores": int(threads), "kind": "port",
+    return {"value": n * cols * s / dt, "unit": UNIT, "cores": int(threads), "kind": kind,
             "sample": f"{n} points x {cols} compounds x {s} substeps in {dt:.2f} s "
-                      f"(oracle/diffchange_oracle.c, OpenMP over compounds, {threads} threads)"}
+                      f"({what}, OpenMP over compounds, {threads} threads)"}
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port; the Rcpp original cannot be
-    built here) on this box's host cores, same config and metric."""
+    """--impl reference: the reference's own diffChangePar (src/diffChange.cpp compiled into
+    oracle/_ref; the oracle port if that library is absent) on this box's host cores, same config
+    and metric."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return

@@ -2,6 +2,8 @@
 // reproduces the two Rcpp entry points call for call.
 #include <algorithm>
 #include <cmath>
+#include <cstring>
+#include <limits>
 #include <memory>
 #include <mutex>
 
@@ -595,8 +597,43 @@ int eut_diffchange(const double *adjmat, int64_t n_edges, const double *nneighbo
         nit.push_back((int32_t)std::ceil(v));
         iv.push_back((int32_t)(i + 1));
     }
-    return oneshot_run(adj.data(), n_edges, nn.data(), n_nn, conc_in, n_rows, n_cols, nit.data(),
-                       iv.data(), (int64_t)iv.size(), conc_out, device);
+    int rc = oneshot_run(adj.data(), n_edges, nn.data(), n_nn, conc_in, n_rows, n_cols, nit.data(),
+                         iv.data(), (int64_t)iv.size(), conc_out, device);
+    if (rc != EUT_OK || iv.size() < 2) return rc;
+    // `ychg = ychg * 0` (src/diffChange.cpp:16) is not a zero fill and ychg (:10) is shared by all
+    // columns: where the last substep of one column left a non-finite change, the next column
+    // starts its inflow sum from NaN at that point.  A change is non-finite exactly where the
+    // column's result is (c + y with y = +-Inf or NaN; an overflow of the final addition alone is
+    // the one case this test cannot see).  Finite data -- every real round -- never gets past the
+    // scan; otherwise the columns after the first affected one are redone in sequence: one
+    // substep, NaN at the carried points, the remaining substeps.
+    auto any_nonfinite = [&](const double *col) {
+        double s = 0.0;
+        for (int64_t i = 0; i < n_rows; i++) s += col[i] * 0.0;
+        return s != s;
+    };
+    size_t first = 0;
+    while (first < iv.size() && !any_nonfinite(conc_out + (size_t)(iv[first] - 1) * n_rows)) first++;
+    if (first + 1 >= iv.size()) return rc;
+    std::vector<double> mid((size_t)n_rows);
+    const int32_t one = 1;
+    for (size_t j = first + 1; j < iv.size(); j++) {
+        const double *prev = conc_out + (size_t)(iv[j - 1] - 1) * n_rows;
+        double *dst = conc_out + (size_t)(iv[j] - 1) * n_rows;
+        rc = oneshot_run(adj.data(), n_edges, nn.data(), n_nn, conc_in + (size_t)(iv[j] - 1) * n_rows, n_rows, 1,
+                         &one, &one, 1, mid.data(), device);
+        if (rc != EUT_OK) return rc;
+        for (int64_t i = 0; i < n_rows; i++)
+            if (!std::isfinite(prev[i])) mid[i] = std::numeric_limits<double>::quiet_NaN();
+        const int32_t rest = nit[j] - 1;
+        if (rest > 0) {
+            rc = oneshot_run(adj.data(), n_edges, nn.data(), n_nn, mid.data(), n_rows, 1, &rest, &one, 1, dst, device);
+            if (rc != EUT_OK) return rc;
+        } else {
+            std::memcpy(dst, mid.data(), sizeof(double) * (size_t)n_rows);
+        }
+    }
+    return rc;
 }
 
 }  // extern "C"

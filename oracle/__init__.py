@@ -2,7 +2,13 @@
 
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s `cpu_baseline` / `--impl reference` legs
 may import this package.  The product package `eutropia_b200` never does (tests/test_boundary.py
-greps for it).  PARITY UNPINNED -- see the header of `diffchange_oracle.c`.
+greps for it).
+
+Parity pin: the reference ships no tests or golden vectors, but its one compiled source file,
+src/diffChange.cpp, builds unmodified against a stand-in for the Armadillo types it uses
+(`ref_shim/RcppArmadillo.h`) into `oracle/_ref/libeutropia_ref.so`; `ref_diffChange*` call it and
+tests/test_oracle.py holds the restatement to it bit for bit.  The R-language parts of the path
+(cell lists, gather, scatter, exoenzymes) have no such pin: R is absent -- "parity unpinned" there.
 """
 from __future__ import annotations
 
@@ -114,6 +120,90 @@ def diffChangePar(adjmat, nneighbors, conc, niter, indvar, ncores=1):
                                          int(ncores))
     _check(rc)
     return out
+
+
+# ---- oracle/_ref: the reference's own src/diffChange.cpp, compiled unmodified (oracle/Makefile `ref`) ----
+_REF_PATH = os.path.join(_HERE, "_ref", "libeutropia_ref.so")
+_REF_SRC = "/root/reference/src/diffChange.cpp"
+_ref = None
+
+
+def ref_build(force: bool = False) -> bool:
+    """Compile oracle/_ref when the reference tree is present (this container); on the GPU box the
+    prebuilt library travels with the snapshot.  Returns whether the library exists afterwards."""
+    deps = [os.path.join(_HERE, "ref_glue.cpp"), os.path.join(_HERE, "ref_shim", "RcppArmadillo.h")]
+    if os.path.exists(_REF_SRC):
+        stale = (not os.path.exists(_REF_PATH)) or any(
+            os.path.getmtime(s) > os.path.getmtime(_REF_PATH) for s in deps + [_REF_SRC])
+        if force or stale:
+            subprocess.run(["make", "-C", _HERE, "-s", "ref"], check=True, stdout=subprocess.DEVNULL)
+    return os.path.exists(_REF_PATH)
+
+
+def ref_available() -> bool:
+    """Whether oracle/_ref exists; compiles it only when it is missing and the reference tree is
+    there (tests in the build container).  On the GPU box the tree is absent: prebuilt file or nothing."""
+    return os.path.exists(_REF_PATH) or ref_build()
+
+
+def ref_lib() -> C.CDLL:
+    global _ref
+    if _ref is None:
+        if not ref_available():
+            raise RuntimeError("oracle/_ref/libeutropia_ref.so is absent (built only where /root/reference exists)")
+        L = C.CDLL(_REF_PATH)
+        sz, vp = C.c_size_t, C.c_void_p
+        L.eut_ref_diffchange.argtypes = [vp, sz, vp, sz, vp, sz, sz, vp, sz]
+        L.eut_ref_diffchange.restype = C.c_int
+        L.eut_ref_diffchange_par.argtypes = [vp, sz, vp, sz, vp, sz, sz, vp, sz, vp, sz, C.c_int]
+        L.eut_ref_diffchange_par.restype = C.c_int
+        L.eut_ref_max_threads.restype = C.c_int
+        _ref = L
+    return _ref
+
+
+def _ref_check(rc):
+    if rc == 1:
+        raise OracleIndexError("Mat::operator(): index out of bounds")
+    if rc:
+        raise RuntimeError("reference library raised")
+
+
+def ref_diffChange(adjmat, nneighbors, conc, niter):
+    """The reference's own `diffChange` (src/diffChange.cpp:6-35) through oracle/_ref."""
+    adj = _f64(np.asarray(adjmat).reshape(-1, 2) if np.size(adjmat) else np.zeros((0, 2)))
+    nn = _f64(np.asarray(nneighbors).reshape(-1, 2) if np.size(nneighbors) else np.zeros((0, 2)))
+    out = np.array(conc, dtype=np.float64, order="F", copy=True)
+    if out.ndim == 1:
+        out = out.reshape(-1, 1, order="F")
+    nit = np.ascontiguousarray(np.asarray(niter, dtype=np.float64).ravel())
+    _ref_check(ref_lib().eut_ref_diffchange(_p(adj), adj.shape[0], _p(nn), nn.shape[0], _p(out),
+                                            out.shape[0], out.shape[1], _p(nit), nit.shape[0]))
+    return out
+
+
+def ref_diffChangePar(adjmat, nneighbors, conc, niter, indvar, ncores=1):
+    """The reference's own `diffChangePar` (src/diffChange.cpp:38-69) through oracle/_ref.  An index
+    error inside its OpenMP region would terminate the process (as it does under R), so callers
+    pass valid indices only."""
+    adj = np.require(np.asarray(adjmat).reshape(-1, 2), dtype=np.int32, requirements=["F", "A"])
+    nn = np.require(np.asarray(nneighbors).reshape(-1, 2), dtype=np.int32, requirements=["F", "A"])
+    out = np.array(conc, dtype=np.float64, order="F", copy=True)
+    if out.ndim == 1:
+        out = out.reshape(-1, 1, order="F")
+    nit = np.ascontiguousarray(np.trunc(np.asarray(niter, dtype=np.float64)).astype(np.int32).ravel())
+    iv = np.ascontiguousarray(np.trunc(np.asarray(indvar, dtype=np.float64)).astype(np.int32).ravel())
+    n, c = out.shape
+    if nit.shape[0] < iv.shape[0] or (iv.size and (iv.min() < 1 or iv.max() > c)) or \
+            (adj.size and (adj.min() < 1 or adj.max() > n)) or (nn.size and (nn[:, 0].min() < 1 or nn[:, 0].max() > n)):
+        raise OracleIndexError("Mat::operator(): index out of bounds")
+    _ref_check(ref_lib().eut_ref_diffchange_par(_p(adj), adj.shape[0], _p(nn), nn.shape[0], _p(out), n, c,
+                                                _p(nit), nit.shape[0], _p(iv), iv.shape[0], int(ncores)))
+    return out
+
+
+def ref_max_threads() -> int:
+    return int(ref_lib().eut_ref_max_threads())
 
 
 def cellmap(pts, cx, cy, csize, cscv, dist_mode=0):

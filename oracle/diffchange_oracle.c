@@ -3,12 +3,16 @@
  * library (eutropia_b200/csrc).  Only tests/, __graft_entry__.smoke() and bench.py's
  * cpu_baseline / --impl reference legs may use it, and only as the checker / the timed CPU arm.
  *
- * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for this path
- *  and cannot be compiled in this image (src/diffChange.cpp:1 needs
- * RcppArmadillo -> R headers, Rcpp, Armadillo; none are installed).  This file is therefore a
- * line-by-line CPU restatement of the reference's arithmetic, in plain C over flat arrays, pinned
- * only by hand-derived known answers (tests/test_oracle.py) and by the invariants the algorithm
- * implies (mass conservation, fixed points, serial == parallel).
+ * PARITY PIN: the reference ships no tests, golden vectors or fixtures for this path (SURVEY.md
+ * section 4 and 8c), but its one compiled source file builds: oracle/Makefile target `ref` compiles
+ * /root/reference/src/diffChange.cpp, unmodified and from where it lies, against a stand-in for the
+ * few Armadillo types it uses (oracle/ref_shim/RcppArmadillo.h; R, Rcpp and Armadillo themselves are
+ * not installed) into oracle/_ref/libeutropia_ref.so.  tests/test_oracle.py holds this restatement
+ * to that library bit for bit (finite, signed-zero, Inf/NaN data, shuffled edge lists, bounds
+ * errors) and to the vectors it wrote (tests/golden/diffusion_reference.npz), and the GPU tests
+ * compare the CUDA path with both.  What the pin cannot cover is Armadillo itself: the stand-in
+ * restates the documented element-wise meaning of `v * s`, `M.col(j) += v` and the checked
+ * operator(); see its header.
  *
  * What is restated (all citations relative to /root/reference):
  *   eut_oracle_diffchange      <- src/diffChange.cpp:6-35   (diffChange: double indices, serial)

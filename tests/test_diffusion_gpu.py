@@ -1,5 +1,6 @@
 """GPU parity tests of the diffusion path, through the C ABI (one-shot and session tiers), against
-the CPU oracle.  Bar: bit-exact (np.array_equal) on finite inputs -- stricter than the 1e-12
+the CPU oracle, against vectors the reference itself produced (tests/golden/diffusion_reference.npz)
+and against the reference's compiled src/diffChange.cpp (oracle/_ref) where that library is present.  Bar: bit-exact (np.array_equal) on finite inputs -- stricter than the 1e-12
 relative tolerance BASELINE.json asks for, which is also asserted explicitly (REL_TOL)."""
 import os
 
@@ -28,6 +29,43 @@ def test_golden_fixture_one_shot():
     g = np.load(os.path.join(GOLD, "diffusion_small.npz"))
     out = eb.diffChangePar(g["mat_in"], g["mat_out"], g["conc"], g["niter"], g["indvar"], 4)
     assert_parity(out, g["expected"])
+
+
+def test_reference_golden_vectors_one_shot():
+    """Vectors written by the reference's own code (tests/golden/make_reference_golden.py)."""
+    g = np.load(os.path.join(GOLD, "diffusion_reference.npz"))
+    assert_parity(eb.diffChangePar(g["a_mat_in"], g["a_mat_out"], g["a_conc"], g["a_niter"], g["a_indvar"], 8),
+                  g["a_expected"])
+    # serial entry point, non-finite data: the `ychg = ychg * 0` carry-over between columns
+    assert_parity(eb.diffChange(g["b_mat_in"], g["b_mat_out"], g["b_conc"], g["b_niter"]), g["b_expected"])
+    assert_parity(eb.diffChange(g["c_mat_in"], g["c_mat_out"], g["c_conc"], g["c_niter"]), g["c_expected"])
+
+
+def test_reference_golden_vectors_session():
+    g = np.load(os.path.join(GOLD, "diffusion_reference.npz"))
+    plan = eb.Plan(g["a_mat_in"], g["a_mat_out"])
+    fld = eb.Field(plan, g["a_conc"].shape[1])
+    fld.upload(g["a_conc"])
+    fld.diffuse(g["a_niter"], g["a_indvar"])
+    assert_parity(fld.download(), g["a_expected"])
+
+
+@pytest.mark.skipif(not oracle.ref_available(), reason="oracle/_ref/libeutropia_ref.so did not travel")
+def test_cuda_matches_compiled_reference():
+    """The CUDA path against src/diffChange.cpp itself on a mesh large enough for full tiles."""
+    m = mesh.make_mesh(mesh.harbor_polygon(150.0), 1.0, 4)
+    conc = synth.synthetic_concentrations(m.field_pts, 8, seed=5)
+    niter = np.array([9, 30, 1, 0, 14, 3], dtype=np.int32)
+    indvar = np.array([8, 2, 5, 3, 1, 7], dtype=np.int32)
+    ref = oracle.ref_diffChangePar(m.mat_in, m.mat_out, conc, niter, indvar, oracle.ref_max_threads())
+    assert_parity(eb.diffChangePar(m.mat_in, m.mat_out, conc, niter, indvar, 1), ref)
+    ref = oracle.ref_diffChange(m.mat_in, m.mat_out, conc, [4.0, 0.5, 0.0, 7.0])
+    assert_parity(eb.diffChange(m.mat_in, m.mat_out, conc, [4.0, 0.5, 0.0, 7.0]), ref)
+    bad = conc[:, :5].copy()
+    bad[17, 0] = np.inf; bad[1234, 1] = np.nan; bad[:, 4] = -bad[:, 4]
+    ref = oracle.ref_diffChange(m.mat_in, m.mat_out, bad, [3, 2, 0, 4, 1])
+    assert np.isnan(ref[:, 3]).any()                       # the carry-over reached a finite column
+    assert_parity(eb.diffChange(m.mat_in, m.mat_out, bad, [3, 2, 0, 4, 1]), ref)
 
 
 @pytest.mark.parametrize("order", [_lib.ORDER_IDENTITY, _lib.ORDER_ROWBLOCK, _lib.ORDER_TILED])

@@ -1,7 +1,10 @@
-"""CPU suite: the oracle against hand-derived known answers and the invariants the reference
-implies but never tests.  The reference ships no golden vectors for this path
-("parity unpinned"), so the committed fixtures under tests/golden/ are produced by the oracle itself
-(tests/golden/make_golden.py) and only guard against regressions of the restatement."""
+"""CPU suite: the oracle against (1) outputs of the reference itself -- src/diffChange.cpp compiled
+unmodified into oracle/_ref, and the vectors it produced in the build container
+(tests/golden/diffusion_reference.npz, tests/golden/make_reference_golden.py); (2) hand-derived
+known answers and the invariants the reference implies but never tests.  The
+reference ships no golden vectors of its own; the fixtures made by tests/golden/make_golden.py come
+from the oracle and only guard the R-language steps (cell lists, gather, scatter) against
+regressions -- parity is unpinned for those."""
 import os
 
 import numpy as np
@@ -143,3 +146,76 @@ def test_golden_fixture_regression():
     g = np.load(path)
     out = oracle.diffChangePar(g["mat_in"], g["mat_out"], g["conc"], g["niter"], g["indvar"], 2)
     assert np.array_equal(out, g["expected"])
+
+
+# ---- the pin: outputs of the reference itself ------------------------------------------------------
+
+def bits_equal(a, b):
+    """Same doubles, NaN == NaN; the sign of zero is part of the contract here."""
+    a, b = np.asarray(a), np.asarray(b)
+    nan = np.isnan(a)
+    return a.shape == b.shape and np.array_equal(nan, np.isnan(b)) and \
+        np.array_equal(a[~nan].view(np.uint64), b[~nan].view(np.uint64))
+
+
+def reference_golden():
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "diffusion_reference.npz"))
+
+
+def test_restatement_matches_reference_golden_vectors():
+    g = reference_golden()
+    out = oracle.diffChangePar(g["a_mat_in"], g["a_mat_out"], g["a_conc"], g["a_niter"], g["a_indvar"], 2)
+    assert bits_equal(out, g["a_expected"])
+    assert np.array_equal(out[:, [2, 4]], g["a_conc"][:, [2, 4]])            # not in indvar: untouched
+    out = oracle.diffChange(g["b_mat_in"], g["b_mat_out"], g["b_conc"], g["b_niter"])
+    assert bits_equal(out, g["b_expected"])
+    # the `ychg = ychg * 0` carry-over is in the vectors: columns 3 and 4 start finite and end with NaN
+    assert np.isfinite(g["b_conc"][:, 2:4]).all() and np.isnan(g["b_expected"][:, 2:4]).any()
+    out = oracle.diffChange(g["c_mat_in"], g["c_mat_out"], g["c_conc"], g["c_niter"])
+    assert bits_equal(out, g["c_expected"])
+
+
+@pytest.mark.skipif(not oracle.ref_available(), reason="oracle/_ref is built only where /root/reference exists")
+@pytest.mark.parametrize("name,layers", [("Rectangle_30_24", 3), ("Petri_23", 6), ("harbor", 4), ("Rectangle_40_12", 1)])
+def test_restatement_matches_compiled_reference(name, layers):
+    m = mesh.make_mesh(mesh.harbor_polygon(40.0) if name == "harbor" else name, 1.0, layers)
+    rng = np.random.default_rng(len(name) + layers)
+    conc = rng.uniform(0, 30, (m.nfields, 6)) * (rng.uniform(0, 1, (m.nfields, 6)) > 0.3)
+    niter = [5, 0, 17, 1, 2, 9]
+    assert bits_equal(oracle.diffChange(m.mat_in, m.mat_out, conc, niter),
+                      oracle.ref_diffChange(m.mat_in, m.mat_out, conc, niter))
+    assert bits_equal(oracle.diffChange(m.mat_in, m.mat_out, conc, [1.5, 0.0, -3.0]),         # double bounds, short niter
+                      oracle.ref_diffChange(m.mat_in, m.mat_out, conc, [1.5, 0.0, -3.0]))
+    iv = [6, 1, 4, 3]
+    assert bits_equal(oracle.diffChangePar(m.mat_in, m.mat_out, conc, [3, 11, 0, 6], iv, 3),
+                      oracle.ref_diffChangePar(m.mat_in, m.mat_out, conc, [3, 11, 0, 6], iv, 3))
+    # edge list in a different order: the summation order follows mat.in, not the point ids
+    shuf = rng.permutation(m.mat_in.shape[0])
+    assert bits_equal(oracle.diffChangePar(m.mat_in[shuf], m.mat_out, conc, [4], [2], 1),
+                      oracle.ref_diffChangePar(m.mat_in[shuf], m.mat_out, conc, [4], [2], 1))
+    # non-finite data, negative values, signed zeros
+    bad = conc.copy()
+    bad[3, 0] = np.inf; bad[9, 2] = np.nan; bad[:, 3] = -bad[:, 3]; bad[:, 4] = -0.0
+    assert bits_equal(oracle.diffChange(m.mat_in, m.mat_out, bad, [2, 1, 2, 3, 2, 1]),
+                      oracle.ref_diffChange(m.mat_in, m.mat_out, bad, [2, 1, 2, 3, 2, 1]))
+    assert bits_equal(oracle.diffChangePar(m.mat_in, m.mat_out, bad, [2, 2, 2, 2, 2, 2], [1, 2, 3, 4, 5, 6], 2),
+                      oracle.ref_diffChangePar(m.mat_in, m.mat_out, bad, [2, 2, 2, 2, 2, 2], [1, 2, 3, 4, 5, 6], 2))
+
+
+@pytest.mark.skipif(not oracle.ref_available(), reason="oracle/_ref is built only where /root/reference exists")
+def test_compiled_reference_edge_cases():
+    mat_in, mat_out = tiny_graph()
+    c = np.array([[13.0], [26.0], [39.0]])
+    assert oracle.ref_diffChangePar(mat_in, mat_out, c, [1], [1], 1)[:, 0].tolist() == [14.0, 26.0, 38.0]
+    # empty edge list, empty niter, zero columns selected
+    assert np.array_equal(oracle.ref_diffChange(np.zeros((0, 2)), mat_out, c, [3]), oracle.diffChange(np.zeros((0, 2)), mat_out, c, [3]))
+    assert np.array_equal(oracle.ref_diffChange(mat_in, mat_out, c, []), c)
+    assert np.array_equal(oracle.ref_diffChangePar(mat_in, mat_out, c, [], [], 1), c)
+    with pytest.raises(oracle.OracleIndexError):
+        oracle.ref_diffChange(np.array([[1, 4]]), mat_out, c, [1])                      # Armadillo's bounds check
+    with pytest.raises(oracle.OracleIndexError):
+        oracle.diffChange(np.array([[1, 4]]), mat_out, c, [1])
+    with pytest.raises(oracle.OracleIndexError):
+        oracle.ref_diffChange(mat_in, mat_out, c, [1, 1])                                # conc(., 1) of a 1-column matrix
+    with pytest.raises(oracle.OracleIndexError):
+        oracle.diffChange(mat_in, mat_out, c, [1, 1])
