@@ -18,10 +18,11 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 def assert_parity(got, ref):
     assert got.shape == ref.shape
-    err = np.abs(got - ref)
-    bound = REL_TOL * np.maximum(np.abs(ref), 1e-300)
-    assert np.all((err <= bound) | (np.isnan(got) & np.isnan(ref))), float(np.nanmax(err / bound))
-    same = (got == ref) | (np.isnan(got) & np.isnan(ref))
+    same = (got == ref) | (np.isnan(got) & np.isnan(ref))       # +-Inf compare equal to themselves
+    with np.errstate(invalid="ignore"):
+        err = np.abs(got - ref)
+        bound = REL_TOL * np.maximum(np.abs(ref), 1e-300)
+        assert np.all((err <= bound) | same), float(np.nanmax(err / bound))
     assert np.all(same), f"{np.count_nonzero(~same)} entries differ in the last bits"
 
 
