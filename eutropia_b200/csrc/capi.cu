@@ -388,31 +388,76 @@ int run_pipeline(CachedPlan *cp, const double *conc_in, int64_t n_rows, int64_t 
         const int rc = field_stream_columns(f, conc_in, conc_out, n_rows, scols.data(), snit.data(), (int64_t)act.size(), verify);
         return rc == -1000 ? kRetry : rc;
     }
-    // Pipeline over chunks of active columns: H2D(g+1) | substeps(g) | D2H(g-1) on three streams.
-    // The call lasts  H2D(first chunk) + all substeps + D2H(last chunk), and a launch over few columns
-    // is less efficient than one over many (tools/cols_scaling.py): the chunks ramp up 1/8, 3/8, 1, ...
-    // of the staging buffer and down again, so that the ends are short and the bulk runs wide.
+    // Pipeline over chunks of active columns: H2D(g+1) | substeps(g) | D2H(g-1) on copy, compute and
+    // download streams.  The call lasts  H2D(first chunk) + all substeps + D2H(last chunk), and a launch
+    // over few columns is less efficient than one over many (tools/cols_scaling.py).
+    // Two compute streams ("lanes"), chunks alternate between them: a launch over few columns has
+    // few CTAs (tiles x column slices) and ends in a partial wave; with a second chunk in flight the
+    // other lane's CTAs fill the SMs that partial wave leaves idle.  Every chunk gets its own range
+    // of the field's launch tables (act_base).  EUT_ONESHOT_LANES=1 restores the single stream.
+    static const int n_lanes = [] { const char *e = getenv("EUT_ONESHOT_LANES"); return (e && atoi(e) == 1) ? 1 : 2; }();
+    if (n_lanes == 2 && !f->lane2) EUT_CUDA(cudaStreamCreateWithFlags(&f->lane2, cudaStreamNonBlocking));
+    cudaStream_t lanes[2] = {f->stream, n_lanes == 2 ? f->lane2 : f->stream};
+    struct Restore {
+        eut_field *f; cudaStream_t s;
+        ~Restore() { f->stream = s; f->act_base = 0; }
+    } restore{f, f->stream};
     const int64_t chunk = f->stage_cols;
     std::vector<size_t> cuts;
-    {
-        const size_t n = act.size();
-        const size_t h1 = (size_t)std::max<int64_t>(1, chunk / 8), h2 = (size_t)std::max<int64_t>(1, 3 * chunk / 8);
+    // EUT_ONESHOT_CHUNKS=4,12,32,12,4: explicit chunk sizes (used when they add up to the active columns)
+    if (const char *e = getenv("EUT_ONESHOT_CHUNKS")) {
         std::vector<size_t> sizes;
+        size_t tot = 0;
+        for (const char *q = e; *q;) {
+            char *end = nullptr;
+            const long v = strtol(q, &end, 10);
+            if (end == q) break;
+            if (v > 0 && v <= chunk) { sizes.push_back((size_t)v); tot += (size_t)v; }
+            q = (*end == ',') ? end + 1 : end;
+        }
+        if (tot == act.size()) {
+            cuts.push_back(0);
+            for (size_t sz : sizes) cuts.push_back(cuts.back() + sz);
+        }
+    }
+    if (cuts.empty()) {
+        // Default: ramp up to a peak chunk of a quarter of the columns and down again, in steps of a
+        // quarter of the peak (64 columns: 4, 8, 12, 16, 12, 8, 4) -- short ends for a short H2D head
+        // and D2H tail, and both lanes get the same share.  Measured on 1 M points x 64 columns x 60
+        // substeps: 19.9 ms per call against 23.8 ms on one stream with chunks 4, 12, 32, 12, 4.
+        // Anything below a quarter of the staging slot (64 MB) goes as one chunk.
+        const size_t n = act.size();
+        std::vector<size_t> sizes;
+        size_t peak = (size_t)chunk;
         auto middle = [&](size_t m) {
             if (m == 0) return;
-            const size_t parts = (m + (size_t)chunk - 1) / (size_t)chunk;
+            const size_t parts = (m + peak - 1) / peak;
             for (size_t k = 0; k < parts; k++) sizes.push_back(m / parts + (k < m % parts ? 1 : 0));
         };
-        if (n > 2 * (h1 + h2)) { sizes.push_back(h1); sizes.push_back(h2); middle(n - 2 * (h1 + h2)); sizes.push_back(h2); sizes.push_back(h1); }
-        else if (n > 2 * h1) { sizes.push_back(h1); middle(n - 2 * h1); sizes.push_back(h1); }
-        else middle(n);
+        if (n * 4 > (size_t)chunk) {
+            peak = std::min<size_t>((size_t)chunk, std::max<size_t>(4, (n + 3) / 4));
+            const size_t r1 = std::max<size_t>(1, peak / 4), r2 = std::max<size_t>(1, peak / 2), r3 = std::max<size_t>(1, 3 * peak / 4);
+            if (n > 2 * (r1 + r2 + r3)) {
+                sizes.push_back(r1); sizes.push_back(r2); sizes.push_back(r3);
+                middle(n - 2 * (r1 + r2 + r3));
+                sizes.push_back(r3); sizes.push_back(r2); sizes.push_back(r1);
+            } else if (n > 2 * r1) { sizes.push_back(r1); middle(n - 2 * r1); sizes.push_back(r1); }
+            else middle(n);
+        } else {
+            middle(n);
+        }
         cuts.push_back(0);
         for (size_t sz : sizes) cuts.push_back(cuts.back() + sz);
     }
-    struct Pending { std::vector<int32_t> cols; bool contiguous; };
+    struct Pending { std::vector<int32_t> cols; bool contiguous; cudaStream_t lane; };
     std::vector<Pending> pending;
     bool verified = !verify;
     auto download = [&](const Pending &pd) -> int {
+        struct Lane {                                   // the un-permute runs on the lane that diffused the chunk
+            eut_field *f; cudaStream_t keep;
+            ~Lane() { f->stream = keep; }
+        } lane{f, f->stream};
+        f->stream = pd.lane;
         if (pd.contiguous) {
             EUT_TRY(field_download_async(f, conc_out + (size_t)(pd.cols[0] - 1) * n_rows, n_rows, pd.cols.data(), (int64_t)pd.cols.size()));
         } else {
@@ -424,7 +469,8 @@ int run_pipeline(CachedPlan *cp, const double *conc_in, int64_t n_rows, int64_t 
     auto check_now = [&]() -> int {
         if (verified) return EUT_OK;
         if (!verify()) {
-            cudaStreamSynchronize(f->copy_stream); cudaStreamSynchronize(f->stream); cudaStreamSynchronize(f->down_stream);
+            cudaStreamSynchronize(f->copy_stream); cudaStreamSynchronize(lanes[0]); cudaStreamSynchronize(lanes[1]);
+            cudaStreamSynchronize(f->down_stream);
             return kRetry;
         }
         verified = true;
@@ -437,6 +483,9 @@ int run_pipeline(CachedPlan *cp, const double *conc_in, int64_t n_rows, int64_t 
         const size_t a0 = cuts[ci], a1 = cuts[ci + 1];
         if (a1 <= a0) continue;
         Pending pd;
+        pd.lane = lanes[ci & 1];
+        f->stream = pd.lane;
+        f->act_base = (int64_t)a0;
         nit.clear();
         for (size_t a = a0; a < a1; a++) { pd.cols.push_back(indvar[act[a]]); nit.push_back(niter[act[a]]); }
         // host column j of this chunk is conc_in column cols[j]-1: upload one column at a time when
@@ -450,7 +499,7 @@ int run_pipeline(CachedPlan *cp, const double *conc_in, int64_t n_rows, int64_t 
                 EUT_TRY(field_upload(f, conc_in + (size_t)(pd.cols[j] - 1) * n_rows, n_rows, &pd.cols[j], 1));
         }
         EUT_TRY(field_diffuse(f, nit.data(), pd.cols.data(), (int64_t)pd.cols.size()));
-        if (!verified && ci >= 1) EUT_TRY(check_now());      // the hash has had two chunks' worth of time
+        if (!verified && ci >= 2) EUT_TRY(check_now());      // the hash has had three chunks' worth of time; the queue stays fed
         if (verified) EUT_TRY(download(pd));
         else pending.push_back(std::move(pd));
     }
@@ -531,6 +580,7 @@ int oneshot_run(const int32_t *adj, int64_t n_edges, const int32_t *nn, int64_t 
     const double t_enq = now_ms();
     EUT_CUDA(cudaStreamSynchronize(f->copy_stream));
     EUT_CUDA(cudaStreamSynchronize(f->stream));
+    if (f->lane2) EUT_CUDA(cudaStreamSynchronize(f->lane2));
     EUT_CUDA(cudaStreamSynchronize(f->down_stream));
     if (trace)
         fprintf(stderr, "[eut] one-shot: plan lookup%s + first chunks %.2f ms, enqueue %.2f ms, drain %.2f ms\n",

@@ -178,8 +178,10 @@ struct eut_field {
     double *d_stage = nullptr;
     int64_t stage_cols = 0;
     // active-column tables of the current diffuse call
-    int32_t *d_act = nullptr;          // [2][cap]: column, starting buffer
+    int32_t *d_act = nullptr;          // [3][cap]: column, starting buffer, final buffer
     int64_t act_cap = 0;
+    int64_t act_base = 0;              // first table entry the next diffuse call uses (one-shot pipeline: per chunk)
+    cudaStream_t lane2 = nullptr;      // second compute stream of the one-shot pipeline (created on demand)
     // the tables the substep launch reads (default: d_act; the column-streaming pipeline points them
     // at a ring of per-launch tables)
     const int32_t *act_col = nullptr, *act_par = nullptr;
@@ -254,6 +256,7 @@ int launch_permute_in(eut_field *f, const double *d_stage, int64_t ld, const int
 int launch_permute_out(eut_field *f, double *d_stage, int64_t ld, const int32_t *d_cols,
                        const int32_t *d_cur, int64_t n_cols, cudaStream_t s);
 int launch_column_stats(eut_field *f, const int32_t *d_cur);
+int launch_set_cur(eut_field *f, const int32_t *d_col, const int32_t *d_value, int n);
 const char *last_error_cstr();
 int launch_fill_column(eut_field *f, int32_t col0, double value);
 // round.cu

@@ -21,8 +21,8 @@ static int field_alloc(eut_field *f)
     EUT_CUDA(cudaMalloc((void **)&f->d_cur, C * sizeof(int32_t)));
     EUT_CUDA(cudaMemset(f->d_cur, 0, C * sizeof(int32_t)));
     f->act_cap = C;
-    EUT_CUDA(cudaMalloc((void **)&f->d_act, 2 * C * sizeof(int32_t)));
-    f->h_act.assign(2 * C, 0);
+    EUT_CUDA(cudaMalloc((void **)&f->d_act, 3 * C * sizeof(int32_t)));
+    f->h_act.assign(3 * C, 0);
     EUT_CUDA(cudaMalloc((void **)&f->d_cols, 4 * C * sizeof(int32_t)));
     f->h_cols.assign(4 * C, 0);
     EUT_CUDA(cudaMalloc((void **)&f->d_stats, 3 * C * sizeof(double)));
@@ -68,6 +68,7 @@ int field_destroy(eut_field *f)
     if (!f) return EUT_OK;
     cudaSetDevice(f->plan->device);
     if (f->stream) cudaStreamSynchronize(f->stream);
+    if (f->lane2) cudaStreamSynchronize(f->lane2);
     if (f->copy_stream) cudaStreamSynchronize(f->copy_stream);
     if (f->down_stream) cudaStreamSynchronize(f->down_stream);
     cudaFree(f->d_buf); cudaFree(f->d_cur); cudaFree(f->d_act); cudaFree(f->d_cols);
@@ -84,6 +85,7 @@ int field_destroy(eut_field *f)
     for (cudaEvent_t e : f->ev_pool) cudaEventDestroy(e);
     cudaFree(f->d_ring); cudaFree(f->d_stream_cols);
     if (f->h_ring) cudaFreeHost(f->h_ring);
+    if (f->lane2) cudaStreamDestroy(f->lane2);
     if (f->own_stream && f->stream) cudaStreamDestroy(f->stream);
     if (f->copy_stream) cudaStreamDestroy(f->copy_stream);
     if (f->down_stream) cudaStreamDestroy(f->down_stream);
@@ -224,16 +226,21 @@ int field_diffuse(eut_field *f, const int32_t *niter, const int32_t *indvar, int
         set_error("eut_field_diffuse: phase %d needs a segment plan with halo lists and exactly one substep", f->opt_phase);
         return EUT_ERR_ARG;
     }
+    // The tables of this call live at [act_base, act_base + n_tot) of d_act's three rows (column,
+    // starting buffer, final buffer): calls that run side by side on two compute streams (the one-shot
+    // pipeline, capi.cu) are given disjoint ranges.
+    const int64_t base = f->act_base;
+    if (base < 0 || base + n_tot > f->act_cap) { set_error("eut_field_diffuse: table range out of bounds"); return EUT_ERR_ARG; }
     for (int a = 0; a < n_tot; a++) {
         const int c = indvar[order[a]] - 1;
-        f->h_act[a] = c;
-        f->h_act[f->act_cap + a] = phase == 2 ? (f->cur[c] ^ 1) : f->cur[c];
+        f->h_act[base + a] = c;
+        f->h_act[f->act_cap + base + a] = phase == 2 ? (f->cur[c] ^ 1) : f->cur[c];
+        f->h_act[2 * f->act_cap + base + a] = phase == 2 ? f->cur[c] : ((f->cur[c] + niter[order[a]]) & 1);
     }
-    f->act_col = f->d_act; f->act_par = f->d_act + f->act_cap;
-    EUT_CUDA(cudaMemcpyAsync(f->d_act, f->h_act.data(), n_tot * sizeof(int32_t),
-                             cudaMemcpyHostToDevice, f->stream));
-    EUT_CUDA(cudaMemcpyAsync(f->d_act + f->act_cap, f->h_act.data() + f->act_cap,
-                             n_tot * sizeof(int32_t), cudaMemcpyHostToDevice, f->stream));
+    f->act_col = f->d_act + base; f->act_par = f->d_act + f->act_cap + base;
+    for (int r = 0; r < 3; r++)
+        EUT_CUDA(cudaMemcpyAsync(f->d_act + r * f->act_cap + base, f->h_act.data() + r * f->act_cap + base,
+                                 n_tot * sizeof(int32_t), cudaMemcpyHostToDevice, f->stream));
     const int max_it = niter[order[0]];
     auto run_loop = [&]() -> int {
         int n_act = n_tot;
@@ -253,7 +260,7 @@ int field_diffuse(eut_field *f, const int32_t *niter, const int32_t *indvar, int
     auto mix = [&](uint64_t v) { key = (key ^ v) * 0x100000001b3ull; };
     for (int a = 0; a < n_tot; a++) mix((uint64_t)niter[order[a]]);
     mix((uint64_t)f->opt_cpt); mix((uint64_t)f->opt_variant); mix((uint64_t)f->opt_nbuf); mix((uint64_t)f->opt_debug);
-    mix((uint64_t)f->opt_shape); mix((uint64_t)f->opt_group_cols);
+    mix((uint64_t)f->opt_shape); mix((uint64_t)f->opt_group_cols); mix((uint64_t)base);
     const auto hit = f->graphs.find(key);
     if (phase != 0) {
         EUT_TRY(run_loop());
@@ -287,9 +294,9 @@ int field_diffuse(eut_field *f, const int32_t *niter, const int32_t *indvar, int
         f->cur[c] = (uint8_t)((f->cur[c] + niter[order[a]]) & 1);
         f->h_cur32[c] = f->cur[c];
     }
-    EUT_CUDA(cudaMemcpyAsync(f->d_cur, f->h_cur32.data(), f->C * sizeof(int32_t),
-                             cudaMemcpyHostToDevice, f->stream));
-    return EUT_OK;
+    // device mirror: only the entries of this call's columns (another call may be in flight on the
+    // other compute stream with its own columns)
+    return launch_set_cur(f, f->act_col, f->d_act + 2 * f->act_cap + base, n_tot);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -193,6 +193,22 @@ int launch_permute_out(eut_field *f, double *d_stage, int64_t ld, const int32_t 
     return EUT_OK;
 }
 
+// d_cur[col[i]] = value[i]: the device mirror of "which buffer holds column c" after a diffuse call
+__global__ void k_set_cur(int32_t *__restrict__ cur, const int32_t *__restrict__ col,
+                          const int32_t *__restrict__ value, const int n)
+{
+    for (int i = threadIdx.x; i < n; i += blockDim.x) cur[col[i]] = value[i];
+}
+
+int launch_set_cur(eut_field *f, const int32_t *d_col, const int32_t *d_value, int n)
+{
+    if (n <= 0) return EUT_OK;
+    k_set_cur<<<1, 128, 0, f->stream>>>(f->d_cur, d_col, d_value, n);
+    f->launches++;
+    EUT_CUDA(cudaGetLastError());
+    return EUT_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Column reductions (min, max, sum) and fill: diffuse_compoundsPar's `sd > 0` column selection and
 // its D = Inf -> column-mean rule (R/growthEnvironment.R:372, :393-401).

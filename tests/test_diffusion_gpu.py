@@ -287,3 +287,23 @@ def test_one_shot_streaming_pipeline_option(small_mesh, tmp_path):
     subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=300)
     ref = oracle.diffChangePar(m.mat_in, m.mat_out, conc, niter, indvar, 2)
     assert_parity(np.load(outp), ref)
+
+
+@pytest.mark.parametrize("chunks", ["1,2,3,1,4", "2,2,2,2,2,1", "5,6"])
+def test_one_shot_two_lane_chunk_pipeline(harbor_mesh, chunks, monkeypatch):
+    """The one-shot pipeline alternates its column chunks between two compute streams, each chunk with
+    its own range of the launch tables.  Small meshes fit one chunk, so the chunk sizes are forced
+    (EUT_ONESHOT_CHUNKS is read per call): odd and even substep counts, columns in any order, repeated
+    calls (the second and third replay CUDA graphs), and the single-lane setting must all give the
+    oracle's bits."""
+    m = harbor_mesh
+    conc = synth.synthetic_concentrations(m.field_pts, 13, seed=31)
+    niter = [9, 3, 12, 1, 7, 7, 2, 30, 5, 4, 8]
+    indvar = [1, 3, 2, 5, 4, 6, 8, 13, 11, 9, 10]
+    ref = oracle.diffChangePar(m.mat_in, m.mat_out, conc, niter, indvar, 2)
+    monkeypatch.setenv("EUT_ONESHOT_CHUNKS", chunks)
+    for _ in range(3):
+        assert_parity(eb.diffChangePar(m.mat_in, m.mat_out, conc, niter, indvar), ref)
+    # feed the result back in, as R does every round
+    ref2 = oracle.diffChangePar(m.mat_in, m.mat_out, ref, niter, indvar, 2)
+    assert_parity(eb.diffChangePar(m.mat_in, m.mat_out, ref, niter, indvar), ref2)
