@@ -400,8 +400,9 @@ int run_pipeline(CachedPlan *cp, const double *conc_in, int64_t n_rows, int64_t 
     cudaStream_t lanes[2] = {f->stream, n_lanes == 2 ? f->lane2 : f->stream};
     struct Restore {
         eut_field *f; cudaStream_t s;
-        ~Restore() { f->stream = s; f->act_base = 0; }
+        ~Restore() { f->stream = s; f->act_base = 0; f->no_split = false; }
     } restore{f, f->stream};
+    f->no_split = true;
     const int64_t chunk = f->stage_cols;
     std::vector<size_t> cuts;
     // EUT_ONESHOT_CHUNKS=4,12,32,12,4: explicit chunk sizes (used when they add up to the active columns)

@@ -181,7 +181,10 @@ struct eut_field {
     int32_t *d_act = nullptr;          // [3][cap]: column, starting buffer, final buffer
     int64_t act_cap = 0;
     int64_t act_base = 0;              // first table entry the next diffuse call uses (one-shot pipeline: per chunk)
-    cudaStream_t lane2 = nullptr;      // second compute stream of the one-shot pipeline (created on demand)
+    cudaStream_t lane2 = nullptr;      // second compute stream (created on demand): wide diffuse calls run their
+                                       // column halves side by side; the one-shot pipeline alternates chunks
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool no_split = false;             // set by the one-shot pipeline, which uses lane2 itself
     // the tables the substep launch reads (default: d_act; the column-streaming pipeline points them
     // at a ring of per-launch tables)
     const int32_t *act_col = nullptr, *act_par = nullptr;

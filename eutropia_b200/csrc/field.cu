@@ -86,6 +86,8 @@ int field_destroy(eut_field *f)
     cudaFree(f->d_ring); cudaFree(f->d_stream_cols);
     if (f->h_ring) cudaFreeHost(f->h_ring);
     if (f->lane2) cudaStreamDestroy(f->lane2);
+    if (f->ev_fork) cudaEventDestroy(f->ev_fork);
+    if (f->ev_join) cudaEventDestroy(f->ev_join);
     if (f->own_stream && f->stream) cudaStreamDestroy(f->stream);
     if (f->copy_stream) cudaStreamDestroy(f->copy_stream);
     if (f->down_stream) cudaStreamDestroy(f->down_stream);
@@ -231,6 +233,25 @@ int field_diffuse(eut_field *f, const int32_t *niter, const int32_t *indvar, int
     // pipeline, capi.cu) are given disjoint ranges.
     const int64_t base = f->act_base;
     if (base < 0 || base + n_tot > f->act_cap) { set_error("eut_field_diffuse: table range out of bounds"); return EUT_ERR_ARG; }
+    // Two lanes: from 32 columns on, the table is dealt out to two halves (alternating entries, so both
+    // keep the descending substep counts) and every substep is two launches side by side on two
+    // streams.  One launch over all columns ends in a partial wave of CTAs and leaves SMs idle until
+    // the next launch may start; the other lane's CTAs take those SMs.  EUT_DIFFUSE_LANES=1 disables.
+    static const bool lanes_off = [] { const char *e = getenv("EUT_DIFFUSE_LANES"); return e && atoi(e) == 1; }();
+    const bool split = !lanes_off && !f->no_split && phase == 0 && f->opt_phase == 0 && n_tot >= 32 &&
+                       f->plan->segmented && f->opt_variant != 1;
+    if (split) {
+        if (!f->lane2) EUT_CUDA(cudaStreamCreateWithFlags(&f->lane2, cudaStreamNonBlocking));
+        if (!f->ev_fork) {
+            EUT_CUDA(cudaEventCreateWithFlags(&f->ev_fork, cudaEventDisableTiming));
+            EUT_CUDA(cudaEventCreateWithFlags(&f->ev_join, cudaEventDisableTiming));
+        }
+        std::vector<int64_t> dealt;
+        for (int a = 0; a < n_tot; a += 2) dealt.push_back(order[a]);
+        for (int a = 1; a < n_tot; a += 2) dealt.push_back(order[a]);
+        order.swap(dealt);
+    }
+    const int n_a = split ? (n_tot + 1) / 2 : n_tot;      // entries [0, n_a) lane one, [n_a, n_tot) lane two
     for (int a = 0; a < n_tot; a++) {
         const int c = indvar[order[a]] - 1;
         f->h_act[base + a] = c;
@@ -242,11 +263,34 @@ int field_diffuse(eut_field *f, const int32_t *niter, const int32_t *indvar, int
         EUT_CUDA(cudaMemcpyAsync(f->d_act + r * f->act_cap + base, f->h_act.data() + r * f->act_cap + base,
                                  n_tot * sizeof(int32_t), cudaMemcpyHostToDevice, f->stream));
     const int max_it = niter[order[0]];
+    const int max_it_b = split ? niter[order[n_a]] : 0;
+    const int n_launches = max_it + max_it_b;
+    cudaStream_t main_stream = f->stream;
+    const int32_t *tab_col = f->act_col, *tab_par = f->act_par;
+    struct Restore {
+        eut_field *f; cudaStream_t s; const int32_t *c, *p;
+        ~Restore() { f->stream = s; f->act_col = c; f->act_par = p; }
+    } restore{f, main_stream, tab_col, tab_par};
     auto run_loop = [&]() -> int {
-        int n_act = n_tot;
+        if (split) {
+            EUT_CUDA(cudaEventRecord(f->ev_fork, main_stream));
+            EUT_CUDA(cudaStreamWaitEvent(f->lane2, f->ev_fork, 0));
+        }
+        int n_act = n_a, n_act_b = n_tot - n_a;
         for (int s = 0; s < max_it; s++) {
             while (n_act > 0 && niter[order[n_act - 1]] <= s) n_act--;
+            f->stream = main_stream; f->act_col = tab_col; f->act_par = tab_par;
             EUT_TRY(launch_substep(f, n_act, s));
+            if (split && s < max_it_b) {
+                while (n_act_b > 0 && niter[order[n_a + n_act_b - 1]] <= s) n_act_b--;
+                f->stream = f->lane2; f->act_col = tab_col + n_a; f->act_par = tab_par + n_a;
+                EUT_TRY(launch_substep(f, n_act_b, s));
+            }
+        }
+        f->stream = main_stream; f->act_col = tab_col; f->act_par = tab_par;
+        if (split) {
+            EUT_CUDA(cudaEventRecord(f->ev_join, f->lane2));
+            EUT_CUDA(cudaStreamWaitEvent(main_stream, f->ev_join, 0));
         }
         return EUT_OK;
     };
@@ -260,13 +304,13 @@ int field_diffuse(eut_field *f, const int32_t *niter, const int32_t *indvar, int
     auto mix = [&](uint64_t v) { key = (key ^ v) * 0x100000001b3ull; };
     for (int a = 0; a < n_tot; a++) mix((uint64_t)niter[order[a]]);
     mix((uint64_t)f->opt_cpt); mix((uint64_t)f->opt_variant); mix((uint64_t)f->opt_nbuf); mix((uint64_t)f->opt_debug);
-    mix((uint64_t)f->opt_shape); mix((uint64_t)f->opt_group_cols); mix((uint64_t)base);
+    mix((uint64_t)f->opt_shape); mix((uint64_t)f->opt_group_cols); mix((uint64_t)base); mix((uint64_t)split);
     const auto hit = f->graphs.find(key);
     if (phase != 0) {
         EUT_TRY(run_loop());
         if (phase == 2) return EUT_OK;                  // the flip happened in phase 1
     } else if (hit != f->graphs.end()) {
-        if (hit->second) { EUT_CUDA(cudaGraphLaunch(hit->second, f->stream)); f->launches += max_it; }
+        if (hit->second) { EUT_CUDA(cudaGraphLaunch(hit->second, f->stream)); f->launches += n_launches; }
         else EUT_TRY(run_loop());                       // capture failed once: plain launches
     } else if (!no_graphs && max_it >= 4 && f->graph_seen.count(key) && f->graphs.size() < 64) {
         cudaGraph_t graph = nullptr;
