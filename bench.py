@@ -125,18 +125,21 @@ def cpu_sample(mesh, substeps_full, n_cols_full, threads, target_s=12.0):
         run, kind, what = oracle.diffChangePar, "port", "oracle/diffchange_oracle.c"
     n = mesh.nfields
     rng = np.random.default_rng(99)
-    # calibration: one substep on one column per thread
+    # calibration: the marginal cost of a substep on one column per thread (two call lengths, so
+    # that the per-call copies of the matrix do not count as substep time)
     c1 = int(max(1, min(n_cols_full, threads)))
     conc = np.asfortranarray(rng.uniform(0.0, 25.0, (n, c1)))
-    t1 = None
-    for _ in range(2):                                     # the first call pays for cold pages and thread start-up
+
+    def once(k):
         t0 = time.perf_counter()
-        run(mesh.mat_in, mesh.mat_out, conc, np.full(c1, 2, np.int32), np.arange(1, c1 + 1), threads)
-        dt = max(time.perf_counter() - t0, 1e-6) / 2
-        t1 = dt if t1 is None else min(t1, dt)
+        run(mesh.mat_in, mesh.mat_out, conc, np.full(c1, k, np.int32), np.arange(1, c1 + 1), threads)
+        return time.perf_counter() - t0
+    once(1)                                                # cold pages, thread start-up
+    ta, tb = once(1), once(5)
+    t1 = max((tb - ta) / 4, 1e-6)
     # sample: full substep count if it fits, on as many column waves (threads columns each) as fit
     s = int(max(1, min(substeps_full, target_s / t1)))
-    waves = int(max(1, min(target_s / (t1 * s), n_cols_full / c1)))
+    waves = int(max(1, min(round(target_s / (t1 * s)), n_cols_full // c1)))
     cols = int(min(n_cols_full, c1 * waves))
     conc = np.asfortranarray(rng.uniform(0.0, 25.0, (n, cols)))
     iv = np.arange(1, cols + 1, dtype=np.int32)

@@ -396,8 +396,8 @@ int run_pipeline(CachedPlan *cp, const double *conc_in, int64_t n_rows, int64_t 
     // other lane's CTAs fill the SMs that partial wave leaves idle.  Every chunk gets its own range
     // of the field's launch tables (act_base).  EUT_ONESHOT_LANES=1 restores the single stream.
     static const int n_lanes = [] { const char *e = getenv("EUT_ONESHOT_LANES"); return (e && atoi(e) == 1) ? 1 : 2; }();
-    if (n_lanes == 2 && !f->lane2) EUT_CUDA(cudaStreamCreateWithFlags(&f->lane2, cudaStreamNonBlocking));
-    cudaStream_t lanes[2] = {f->stream, n_lanes == 2 ? f->lane2 : f->stream};
+    if (n_lanes == 2 && !f->lane[0]) EUT_CUDA(cudaStreamCreateWithFlags(&f->lane[0], cudaStreamNonBlocking));
+    cudaStream_t lanes[2] = {f->stream, n_lanes == 2 ? f->lane[0] : f->stream};
     struct Restore {
         eut_field *f; cudaStream_t s;
         ~Restore() { f->stream = s; f->act_base = 0; f->no_split = false; }
@@ -581,7 +581,7 @@ int oneshot_run(const int32_t *adj, int64_t n_edges, const int32_t *nn, int64_t 
     const double t_enq = now_ms();
     EUT_CUDA(cudaStreamSynchronize(f->copy_stream));
     EUT_CUDA(cudaStreamSynchronize(f->stream));
-    if (f->lane2) EUT_CUDA(cudaStreamSynchronize(f->lane2));
+    if (f->lane[0]) EUT_CUDA(cudaStreamSynchronize(f->lane[0]));
     EUT_CUDA(cudaStreamSynchronize(f->down_stream));
     if (trace)
         fprintf(stderr, "[eut] one-shot: plan lookup%s + first chunks %.2f ms, enqueue %.2f ms, drain %.2f ms\n",

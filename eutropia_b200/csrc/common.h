@@ -166,6 +166,8 @@ struct eut_plan {
 // ---------------------------------------------------------------------------------------------
 // field: N x C concentrations resident in HBM (two buffers, Jacobi ping-pong per column)
 // ---------------------------------------------------------------------------------------------
+constexpr int kMaxLanes = 4;
+
 struct eut_field {
     eut_plan *plan = nullptr;
     int64_t C = 0;
@@ -181,10 +183,12 @@ struct eut_field {
     int32_t *d_act = nullptr;          // [3][cap]: column, starting buffer, final buffer
     int64_t act_cap = 0;
     int64_t act_base = 0;              // first table entry the next diffuse call uses (one-shot pipeline: per chunk)
-    cudaStream_t lane2 = nullptr;      // second compute stream (created on demand): wide diffuse calls run their
-                                       // column halves side by side; the one-shot pipeline alternates chunks
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    bool no_split = false;             // set by the one-shot pipeline, which uses lane2 itself
+    // extra compute streams (created on demand): wide diffuse calls run their columns in up to
+    // kMaxLanes parts side by side; the one-shot pipeline alternates its chunks between stream and lane[0]
+    cudaStream_t lane[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+    bool in_lanes = false;             // a lane launch is being issued (stencil_seg.cu slices the columns coarser)
+    bool no_split = false;             // set by the one-shot pipeline, which uses lane[0] itself
     // the tables the substep launch reads (default: d_act; the column-streaming pipeline points them
     // at a ring of per-launch tables)
     const int32_t *act_col = nullptr, *act_par = nullptr;

@@ -68,7 +68,7 @@ int field_destroy(eut_field *f)
     if (!f) return EUT_OK;
     cudaSetDevice(f->plan->device);
     if (f->stream) cudaStreamSynchronize(f->stream);
-    if (f->lane2) cudaStreamSynchronize(f->lane2);
+    for (cudaStream_t l : f->lane) if (l) cudaStreamSynchronize(l);
     if (f->copy_stream) cudaStreamSynchronize(f->copy_stream);
     if (f->down_stream) cudaStreamSynchronize(f->down_stream);
     cudaFree(f->d_buf); cudaFree(f->d_cur); cudaFree(f->d_act); cudaFree(f->d_cols);
@@ -85,9 +85,9 @@ int field_destroy(eut_field *f)
     for (cudaEvent_t e : f->ev_pool) cudaEventDestroy(e);
     cudaFree(f->d_ring); cudaFree(f->d_stream_cols);
     if (f->h_ring) cudaFreeHost(f->h_ring);
-    if (f->lane2) cudaStreamDestroy(f->lane2);
+    for (cudaStream_t l : f->lane) if (l) cudaStreamDestroy(l);
     if (f->ev_fork) cudaEventDestroy(f->ev_fork);
-    if (f->ev_join) cudaEventDestroy(f->ev_join);
+    for (cudaEvent_t e : f->ev_join) if (e) cudaEventDestroy(e);
     if (f->own_stream && f->stream) cudaStreamDestroy(f->stream);
     if (f->copy_stream) cudaStreamDestroy(f->copy_stream);
     if (f->down_stream) cudaStreamDestroy(f->down_stream);
@@ -233,25 +233,29 @@ int field_diffuse(eut_field *f, const int32_t *niter, const int32_t *indvar, int
     // pipeline, capi.cu) are given disjoint ranges.
     const int64_t base = f->act_base;
     if (base < 0 || base + n_tot > f->act_cap) { set_error("eut_field_diffuse: table range out of bounds"); return EUT_ERR_ARG; }
-    // Two lanes: from 32 columns on, the table is dealt out to two halves (alternating entries, so both
-    // keep the descending substep counts) and every substep is two launches side by side on two
-    // streams.  One launch over all columns ends in a partial wave of CTAs and leaves SMs idle until
-    // the next launch may start; the other lane's CTAs take those SMs.  EUT_DIFFUSE_LANES=1 disables.
-    static const bool lanes_off = [] { const char *e = getenv("EUT_DIFFUSE_LANES"); return e && atoi(e) == 1; }();
-    const bool split = !lanes_off && !f->no_split && phase == 0 && f->opt_phase == 0 && n_tot >= 32 &&
-                       f->plan->segmented && f->opt_variant != 1;
-    if (split) {
-        if (!f->lane2) EUT_CUDA(cudaStreamCreateWithFlags(&f->lane2, cudaStreamNonBlocking));
-        if (!f->ev_fork) {
-            EUT_CUDA(cudaEventCreateWithFlags(&f->ev_fork, cudaEventDisableTiming));
-            EUT_CUDA(cudaEventCreateWithFlags(&f->ev_join, cudaEventDisableTiming));
+    // Lanes: from 32 columns on, the table is dealt out to L parts (round robin, so each keeps the
+    // descending substep counts) and every substep is L launches side by side on L streams.  One
+    // launch over all columns ends in a partial wave of CTAs and leaves SMs idle until the next launch
+    // may start; the other lanes' CTAs take those SMs.  About 32 columns per lane, at most kMaxLanes lanes
+    // (EUT_DIFFUSE_LANES caps the number, 1 disables).
+    static const int lanes_env = [] { const char *e = getenv("EUT_DIFFUSE_LANES"); return e ? std::min(kMaxLanes, std::max(1, atoi(e))) : kMaxLanes; }();
+    int L = 1;
+    if (lanes_env > 1 && !f->no_split && phase == 0 && f->opt_phase == 0 && f->plan->segmented && f->opt_variant != 1)
+        L = std::max(1, std::min(lanes_env, n_tot < 64 ? n_tot / 16 : n_tot / 32));
+    if (L > 1) {
+        for (int l = 1; l < L; l++) {
+            if (!f->lane[l - 1]) EUT_CUDA(cudaStreamCreateWithFlags(&f->lane[l - 1], cudaStreamNonBlocking));
+            if (!f->ev_join[l - 1]) EUT_CUDA(cudaEventCreateWithFlags(&f->ev_join[l - 1], cudaEventDisableTiming));
         }
+        if (!f->ev_fork) EUT_CUDA(cudaEventCreateWithFlags(&f->ev_fork, cudaEventDisableTiming));
         std::vector<int64_t> dealt;
-        for (int a = 0; a < n_tot; a += 2) dealt.push_back(order[a]);
-        for (int a = 1; a < n_tot; a += 2) dealt.push_back(order[a]);
+        for (int l = 0; l < L; l++)
+            for (int a = l; a < n_tot; a += L) dealt.push_back(order[a]);
         order.swap(dealt);
     }
-    const int n_a = split ? (n_tot + 1) / 2 : n_tot;      // entries [0, n_a) lane one, [n_a, n_tot) lane two
+    int lane_begin[kMaxLanes + 1];                      // table entries [lane_begin[l], lane_begin[l + 1]) belong to lane l
+    lane_begin[0] = 0;
+    for (int l = 0; l < L; l++) lane_begin[l + 1] = lane_begin[l] + (n_tot - l + L - 1) / L;
     for (int a = 0; a < n_tot; a++) {
         const int c = indvar[order[a]] - 1;
         f->h_act[base + a] = c;
@@ -263,34 +267,36 @@ int field_diffuse(eut_field *f, const int32_t *niter, const int32_t *indvar, int
         EUT_CUDA(cudaMemcpyAsync(f->d_act + r * f->act_cap + base, f->h_act.data() + r * f->act_cap + base,
                                  n_tot * sizeof(int32_t), cudaMemcpyHostToDevice, f->stream));
     const int max_it = niter[order[0]];
-    const int max_it_b = split ? niter[order[n_a]] : 0;
-    const int n_launches = max_it + max_it_b;
+    int n_launches = 0;
+    for (int l = 0; l < L; l++) n_launches += niter[order[lane_begin[l]]];
     cudaStream_t main_stream = f->stream;
     const int32_t *tab_col = f->act_col, *tab_par = f->act_par;
     struct Restore {
         eut_field *f; cudaStream_t s; const int32_t *c, *p;
-        ~Restore() { f->stream = s; f->act_col = c; f->act_par = p; }
+        ~Restore() { f->stream = s; f->act_col = c; f->act_par = p; f->in_lanes = false; }
     } restore{f, main_stream, tab_col, tab_par};
     auto run_loop = [&]() -> int {
-        if (split) {
+        if (L > 1) {
             EUT_CUDA(cudaEventRecord(f->ev_fork, main_stream));
-            EUT_CUDA(cudaStreamWaitEvent(f->lane2, f->ev_fork, 0));
+            for (int l = 1; l < L; l++) EUT_CUDA(cudaStreamWaitEvent(f->lane[l - 1], f->ev_fork, 0));
         }
-        int n_act = n_a, n_act_b = n_tot - n_a;
+        int n_act[kMaxLanes];
+        for (int l = 0; l < L; l++) n_act[l] = lane_begin[l + 1] - lane_begin[l];
+        f->in_lanes = L > 1;
         for (int s = 0; s < max_it; s++) {
-            while (n_act > 0 && niter[order[n_act - 1]] <= s) n_act--;
-            f->stream = main_stream; f->act_col = tab_col; f->act_par = tab_par;
-            EUT_TRY(launch_substep(f, n_act, s));
-            if (split && s < max_it_b) {
-                while (n_act_b > 0 && niter[order[n_a + n_act_b - 1]] <= s) n_act_b--;
-                f->stream = f->lane2; f->act_col = tab_col + n_a; f->act_par = tab_par + n_a;
-                EUT_TRY(launch_substep(f, n_act_b, s));
+            for (int l = 0; l < L; l++) {
+                const int b = lane_begin[l];
+                while (n_act[l] > 0 && niter[order[b + n_act[l] - 1]] <= s) n_act[l]--;
+                if (n_act[l] == 0) continue;
+                f->stream = l == 0 ? main_stream : f->lane[l - 1];
+                f->act_col = tab_col + b; f->act_par = tab_par + b;
+                EUT_TRY(launch_substep(f, n_act[l], s));
             }
         }
-        f->stream = main_stream; f->act_col = tab_col; f->act_par = tab_par;
-        if (split) {
-            EUT_CUDA(cudaEventRecord(f->ev_join, f->lane2));
-            EUT_CUDA(cudaStreamWaitEvent(main_stream, f->ev_join, 0));
+        f->stream = main_stream; f->act_col = tab_col; f->act_par = tab_par; f->in_lanes = false;
+        for (int l = 1; l < L; l++) {
+            EUT_CUDA(cudaEventRecord(f->ev_join[l - 1], f->lane[l - 1]));
+            EUT_CUDA(cudaStreamWaitEvent(main_stream, f->ev_join[l - 1], 0));
         }
         return EUT_OK;
     };
@@ -304,7 +310,7 @@ int field_diffuse(eut_field *f, const int32_t *niter, const int32_t *indvar, int
     auto mix = [&](uint64_t v) { key = (key ^ v) * 0x100000001b3ull; };
     for (int a = 0; a < n_tot; a++) mix((uint64_t)niter[order[a]]);
     mix((uint64_t)f->opt_cpt); mix((uint64_t)f->opt_variant); mix((uint64_t)f->opt_nbuf); mix((uint64_t)f->opt_debug);
-    mix((uint64_t)f->opt_shape); mix((uint64_t)f->opt_group_cols); mix((uint64_t)base); mix((uint64_t)split);
+    mix((uint64_t)f->opt_shape); mix((uint64_t)f->opt_group_cols); mix((uint64_t)base); mix((uint64_t)L);
     const auto hit = f->graphs.find(key);
     if (phase != 0) {
         EUT_TRY(run_loop());
