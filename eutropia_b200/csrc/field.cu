@@ -242,6 +242,12 @@ int field_diffuse(eut_field *f, const int32_t *niter, const int32_t *indvar, int
     int L = 1;
     if (lanes_env > 1 && !f->no_split && phase == 0 && f->opt_phase == 0 && f->plan->segmented && f->opt_variant != 1)
         L = std::max(1, std::min(lanes_env, n_tot < 64 ? n_tot / 16 : n_tot / 32));
+    // ... provided the lanes together still put a full wave of CTAs on the GPU (one or two CTAs per SM,
+    // by tile size); smaller fields keep the single launch with finer column slices.  Measured at 64
+    // columns, lanes against one stream: 100 k points 155 vs 189 G updates/s (below the threshold),
+    // 300 k 282 vs 251, 420 k 300 vs 246, 600 k 307 vs 262 (tools/cols_scaling.py); bench step at 1 M: 232 vs 213.
+    static const bool lanes_force = getenv("EUT_DIFFUSE_LANES_FORCE") != nullptr;
+    if (L > 1 && !lanes_force && (int64_t)p->n_tiles * L < 148ll * (p->segs.max_tile_segs > 224 ? 1 : 2)) L = 1;
     if (L > 1) {
         for (int l = 1; l < L; l++) {
             if (!f->lane[l - 1]) EUT_CUDA(cudaStreamCreateWithFlags(&f->lane[l - 1], cudaStreamNonBlocking));
