@@ -246,7 +246,7 @@ int field_diffuse(eut_field *f, const int32_t *niter, const int32_t *indvar, int
     // by tile size); smaller fields keep the single launch with finer column slices.  Measured at 64
     // columns, lanes against one stream: 100 k points 155 vs 189 G updates/s (below the threshold),
     // 300 k 282 vs 251, 420 k 300 vs 246, 600 k 307 vs 262 (tools/cols_scaling.py); bench step at 1 M: 232 vs 213.
-    static const bool lanes_force = getenv("EUT_DIFFUSE_LANES_FORCE") != nullptr;
+    const bool lanes_force = getenv("EUT_DIFFUSE_LANES_FORCE") != nullptr;      // read per call: the tests force lanes on small meshes
     if (L > 1 && !lanes_force && (int64_t)p->n_tiles * L < 148ll * (p->segs.max_tile_segs > 224 ? 1 : 2)) L = 1;
     if (L > 1) {
         for (int l = 1; l < L; l++) {

@@ -307,3 +307,36 @@ def test_one_shot_two_lane_chunk_pipeline(harbor_mesh, chunks, monkeypatch):
     # feed the result back in, as R does every round
     ref2 = oracle.diffChangePar(m.mat_in, m.mat_out, ref, niter, indvar, 2)
     assert_parity(eb.diffChangePar(m.mat_in, m.mat_out, ref, niter, indvar), ref2)
+
+
+@pytest.mark.parametrize("n_cols", [40, 70, 131])
+def test_session_lanes_match_oracle(harbor_mesh, n_cols, monkeypatch):
+    """A wide diffuse call deals its columns out to 2..4 lanes (streams) that run side by side
+    (field.cu).  Small meshes stay below the lane threshold, so the lanes are forced here: mixed
+    substep counts (zeros, odd, even), columns in any order, three calls in a row (the second captures,
+    the third replays the CUDA graph with its fork / join), then a narrow call on the same field."""
+    m = harbor_mesh
+    monkeypatch.setenv("EUT_DIFFUSE_LANES_FORCE", "1")
+    rng = np.random.default_rng(n_cols)
+    conc = synth.synthetic_concentrations(m.field_pts, n_cols, seed=n_cols)
+    indvar = rng.permutation(n_cols)[: n_cols - 3] + 1
+    niter = rng.integers(0, 9, indvar.size)
+    niter[:4] = [8, 1, 0, 5]
+    plan = eb.Plan(m.mat_in, m.mat_out)
+    assert plan.info.segmented == 1
+    fld = eb.Field(plan, n_cols)
+    fld.upload(conc)
+    ref = conc
+    for _ in range(3):
+        fld.diffuse(niter, indvar)
+        ref = oracle.diffChangePar(m.mat_in, m.mat_out, ref, niter, indvar, 4)
+        assert_parity(fld.download(), ref)
+    fld.diffuse([3, 2], [2, 1])
+    ref = oracle.diffChangePar(m.mat_in, m.mat_out, ref, [3, 2], [2, 1], 2)
+    assert_parity(fld.download(), ref)
+    # the same through the ELL cross-check kernel (never uses lanes)
+    fld2 = eb.Field(plan, n_cols)
+    fld2.set_option("variant", 1)
+    fld2.upload(conc)
+    fld2.diffuse(niter, indvar)
+    assert_parity(fld2.download(), oracle.diffChangePar(m.mat_in, m.mat_out, conc, niter, indvar, 4))
