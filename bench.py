@@ -50,15 +50,56 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons during the timed region: NVML polled from a thread every few
+    milliseconds (starts at once, so even a region of a few steps is sampled); `nvidia-smi -lms` as
+    the fallback when NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.nvml, self.handle, self.thread, self.halt = None, None, None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            handle = None
+            try:                                    # CUDA ordinal -> NVML device by PCI address
+                import torch
+                pr = torch.cuda.get_device_properties(index)
+                handle = pynvml.nvmlDeviceGetHandleByPciBusId("%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id))
+            except Exception:
+                handle = None
+            if handle is None:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                ids = [v for v in vis.split(",") if v.strip().isdigit()]
+                handle = pynvml.nvmlDeviceGetHandleByIndex(int(ids[index]) if index < len(ids) else index)
+            self.nvml, self.handle = pynvml, handle
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _sample(self):
+        n = self.nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        mask = int(get(self.handle))
+        self.rows.append((sm, self.max_mhz, {nm for nm, bit in self.BITS if mask & bit}))
+
+    def _poll(self):
+        while not self.halt.is_set():
+            try:
+                self._sample()
+            except Exception:
+                return
+            self.halt.wait(0.005)
 
     def start(self):
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -68,26 +109,32 @@ class ClockSampler:
             self.proc = None
 
     def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for line in self.proc.stdout:
+            r = [x.strip() for x in line.split(",")]
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for nm, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
+                self.rows.append((float(r[0]), float(r[1]),
+                                  {nm for nm, v in zip(names, r[3:7]) if v.lower().startswith("active")}))
             except Exception:
                 continue
+
+    def stop(self):
+        """Call while the last timed kernels are still in flight (before the closing synchronize)."""
+        source = "nvml"
+        if self.thread is not None:
+            self.halt.set()
+            self.thread.join(timeout=1.0)
+        elif self.proc is not None:
+            source = "nvidia-smi"
+            time.sleep(0.15)
+            self.proc.terminate()
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML and no nvidia-smi"], "samples": 0}
+        sm = [r[0] for r in self.rows]
+        mx = [r[1] for r in self.rows]
+        reasons = set().union(*[r[2] for r in self.rows]) if self.rows else set()
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": source}
 
 
 def build_inputs(workload: str, n_cols: int, seed: int, want_conc=True):
