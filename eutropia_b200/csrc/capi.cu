@@ -5,7 +5,9 @@
 #include <cstring>
 #include <limits>
 #include <memory>
+#include <atomic>
 #include <mutex>
+#include <thread>
 
 #include <functional>
 #include <future>
@@ -658,13 +660,33 @@ int eut_diffchange(const double *adjmat, int64_t n_edges, const double *nneighbo
     // the one case this test cannot see).  Finite data -- every real round -- never gets past the
     // scan; otherwise the columns after the first affected one are redone in sequence: one
     // substep, NaN at the carried points, the remaining substeps.
+    // exponent all ones <=> adding 2^52 to the magnitude bits carries into bit 63 (integer adds and
+    // ors only: vectorises, no dependent floating-point chain); columns are scanned by a few threads
     auto any_nonfinite = [&](const double *col) {
-        double s = 0.0;
-        for (int64_t i = 0; i < n_rows; i++) s += col[i] * 0.0;
-        return s != s;
+        uint64_t acc = 0;
+        for (int64_t i = 0; i < n_rows; i++) {
+            uint64_t b;
+            std::memcpy(&b, col + i, sizeof b);
+            acc |= (b & 0x7fffffffffffffffull) + 0x0010000000000000ull;
+        }
+        return (acc >> 63) != 0;
     };
+    std::vector<uint8_t> bad(iv.size(), 0);
+    {
+        const size_t work = iv.size() * (size_t)n_rows;
+        const unsigned nt = work < (1u << 22) ? 1u : std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()));
+        std::atomic<size_t> next{0};
+        auto scan = [&]() {
+            for (size_t k = next++; k < iv.size(); k = next++)
+                bad[k] = any_nonfinite(conc_out + (size_t)(iv[k] - 1) * n_rows) ? 1 : 0;
+        };
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < nt; t++) pool.emplace_back(scan);
+        scan();
+        for (auto &th : pool) th.join();
+    }
     size_t first = 0;
-    while (first < iv.size() && !any_nonfinite(conc_out + (size_t)(iv[first] - 1) * n_rows)) first++;
+    while (first < iv.size() && !bad[first]) first++;
     if (first + 1 >= iv.size()) return rc;
     std::vector<double> mid((size_t)n_rows);
     const int32_t one = 1;
