@@ -16,6 +16,88 @@
 
 using namespace eut;
 
+// Replays the tables the segment kernel indexes with (tile meta records, copy lists, segment and
+// generic-point records): the image of every tile (image cell -> internal position) from its copy
+// lists, then per point the cells its summation chain reads, in the kernel's order
+// A A B B C O- O+ D E E F F (stencil_seg.cu), translated to reference ids.
+static int decode_seg_tables(const eut_plan *p, const std::vector<int32_t> &meta, const std::vector<int2> &copies,
+                             const std::vector<uint16_t> &segs, const std::vector<uint16_t> &gens,
+                             int64_t *row_ptr, int32_t *col)
+{
+    const int64_t N = p->N;
+    const int R = p->segs.R;
+    const int nt = p->n_tiles;
+    std::vector<int32_t> nbr((size_t)12 * p->Np, -1);          // [position][slot], reference ids (0-based)
+    std::vector<uint8_t> deg(p->Np, 0), done(p->Np, 0);
+    std::vector<int32_t> img;
+    for (int t = 0; t < nt; t++) {
+        const int32_t *m = meta.data() + (size_t)12 * t;
+        const int32_t t0 = m[0], cnt = m[1], b0 = m[2], nb = m[3], s0 = m[4], ns = m[5], cells = m[7];
+        const int32_t g0 = m[8], ng = m[9], x0 = m[10], nx = m[11];
+        img.assign((size_t)cells + 1, -1);                     // -1: the copies never write the cell (zero header, holes)
+        for (int32_t k = b0; k < b0 + nb; k++) {
+            const int32_t g = copies[k].x, so = copies[k].y & 0xffff, n = (int32_t)((uint32_t)copies[k].y >> 16);
+            for (int32_t j = 0; j < n; j++)
+                if (so + j <= cells && g + j < p->Np) img[so + j] = g + j;
+        }
+        for (int32_t k = s0; k < s0 + ns; k++)
+            if (copies[k].y >= 0 && copies[k].y <= cells) img[copies[k].y] = copies[k].x;
+        const int head = t0 & 1;
+        auto add = [&](int64_t q, int64_t cell) {
+            if (cell < 0 || cell > cells) return;
+            const int32_t src = img[cell];
+            if (src < 0 || p->iperm[src] < 0) return;          // absent neighbour: the kernel adds +0.0
+            if (deg[q] < 12) nbr[(size_t)q * 12 + deg[q]] = p->iperm[src];
+            deg[q]++;
+        };
+        for (int32_t s = g0; s < g0 + ng; s++) {
+            const uint16_t *r = segs.data() + (size_t)24 * s;
+            const int len = r[7] >> 12, out = r[7] & 0xfff;
+            auto pair_cell = [&](int col, int red, int k) -> int64_t {   // cell k (0..R) of a pair stream
+                if (k == 0) return r[red] / 8;
+                if (k == R) return r[red + 1] / 8;
+                return r[col] / 8 + k;
+            };
+            for (int j = 0; j < len; j++) {
+                const int64_t q = (int64_t)t0 + out + j - head;
+                if (q < 0 || q >= p->Np || done[q]) { set_error("eut_plan_get_csr: segment tables produce position %lld twice or out of range", (long long)q); return EUT_ERR_UNSUPPORTED; }
+                done[q] = 1;
+                add(q, pair_cell(1, 10, j)); add(q, pair_cell(1, 10, j + 1));       // A A
+                add(q, pair_cell(2, 12, j)); add(q, pair_cell(2, 12, j + 1));       // B B
+                add(q, r[3] / 8 + j);                                                  // C
+                add(q, j == 0 ? r[8] / 8 : r[0] / 8 + j - 1);                          // O-
+                add(q, j == R - 1 ? r[9] / 8 : r[0] / 8 + j + 1);                      // O+
+                add(q, r[4] / 8 + j);                                                  // D
+                add(q, pair_cell(5, 14, j)); add(q, pair_cell(5, 14, j + 1));       // E E
+                add(q, pair_cell(6, 16, j)); add(q, pair_cell(6, 16, j + 1));       // F F
+                if (img[r[0] / 8 + j] != q) { set_error("eut_plan_get_csr: segment %d does not read its own point", s); return EUT_ERR_UNSUPPORTED; }
+            }
+        }
+        for (int32_t x = x0; x < x0 + nx; x++) {
+            const uint16_t *r = gens.data() + (size_t)16 * x;
+            const int64_t q = (int64_t)t0 + r[13] - head;
+            if (q < 0 || q >= p->Np || done[q]) { set_error("eut_plan_get_csr: generic tables produce position %lld twice or out of range", (long long)q); return EUT_ERR_UNSUPPORTED; }
+            done[q] = 1;
+            for (int k = 0; k < 12; k++)
+                if (r[k]) add(q, r[k]);
+            if (img[r[12]] != q) { set_error("eut_plan_get_csr: generic point %d does not read its own cell", x); return EUT_ERR_UNSUPPORTED; }
+        }
+        (void)cnt;
+    }
+    row_ptr[0] = 0;
+    for (int64_t i = 0; i < N; i++) {
+        const int64_t q = p->perm[i];
+        if (!done[q] || deg[q] > 12) { set_error("eut_plan_get_csr: point %lld is not produced by any segment", (long long)i + 1); return EUT_ERR_UNSUPPORTED; }
+        row_ptr[i + 1] = row_ptr[i] + deg[q];
+    }
+    if (row_ptr[N] != p->E) { set_error("eut_plan_get_csr: the segment tables hold %lld edges, mat.in has %lld", (long long)row_ptr[N], (long long)p->E); return EUT_ERR_UNSUPPORTED; }
+    for (int64_t i = 0; i < N; i++) {
+        const int64_t q = p->perm[i];
+        for (int k = 0; k < deg[q]; k++) col[row_ptr[i] + k] = nbr[(size_t)q * 12 + k] + 1;
+    }
+    return EUT_OK;
+}
+
 extern "C" {
 
 const char *eut_last_error(void) { return last_error_cstr(); }
@@ -99,9 +181,24 @@ int eut_plan_get_csr(const eut_plan *p, int64_t *row_ptr, int32_t *col)
 {
     clear_error();
     if (!p || !row_ptr || (!col && p->E > 0)) { set_error("eut_plan_get_csr: NULL argument"); return EUT_ERR_ARG; }
-    if (p->host_only) { set_error("eut_plan_get_csr: host-only plan has no device tables"); return EUT_ERR_UNSUPPORTED; }
-    EUT_TRY(ensure_device(p->device));
+    if (p->host_only && !p->segmented) { set_error("eut_plan_get_csr: host-only plan has no device tables"); return EUT_ERR_UNSUPPORTED; }
+    if (!p->host_only) EUT_TRY(ensure_device(p->device));
     const int64_t N = p->N;
+    if (p->segmented) {
+        // The segment kernel does not index with the ELL tables: read ITS tables back from the device
+        // (a host-only plan: the planner's host copies) and replay them.
+        const SegPlanHost &S = p->segs;
+        if (p->host_only) return decode_seg_tables(p, S.meta, S.copies, S.segs, S.gens, row_ptr, col);
+        const int nt = p->n_tiles;
+        std::vector<int32_t> meta((size_t)12 * nt);
+        std::vector<int2> copies((size_t)S.n_copies);
+        std::vector<uint16_t> segs((size_t)24 * S.n_segs), gens((size_t)16 * S.n_gens);
+        if (nt) EUT_CUDA(cudaMemcpy(meta.data(), p->d_seg_meta, meta.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        if (!copies.empty()) EUT_CUDA(cudaMemcpy(copies.data(), p->d_copies, copies.size() * sizeof(int2), cudaMemcpyDeviceToHost));
+        if (!segs.empty()) EUT_CUDA(cudaMemcpy(segs.data(), p->d_segs, segs.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+        if (!gens.empty()) EUT_CUDA(cudaMemcpy(gens.data(), p->d_gens, gens.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+        return decode_seg_tables(p, meta, copies, segs, gens, row_ptr, col);
+    }
     if (p->ell_w > 0) {
         std::vector<int32_t> nbr((size_t)p->ell_w * p->Np);
         std::vector<uint8_t> deg(p->Np);

@@ -45,7 +45,7 @@ static int to_positions(const eut_plan *p, const int32_t *ids, int64_t n, std::v
 static int upload_cols(eut_field *f, const int32_t *cols, int64_t n_cols, int32_t **d_cols)
 {
     if (n_cols < 0 || n_cols > f->C || (n_cols > 0 && !cols)) { set_error("halo: bad column list"); return EUT_ERR_ARG; }
-    // the 4th quarter of d_cols/h_cols is reserved for the halo calls (field.cu uses 0..2... [0,1] up, [2,3] down)
+    // the halo calls have their own column list (h_halo_cols / d_halo_cols); field.cu's d_cols slots belong to the transfers
     int32_t *hc = f->h_halo_cols.data();
     for (int64_t j = 0; j < n_cols; j++) {
         if (cols[j] < 1 || cols[j] > f->C) { set_error("halo: column %d out of bounds", cols[j]); return EUT_ERR_INDEX; }

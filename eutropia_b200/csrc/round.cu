@@ -110,6 +110,15 @@ int field_exoenzyme_catalysis(eut_field *cf, eut_field *ef, int32_t exo_col, dou
                                                                            (int)p->Np, kcat, km, delta_time, m);
     cf->launches++;
     EUT_CUDA(cudaGetLastError());
+    // ... and whatever the exoenzyme field does next on its own stream (the decay k_scale of
+    // R/run_simulation.R:367-371 overwrites the column read here) has to wait for this kernel
+    if (ef->stream != cf->stream) {
+        cudaEvent_t done = nullptr;
+        EUT_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+        EUT_CUDA(cudaEventRecord(done, cf->stream));
+        EUT_CUDA(cudaStreamWaitEvent(ef->stream, done, 0));
+        EUT_CUDA(cudaEventDestroy(done));          // released by the runtime once the wait has completed
+    }
     return EUT_OK;
 }
 

@@ -153,7 +153,10 @@ EUT_API int eut_plan_create(eut_plan **out,
 EUT_API int eut_plan_destroy(eut_plan *plan);
 EUT_API int eut_plan_get_info(const eut_plan *plan, eut_plan_info *info);
 /* The in-neighbour index map the device uses, translated back to reference ids (1-based), for
- * bit-exact comparison with the CSR derived from mat.in: row_ptr[N+1], col[E]. */
+ * bit-exact comparison with the CSR derived from mat.in: row_ptr[N+1], col[E].  Read back from the
+ * tables the selected kernel indexes with: ELL / CSR arrays, or -- for a segment plan -- the tile
+ * meta records, copy lists, segment and generic-point records, replayed in the kernel's summation
+ * order (a EUT_PLAN_HOST_ONLY segment plan replays the planner's host copies of the same tables). */
 EUT_API int eut_plan_get_csr(const eut_plan *plan, int64_t *row_ptr, int32_t *col);
 /* Tile tables of a EUT_PLAN_HOST_ONLY plan (sizes from eut_plan_get_info), for inspection and for
  * the CPU tests of the planner:

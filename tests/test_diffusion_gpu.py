@@ -96,14 +96,17 @@ def test_index_map_bit_exact(harbor_mesh):
     to, frm = m.mat_in[:, 1].astype(np.int64), m.mat_in[:, 0]
     order = np.argsort(to, kind="stable")
     row_ptr = np.concatenate([[0], np.cumsum(np.bincount(to, minlength=n + 1)[1:])])
-    for o in (_lib.ORDER_IDENTITY, _lib.ORDER_ROWBLOCK, _lib.ORDER_TILED):
+    # ORDER_SEGMENTS: the map is replayed from the segment kernel's own tables (meta, copy lists,
+    # segment and generic-point records) read back from the device, not from the ELL tables
+    for o in (_lib.ORDER_IDENTITY, _lib.ORDER_ROWBLOCK, _lib.ORDER_TILED, _lib.ORDER_SEGMENTS):
         for generic in (False, True):
             plan = eb.Plan(m.mat_in, m.mat_out, order=o, force_generic=generic)
+            assert bool(plan.info.segmented) == (o == _lib.ORDER_SEGMENTS and not generic)
             rp, col = plan.csr()
             assert np.array_equal(rp, row_ptr)
             assert np.array_equal(col, frm[order])
             perm = plan.perm()
-            assert np.array_equal(np.sort(perm), np.arange(n))
+            assert np.unique(perm).size == n and perm.min() >= 0 and perm.max() < plan.info.n_padded   # injective (segment plans leave gap cells)
 
 
 def test_shuffled_mat_in_keeps_row_order_semantics(small_mesh):

@@ -45,8 +45,8 @@ def test_adjust_uptake_arithmetic():
     assert exchange.adjust_uptake(["BIO"], [0.0], 0.28, acc, 1 / 6) == (None, None)
 
 
-def _small_env(layers=3, seed=3, **kw):
-    m = mesh.make_mesh("Rectangle_30_24", 1.0, layers)
+def _small_env(layers=3, seed=3, polygon="Rectangle_30_24", **kw):
+    m = mesh.make_mesh(polygon, 1.0, layers)
     rng = np.random.default_rng(seed)
     cpds = ["glc", "ac", "o2", "sucr", "fru", "const"]
     conc = rng.uniform(0, 25, (m.nfields, len(cpds)))
@@ -81,6 +81,28 @@ def test_exoenzyme_catalysis_and_decay_match_oracle():
     assert np.all(np.isfinite(got_c)) and err.max() <= TOL, err.max()
     assert np.array_equal(got_e, want_e)                                 # one multiplication: bit-exact
     assert np.any(want_c[:, 3] < conc[:, 3]) and np.all(want_c[:, 3] >= 0)   # substrate is consumed, never negative
+
+
+@pytest.mark.gpu
+def test_exoenzyme_decay_waits_for_catalysis_on_a_large_mesh():
+    """Catalysis runs on the concentration field's stream and READS the exoenzyme column; the decay
+    runs on the exoenzyme field's stream and overwrites it (R/run_simulation.R:343-371).  On a mesh
+    large enough that the catalysis kernel is still running when the decay is queued, the second
+    must wait for the first (an event between the two streams) -- several rounds back to back."""
+    m, cpds, conc, rng = _small_env(polygon="Rectangle_520_500", seed=11)
+    exo = rng.uniform(1, 50, (m.nfields, 1))
+    enz = [environment.Exoenzyme("inv", ["sucr", "glc", "fru"], [-1.0, 1.0, 1.0], Kcat=1200.0, Km=4.0, D=10.0, lambda_=0.9)]
+    env = environment.GrowthEnvironment(m, cpds, conc, np.full(6, 75.0), None, exoenzymes=enz, exoenzymes_conc=exo)
+    dt = 1 / 6
+    want_c, want_e = conc.copy(), exo.copy()
+    for _ in range(3):
+        env.exoenzyme_activity(dt)
+        want_c = oracle.exoenzyme_catalysis(want_c, want_e, 1, 1200.0, 4.0, [4, 1, 5], enz[0].stoich, None, dt)
+        want_e = oracle.exoenzyme_decay(want_e, 1, 0.9, dt)
+    got_c, got_e = env.concentrations, env.exoenzymes_conc
+    assert np.array_equal(got_e, want_e)
+    scale = np.maximum(np.abs(want_c), np.abs(conc[:, :5]).max(axis=1, keepdims=True))
+    assert (np.abs(got_c - want_c) / scale).max() <= 3 * TOL
 
 
 @pytest.mark.gpu

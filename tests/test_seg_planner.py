@@ -152,3 +152,19 @@ def test_shuffled_ids_still_exact():
         replay(mm, plan, check_alignment=True, max_growth=8.0)
     else:
         assert plan.info.order in (_lib.ORDER_TILED, _lib.ORDER_ROWBLOCK)
+
+
+@pytest.mark.parametrize("name,layers", [("Rectangle_40_33", 3), ("Petri_23", 6), ("harbor", 4), ("Rectangle_11_10", 2)])
+def test_segment_tables_decode_to_mat_in(name, layers):
+    """eut_plan_get_csr on a segment plan replays the kernel's tables (here the planner's host copies; the
+    -m gpu suite reads the same tables back from the device): the in-neighbour map must be mat.in, bit for bit."""
+    poly = mesh.harbor_polygon(90.0) if name == "harbor" else name
+    m = mesh.make_mesh(poly, 1.0, layers)
+    n = m.nfields
+    to, frm = m.mat_in[:, 1].astype(np.int64), m.mat_in[:, 0]
+    order = np.argsort(to, kind="stable")
+    row_ptr = np.concatenate([[0], np.cumsum(np.bincount(to, minlength=n + 1)[1:])])
+    plan = eb.Plan(m.mat_in, m.mat_out, order=_lib.ORDER_SEGMENTS, host_only=True)
+    assert plan.info.segmented == 1
+    rp, col = plan.csr()
+    assert np.array_equal(rp, row_ptr) and np.array_equal(col, frm[order])
