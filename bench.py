@@ -198,6 +198,86 @@ def cpu_sample(mesh, substeps_full, n_cols_full, threads, target_s=12.0):
                       f"({what}, OpenMP over compounds, {threads} threads)"}
 
 
+
+def reference_columns(mesh, conc, substeps, threads):
+    """`conc` (N x k) diffused `substeps` times by the reference's own diffChangePar (oracle/_ref) or, if
+    that library is absent, by the oracle port; the checker of the parity gates."""
+    import oracle
+    oracle.build()
+    run = oracle.ref_diffChangePar if oracle.ref_available() else oracle.diffChangePar
+    k = conc.shape[1]
+    return run(mesh.mat_in, mesh.mat_out, np.asfortranarray(conc), np.full(k, substeps, np.int32),
+               np.arange(1, k + 1, dtype=np.int32), max(1, min(threads, k))), ("reference" if oracle.ref_available() else "port")
+
+
+def compare(got, ref):
+    denom = np.maximum(np.abs(ref), 1e-300)
+    return {"bit_equal": bool(np.array_equal(got, ref)), "max_rel": float(np.max(np.abs(got - ref) / denom))}
+
+
+def parity_gate(eb, mesh, plan, conc, substeps, dev, k=4):
+    """BASELINE.md 3 "parity gate on every timed config": k columns of the TIMED mesh x the timed substep
+    count through the session tier (the kernels `value` times) and through the one-shot C ABI (what `e2e`
+    times), against the reference's diffChangePar on the host.  Outside every timed region."""
+    sub = np.asfortranarray(conc[:, :k])
+    ref, kind = reference_columns(mesh, sub, substeps, host_threads())
+    niter, indvar = np.full(k, substeps, np.int32), np.arange(1, k + 1, dtype=np.int32)
+    f = eb.Field(plan, k)
+    f.upload(sub)
+    f.diffuse(niter, indvar)
+    a = compare(f.download(), ref)
+    f.close()
+    b = compare(eb.diffChangePar(mesh.mat_in, mesh.mat_out, sub, niter, indvar, device=dev), ref)
+    out = {"columns": k, "substeps": int(substeps), "points": int(mesh.nfields), "against": kind,
+           "session": a, "one_shot": b, "bit_equal": a["bit_equal"] and b["bit_equal"],
+           "max_rel": max(a["max_rel"], b["max_rel"]), "tolerance": 1e-12}
+    if not (out["max_rel"] <= 1e-12):
+        raise SystemExit(f"bench.py: parity gate failed on the timed configuration: {json.dumps(out)}")
+    return out
+
+
+def square100k_leg(eb, torch, dev, peak):
+    """BASELINE.json configs[1]: square field, 100 467 points x 16 compounds x 1000 substeps on one GPU
+    (L2-resident; bounded by launch latency, not HBM).  Device time by CUDA events; parity on 2 columns x
+    1000 substeps against the reference."""
+    from eutropia_b200 import synth
+    mesh = synth.config_mesh("square100k")
+    n, c, s = mesh.nfields, 16, 1000
+    conc = synth.synthetic_concentrations(mesh.field_pts, c, seed=7)
+    plan = eb.Plan(mesh.mat_in, mesh.mat_out, device=dev)
+    field = eb.Field(plan, c)
+    field.upload(conc)
+    niter, indvar = np.full(c, s, np.int32), np.arange(1, c + 1, dtype=np.int32)
+    stream = torch.cuda.ExternalStream(field.stream, device=dev)
+    for _ in range(3):
+        field.diffuse(niter, indvar)
+    field.sync()
+    steps = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = field.launch_count
+    with torch.cuda.stream(stream):
+        e0.record()
+    for _ in range(steps):
+        field.diffuse(niter, indvar)
+    with torch.cuda.stream(stream):
+        e1.record()
+    field.sync()
+    ms = e0.elapsed_time(e1) / steps
+    launches = (field.launch_count - l0) // steps
+    field.upload(conc)
+    field.diffuse(niter[:2], indvar[:2])
+    ref, kind = reference_columns(mesh, conc[:, :2], s, 2)
+    par = compare(field.download(cols=[1, 2]), ref)
+    field.close(); plan.close()
+    if not (par["max_rel"] <= 1e-12):
+        raise SystemExit(f"bench.py: parity gate failed on square100k: {json.dumps(par)}")
+    value = n * c * s / (ms * 1e-3)
+    return {"workload": f"square100k: {n} points x {c} compounds x {s} substeps (configs[1]), field resident in L2",
+            "value": value, "unit": UNIT, "ms_per_step": ms, "us_per_substep": ms * 1e3 / s, "launches_per_step": int(launches),
+            "algorithmic_GBps": BYTES_PER_UPDATE * value / 1e9, "frac_of_hbm_peak": BYTES_PER_UPDATE * value / 1e9 / peak,
+            "parity": dict(par, against=kind, columns=2, substeps=s)}
+
+
 def run_reference(args):
     """--impl reference: the reference's own diffChangePar (src/diffChange.cpp compiled into
     oracle/_ref; the oracle port if that library is absent) on this box's host cores, same config
@@ -246,6 +326,7 @@ def run_ours(args):
             os.environ["NCCL_DEBUG"] = "WARN"
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        cpu_group = dist.new_group(backend="gloo")       # host-side barriers (an NCCL barrier spins on the GPU)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: eutropia_b200 has no CPU path")
     torch.cuda.set_device(local)
@@ -317,35 +398,114 @@ def run_ours(args):
     updates_per_step = n * cpg * world * substeps
     value = updates_per_step * args.steps / (ms * 1e-3)
 
+    # ---- parity gate on the timed configuration (outside the timed regions) -------------------
+    parity = parity_gate(eb, mesh, plan, conc, substeps, dev) if (rank == 0 and not args.no_parity) else None
+
     # ---- end to end through the C ABI with host buffers (one-shot diffChangePar) ------------
-    pin_in = torch.from_numpy(conc.T).contiguous().pin_memory()      # [cpg, n] == column-major n x cpg
-    pin_out = torch.empty_like(pin_in).pin_memory()
+    # N = 1: eut_diffchange_par on this GPU.  N > 1: ONE process (rank 0) hands the whole N x (64 N)
+    # matrix to eut_diffchange_par_multi with all N devices -- the way R would call it -- while the other
+    # ranks wait on a host-side (gloo) barrier; the N private per-rank calls of round 1 are kept as
+    # `e2e_ranks`.  Pinned and pageable (plain numpy, what R's REALSXP memory is) caller buffers.
     adj = np.require(mesh.mat_in, dtype=np.int32, requirements=["F", "A"])
     nn = np.require(mesh.mat_out, dtype=np.int32, requirements=["F", "A"])
     L = eb._lib.lib()
-
-    def e2e_call():
-        eb._lib.check(L.eut_diffchange_par(eb._lib.ptr(adj), adj.shape[0], eb._lib.ptr(nn), nn.shape[0],
-                                           pin_in.data_ptr(), n, cpg, eb._lib.ptr(niter), eb._lib.ptr(indvar),
-                                           cpg, 1, pin_out.data_ptr(), dev))
-
     e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, 5))
-    for _ in range(0 if args.no_e2e else 2):
-        e2e_call()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_call()
-        pin_in, pin_out = pin_out, pin_in       # next round starts from this round's result
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{dev}")
+
+    def host_barrier():
+        field.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=cpu_group)
+
+    def time_calls(call, swap):
+        for _ in range(2):
+            call()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            call()
+            swap()                                  # next round starts from this round's result
+        return time.perf_counter() - t0
+
+    def one_device(buf_in, buf_out):
+        state = [buf_in, buf_out]
+
+        def call():
+            eb._lib.check(L.eut_diffchange_par(eb._lib.ptr(adj), adj.shape[0], eb._lib.ptr(nn), nn.shape[0],
+                                               state[0], n, cpg, eb._lib.ptr(niter), eb._lib.ptr(indvar),
+                                               cpg, 1, state[1], dev))
+        return call, (lambda: state.reverse())
+
+    e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": n * cpg * world * 8, "d2h_bytes_per_step": n * cpg * world * 8,
+           "steps": e2e_steps, "timer": "host wall clock around the blocking calls"}
+    e2e_ranks = None
+    if e2e_steps:
+        pin_in = torch.from_numpy(conc.T).contiguous().pin_memory()      # [cpg, n] == column-major n x cpg
+        pin_out = torch.empty_like(pin_in).pin_memory()
+        # (a) every rank on its own GPU with its own columns, all at once (N = 1: the headline)
+        host_barrier()
+        call, swap = one_device(pin_in.data_ptr(), pin_out.data_ptr())
+        dt = time_calls(call, swap)
+        host_barrier()
+        te = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{dev}")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        ranks_value = updates_per_step * e2e_steps / float(te[0])
+        if world == 1:
+            e2e.update(value=ranks_value, api="eut_diffchange_par (one-shot C ABI, pinned host buffers, graph recognised by byte comparison)")
+            pg_in = np.array(conc, order="F")                             # plain malloc'ed memory, touched
+            pg_out = np.zeros_like(pg_in, order="F")
+            call, swap = one_device(pg_in.ctypes.data, pg_out.ctypes.data)
+            dt = time_calls(call, swap)
+            e2e["pageable_value"] = updates_per_step * e2e_steps / dt
+            e2e["pageable_note"] = "same call with pageable (numpy) caller buffers: staged through pinned slot rings by copier threads"
+            del pg_in, pg_out
+        else:
+            e2e_ranks = {"value": ranks_value, "unit": UNIT, "api": f"{world} processes, each eut_diffchange_par on its own GPU and columns (max over ranks)"}
+            del pin_out
+            # (b) one process, all GPUs
+            if rank == 0:
+                ct = cpg * world
+                big_in = torch.empty((ct, n), dtype=torch.float64).pin_memory()
+                for r in range(world):
+                    big_in[r * cpg:(r + 1) * cpg].copy_(pin_in)
+                big_out = torch.empty_like(big_in).pin_memory()
+                nit_all = np.full(ct, substeps, dtype=np.int32)
+                iv_all = np.arange(1, ct + 1, dtype=np.int32)
+                devs = np.arange(world, dtype=np.int32)
+
+                def multi(bufs, addr):
+                    def call():
+                        eb._lib.check(L.eut_diffchange_par_multi(eb._lib.ptr(adj), adj.shape[0], eb._lib.ptr(nn), nn.shape[0],
+                                                                 addr(bufs[0]), n, ct, eb._lib.ptr(nit_all), eb._lib.ptr(iv_all), ct, 1,
+                                                                 addr(bufs[1]), eb._lib.ptr(devs), world))
+                    return call, (lambda: bufs.reverse())
+                bufs = [big_in, big_out]
+                del big_in, big_out
+                call, swap = multi(bufs, lambda t: t.data_ptr())
+                dt = time_calls(call, swap)
+                e2e.update(value=updates_per_step * e2e_steps / dt,
+                           api=f"eut_diffchange_par_multi: ONE process, {world} GPUs, {ct} columns in one call (pinned host buffers)")
+                # every GPU started from the same 64 columns: the blocks of the result must agree bit for bit
+                e2e["blocks_agree"] = all(bool(torch.equal(bufs[0][:cpg], bufs[0][r * cpg:(r + 1) * cpg])) for r in range(1, world))
+                pg = [bufs[0].numpy().copy(), np.zeros((ct, n))]
+                del bufs
+                call, swap = multi(pg, lambda t: t.ctypes.data)
+                dt = time_calls(call, swap)
+                e2e["pageable_value"] = updates_per_step * e2e_steps / dt
+                e2e["pageable_note"] = "same call with pageable (numpy) caller buffers"
+                del pg
+                L.eut_oneshot_reset()
+            host_barrier()
+
+    # ---- other BASELINE.json configurations, driver-visible ---------------------------------
+    peak, peak_src = peaks()
+    extra = {}
+    if rank == 0 and not args.no_extra:
+        extra["square100k"] = square100k_leg(eb, torch, dev, peak)
     if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = updates_per_step * e2e_steps / float(te[0]) if e2e_steps else None
+        host_barrier()
 
     if rank == 0:
-        peak, peak_src = peaks()
         n_sub = substeps * args.steps
         launch_ms = diff_ms / n_sub
         achieved = BYTES_PER_UPDATE * n * cpg / (launch_ms * 1e-3) / 1e9
@@ -356,11 +516,14 @@ def run_ours(args):
                 traffic = json.load(open(tp)).get(args.workload)
             except Exception:
                 traffic = None
-        cpu = None
+        cpu = cpu_policy = None
         if world == 1 and not args.no_cpu:
             import oracle
             oracle.build()
             cpu = cpu_sample(mesh, substeps, cpg, host_threads())
+            # the reference's own default: n.cores = min(10, detectCores() - 1)  (R/run_simulation.R:137-138)
+            pol = max(1, min(10, host_threads() - 1))
+            cpu_policy = cpu_sample(mesh, substeps, cpg, pol, target_s=6.0) if pol != host_threads() else cpu
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -374,16 +537,19 @@ def run_ours(args):
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel": "k_substep_seg" if plan.info.segmented else "k_substep_tile" if plan.info.tiled else ("k_substep_ell" if plan.info.ell_width else "k_substep_csr"),
                          "launch_ms": launch_ms,
-                         "algorithmic_bytes_per_launch": BYTES_PER_UPDATE * n * cpg},
+                         "algorithmic_bytes_per_launch": BYTES_PER_UPDATE * n * cpg,
+                         "whole_step_frac": BYTES_PER_UPDATE * value / world / 1e9 / peak},
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * cpg * 8,
-                    "d2h_bytes_per_step": n * cpg * 8, "steps": e2e_steps,
-                    "api": "eut_diffchange_par (one-shot C ABI, pinned host buffers, graph cached by hash)",
-                    "timer": "host wall clock around the blocking calls, max over ranks"},
+            "cpu_baseline_reference_policy": cpu_policy,
+            "e2e": e2e,
+            "parity": parity,
             "gpu_launches": int(launches), "clocks": clocks,
             "breakdown_ms_per_step": {"diffusion_substeps": diff_ms / args.steps,
                                       "scatter_clamp_and_gather": (ms - diff_ms) / args.steps},
         }
+        if e2e_ranks is not None:
+            line["e2e_ranks"] = e2e_ranks
+        line.update(extra)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -398,6 +564,8 @@ def main():
     ap.add_argument("--workload", default="harbor1m", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity gate (profiling runs)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the square100k / slab legs")
     ap.add_argument("--opt", action="append", type=lambda s: (s.split("=")[0], int(s.split("=")[1])),
                     help="field option, e.g. --opt cpt=4")
     args = ap.parse_args()

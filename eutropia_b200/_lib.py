@@ -63,6 +63,8 @@ def lib() -> C.CDLL:
         "eut_device_count": (C.c_int, []),
         "eut_diffchange": (C.c_int, [vp, i64, vp, i64, vp, i64, i64, vp, i64, vp, C.c_int]),
         "eut_diffchange_par": (C.c_int, [vp, i64, vp, i64, vp, i64, i64, vp, vp, i64, C.c_int, vp, C.c_int]),
+        "eut_diffchange_par_multi": (C.c_int, [vp, i64, vp, i64, vp, i64, i64, vp, vp, i64, C.c_int, vp, vp, C.c_int]),
+        "eut_deal_columns": (C.c_int, [vp, vp, i64, C.c_int, vp]),
         "eut_oneshot_reset": (None, []),
         "eut_build_dcm": (C.c_int, [vp, i64, i64, dbl, C.c_int, vp, i64, C.POINTER(i64), vp]),
         "eut_plan_create": (C.c_int, [C.POINTER(vp), vp, vp, i64, vp, vp, i64, i64, C.c_int, C.c_uint32]),
@@ -110,7 +112,7 @@ def lib() -> C.CDLL:
 
 
 EXPORTS = (
-    "eut_last_error eut_abi_version eut_device_count eut_diffchange eut_diffchange_par "
+    "eut_last_error eut_abi_version eut_device_count eut_diffchange eut_diffchange_par eut_diffchange_par_multi eut_deal_columns "
     "eut_oneshot_reset eut_build_dcm eut_plan_create eut_plan_destroy eut_plan_get_info eut_plan_get_csr "
     "eut_plan_get_perm eut_plan_get_tiles eut_plan_get_segs eut_field_create eut_field_destroy eut_field_upload eut_field_download "
     "eut_field_diffuse eut_field_sync eut_field_stream eut_field_set_stream "

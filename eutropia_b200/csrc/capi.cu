@@ -299,7 +299,7 @@ int eut_field_sync(eut_field *f)
     EUT_TRY(ensure_device(f->plan->device));
     EUT_CUDA(cudaStreamSynchronize(f->copy_stream));
     EUT_CUDA(cudaStreamSynchronize(f->stream));
-    EUT_CUDA(cudaStreamSynchronize(f->down_stream));
+    EUT_TRY(field_sync_down(f));
     return EUT_OK;
 }
 
@@ -387,423 +387,6 @@ int eut_field_scale_column(eut_field *f, int32_t col, double factor)
     if (col < 1 || col > f->C) { set_error("eut_field_scale_column: column %d out of bounds", col); return EUT_ERR_INDEX; }
     EUT_TRY(ensure_device(f->plan->device));
     return field_scale_column(f, col - 1, factor);
-}
-
-// ---- one-shot tier ---------------------------------------------------------------------------
-namespace {
-
-struct CachedPlan {
-    uint64_t h_edges = 0, h_nn = 0;
-    int64_t n_edges = 0, n_nn = 0, n_rows = 0;
-    int device = 0;
-    eut_plan *plan = nullptr;
-    eut_field *field = nullptr;
-    int64_t field_cols = 0;
-    uint64_t stamp = 0;
-    const void *last_adj = nullptr, *last_nn = nullptr;   // the arrays of the last call (a hint, never trusted)
-};
-
-std::mutex g_mu;
-std::vector<CachedPlan> g_cache;
-uint64_t g_stamp = 0;
-constexpr size_t kMaxCached = 4;
-
-void drop(CachedPlan &c)
-{
-    if (c.field) field_destroy(c.field);
-    if (c.plan) { plan_free(c.plan); delete c.plan; }
-    c.field = nullptr; c.plan = nullptr;
-}
-
-// R calls diffChangePar every round with the same mat.in / mat.out (R/growthEnvironment.R:385-390);
-// the graph analysis and its device tables are kept and recognised by content hash.
-struct GraphHash { uint64_t he = 0, hn = 0; };
-
-GraphHash hash_graph(const int32_t *adj, int64_t n_edges, const int32_t *nn, int64_t n_nn)
-{
-    GraphHash h;
-    h.he = hash_bytes(adj, (size_t)n_edges * 2 * sizeof(int32_t), 0x5eedull);
-    h.hn = hash_bytes(nn, (size_t)n_nn * 2 * sizeof(int32_t), 0xfeedull);
-    return h;
-}
-
-int get_cached(const GraphHash &h, const int32_t *adj, int64_t n_edges, const int32_t *nn, int64_t n_nn,
-               int64_t n_rows, int device, CachedPlan **out)
-{
-    for (auto &c : g_cache)
-        if (c.h_edges == h.he && c.h_nn == h.hn && c.n_edges == n_edges && c.n_nn == n_nn &&
-            c.n_rows == n_rows && c.device == device) {
-            c.stamp = ++g_stamp;
-            c.last_adj = adj; c.last_nn = nn;
-            *out = &c;
-            return EUT_OK;
-        }
-    if (g_cache.size() >= kMaxCached) {
-        auto it = std::min_element(g_cache.begin(), g_cache.end(),
-                                   [](const CachedPlan &a, const CachedPlan &b) { return a.stamp < b.stamp; });
-        drop(*it);
-        g_cache.erase(it);
-    }
-    CachedPlan c;
-    c.h_edges = h.he; c.h_nn = h.hn; c.n_edges = n_edges; c.n_nn = n_nn; c.n_rows = n_rows;
-    c.device = device; c.stamp = ++g_stamp;
-    c.last_adj = adj; c.last_nn = nn;
-    c.plan = new eut_plan();
-    int rc = plan_build(c.plan, adj, adj + n_edges, n_edges, nn, nn + n_nn, n_nn, n_rows, device,
-                        EUT_ORDER_AUTO);
-    if (rc != EUT_OK) {
-        plan_free(c.plan);
-        delete c.plan;
-        return rc;
-    }
-    g_cache.push_back(c);
-    *out = &g_cache.back();
-    return EUT_OK;
-}
-
-constexpr int kRetry = -1000;   // internal: the speculated plan was not the right one
-
-// The column pipeline on the plan / field of `cp`.  `verify` (may be empty) is called once, after the
-// first chunks have been queued and before anything is written to conc_out; when it returns false
-// the streams are drained and kRetry is returned (nothing has been written to conc_out).
-int run_pipeline(CachedPlan *cp, const double *conc_in, int64_t n_rows, int64_t n_cols, const int32_t *niter,
-                 const int32_t *indvar, const std::vector<int64_t> &act, double *conc_out,
-                 const std::function<bool()> &verify)
-{
-    if (!cp->field || cp->field_cols != n_cols) {
-        if (cp->field) field_destroy(cp->field);
-        cp->field = nullptr;
-        EUT_TRY(field_create(&cp->field, cp->plan, n_cols));
-        cp->field_cols = n_cols;
-    }
-    eut_field *f = cp->field;
-    // EUT_ONESHOT_STREAM=1: column streaming (field.cu: one launch at a time over all columns that have
-    // arrived).  Measured equal to the chunked pipeline below (157 vs 160 G updates/s): what both pay
-    // for is the fixed cost of a launch over few columns (~26 us), and the chunked one replays CUDA graphs.
-    static const bool streaming = getenv("EUT_ONESHOT_STREAM") != nullptr;
-    if (streaming && act.size() >= 2) {
-        std::vector<int32_t> scols(act.size()), snit(act.size());
-        for (size_t a = 0; a < act.size(); a++) { scols[a] = indvar[act[a]]; snit[a] = niter[act[a]]; }
-        const int rc = field_stream_columns(f, conc_in, conc_out, n_rows, scols.data(), snit.data(), (int64_t)act.size(), verify);
-        return rc == -1000 ? kRetry : rc;
-    }
-    // Pipeline over chunks of active columns: H2D(g+1) | substeps(g) | D2H(g-1) on copy, compute and
-    // download streams.  The call lasts  H2D(first chunk) + all substeps + D2H(last chunk), and a launch
-    // over few columns is less efficient than one over many (tools/cols_scaling.py).
-    // Two compute streams ("lanes"), chunks alternate between them: a launch over few columns has
-    // few CTAs (tiles x column slices) and ends in a partial wave; with a second chunk in flight the
-    // other lane's CTAs fill the SMs that partial wave leaves idle.  Every chunk gets its own range
-    // of the field's launch tables (act_base).  EUT_ONESHOT_LANES=1 restores the single stream.
-    static const int n_lanes = [] { const char *e = getenv("EUT_ONESHOT_LANES"); return (e && atoi(e) == 1) ? 1 : 2; }();
-    if (n_lanes == 2 && !f->lane[0]) EUT_CUDA(cudaStreamCreateWithFlags(&f->lane[0], cudaStreamNonBlocking));
-    cudaStream_t lanes[2] = {f->stream, n_lanes == 2 ? f->lane[0] : f->stream};
-    struct Restore {
-        eut_field *f; cudaStream_t s;
-        ~Restore() { f->stream = s; f->act_base = 0; f->no_split = false; }
-    } restore{f, f->stream};
-    f->no_split = true;
-    const int64_t chunk = f->stage_cols;
-    std::vector<size_t> cuts;
-    // EUT_ONESHOT_CHUNKS=4,12,32,12,4: explicit chunk sizes (used when they add up to the active columns)
-    if (const char *e = getenv("EUT_ONESHOT_CHUNKS")) {
-        std::vector<size_t> sizes;
-        size_t tot = 0;
-        for (const char *q = e; *q;) {
-            char *end = nullptr;
-            const long v = strtol(q, &end, 10);
-            if (end == q) break;
-            if (v > 0 && v <= chunk) { sizes.push_back((size_t)v); tot += (size_t)v; }
-            q = (*end == ',') ? end + 1 : end;
-        }
-        if (tot == act.size()) {
-            cuts.push_back(0);
-            for (size_t sz : sizes) cuts.push_back(cuts.back() + sz);
-        }
-    }
-    if (cuts.empty()) {
-        // Default: ramp up to a peak chunk of a quarter of the columns and down again, in steps of a
-        // quarter of the peak (64 columns: 4, 8, 12, 16, 12, 8, 4) -- short ends for a short H2D head
-        // and D2H tail, and both lanes get the same share.  Measured on 1 M points x 64 columns x 60
-        // substeps: 19.9 ms per call against 23.8 ms on one stream with chunks 4, 12, 32, 12, 4.
-        // Anything below a quarter of the staging slot (64 MB) goes as one chunk.
-        const size_t n = act.size();
-        std::vector<size_t> sizes;
-        size_t peak = (size_t)chunk;
-        auto middle = [&](size_t m) {
-            if (m == 0) return;
-            const size_t parts = (m + peak - 1) / peak;
-            for (size_t k = 0; k < parts; k++) sizes.push_back(m / parts + (k < m % parts ? 1 : 0));
-        };
-        if (n * 4 > (size_t)chunk) {
-            peak = std::min<size_t>((size_t)chunk, std::max<size_t>(4, (n + 3) / 4));
-            const size_t r1 = std::max<size_t>(1, peak / 4), r2 = std::max<size_t>(1, peak / 2), r3 = std::max<size_t>(1, 3 * peak / 4);
-            if (n > 2 * (r1 + r2 + r3)) {
-                sizes.push_back(r1); sizes.push_back(r2); sizes.push_back(r3);
-                middle(n - 2 * (r1 + r2 + r3));
-                sizes.push_back(r3); sizes.push_back(r2); sizes.push_back(r1);
-            } else if (n > 2 * r1) { sizes.push_back(r1); middle(n - 2 * r1); sizes.push_back(r1); }
-            else middle(n);
-        } else {
-            middle(n);
-        }
-        cuts.push_back(0);
-        for (size_t sz : sizes) cuts.push_back(cuts.back() + sz);
-    }
-    struct Pending { std::vector<int32_t> cols; bool contiguous; cudaStream_t lane; };
-    std::vector<Pending> pending;
-    bool verified = !verify;
-    auto download = [&](const Pending &pd) -> int {
-        struct Lane {                                   // the un-permute runs on the lane that diffused the chunk
-            eut_field *f; cudaStream_t keep;
-            ~Lane() { f->stream = keep; }
-        } lane{f, f->stream};
-        f->stream = pd.lane;
-        if (pd.contiguous) {
-            EUT_TRY(field_download_async(f, conc_out + (size_t)(pd.cols[0] - 1) * n_rows, n_rows, pd.cols.data(), (int64_t)pd.cols.size()));
-        } else {
-            for (size_t j = 0; j < pd.cols.size(); j++)
-                EUT_TRY(field_download_async(f, conc_out + (size_t)(pd.cols[j] - 1) * n_rows, n_rows, &pd.cols[j], 1));
-        }
-        return EUT_OK;
-    };
-    auto check_now = [&]() -> int {
-        if (verified) return EUT_OK;
-        if (!verify()) {
-            cudaStreamSynchronize(f->copy_stream); cudaStreamSynchronize(lanes[0]); cudaStreamSynchronize(lanes[1]);
-            cudaStreamSynchronize(f->down_stream);
-            return kRetry;
-        }
-        verified = true;
-        for (const Pending &pd : pending) EUT_TRY(download(pd));
-        pending.clear();
-        return EUT_OK;
-    };
-    std::vector<int32_t> nit;
-    for (size_t ci = 0; ci + 1 < cuts.size(); ci++) {
-        const size_t a0 = cuts[ci], a1 = cuts[ci + 1];
-        if (a1 <= a0) continue;
-        Pending pd;
-        pd.lane = lanes[ci & 1];
-        f->stream = pd.lane;
-        f->act_base = (int64_t)a0;
-        nit.clear();
-        for (size_t a = a0; a < a1; a++) { pd.cols.push_back(indvar[act[a]]); nit.push_back(niter[act[a]]); }
-        // host column j of this chunk is conc_in column cols[j]-1: upload one column at a time when
-        // they are not contiguous, as one 2-D copy when they are
-        pd.contiguous = true;
-        for (size_t j = 1; j < pd.cols.size(); j++) pd.contiguous &= (pd.cols[j] == pd.cols[j - 1] + 1);
-        if (pd.contiguous) {
-            EUT_TRY(field_upload(f, conc_in + (size_t)(pd.cols[0] - 1) * n_rows, n_rows, pd.cols.data(), (int64_t)pd.cols.size()));
-        } else {
-            for (size_t j = 0; j < pd.cols.size(); j++)
-                EUT_TRY(field_upload(f, conc_in + (size_t)(pd.cols[j] - 1) * n_rows, n_rows, &pd.cols[j], 1));
-        }
-        EUT_TRY(field_diffuse(f, nit.data(), pd.cols.data(), (int64_t)pd.cols.size()));
-        if (!verified && ci >= 2) EUT_TRY(check_now());      // the hash has had three chunks' worth of time; the queue stays fed
-        if (verified) EUT_TRY(download(pd));
-        else pending.push_back(std::move(pd));
-    }
-    EUT_TRY(check_now());
-    return EUT_OK;
-}
-
-// Shared body: `niter[i]` substeps on 1-based column `indvar[i]`; all other columns pass through.
-int oneshot_run(const int32_t *adj, int64_t n_edges, const int32_t *nn, int64_t n_nn,
-                const double *conc_in, int64_t n_rows, int64_t n_cols, const int32_t *niter,
-                const int32_t *indvar, int64_t n_indvar, double *conc_out, int device)
-{
-    if (n_rows < 0 || n_cols < 0 || n_edges < 0 || n_nn < 0 || n_indvar < 0 ||
-        (n_rows * n_cols > 0 && (!conc_in || !conc_out)) || (n_edges > 0 && !adj) ||
-        (n_nn > 0 && !nn) || (n_indvar > 0 && (!niter || !indvar))) {
-        set_error("one-shot call: NULL pointer or negative size");
-        return EUT_ERR_ARG;
-    }
-    if (conc_in == conc_out && n_rows * n_cols > 0) {
-        set_error("one-shot call: conc_out must not alias conc_in (R value semantics)");
-        return EUT_ERR_ARG;
-    }
-    std::lock_guard<std::mutex> lock(g_mu);
-    static const bool trace = getenv("EUT_TRACE") != nullptr;
-    const double t_begin = now_ms();
-    EUT_TRY(ensure_device(device));
-    // active columns (validated by field_diffuse's rules before any work is queued)
-    std::vector<int64_t> act;
-    std::vector<uint8_t> is_act(std::max<int64_t>(n_cols, 1), 0);
-    for (int64_t i = 0; i < n_indvar; i++) {
-        if (niter[i] <= 0) continue;
-        if (indvar[i] < 1 || indvar[i] > n_cols) {
-            set_error("index out of bounds: column %d of a %lld-column matrix", indvar[i], (long long)n_cols);
-            return EUT_ERR_INDEX;
-        }
-        if (is_act[indvar[i] - 1]) {
-            set_error("column %d listed twice in indvar", indvar[i]);
-            return EUT_ERR_ARG;
-        }
-        is_act[indvar[i] - 1] = 1;
-        act.push_back(i);
-    }
-    // Which plan?  Decided by the content hash of the graph (83 MB at 1 M points: ~3 ms).  When the
-    // caller hands over the same arrays as last time -- R does, every round -- the hash is taken on
-    // another thread while the first chunks are already uploaded and diffused on the plan used last
-    // time; conc_out is not touched before the hash has confirmed the guess.
-    CachedPlan *guess = nullptr;
-    for (auto &c : g_cache)
-        if (c.last_adj == adj && c.last_nn == nn && c.n_edges == n_edges && c.n_nn == n_nn && c.n_rows == n_rows &&
-            c.device == device && c.field && c.field_cols == n_cols && (!guess || c.stamp > guess->stamp))
-            guess = &c;
-    int rc = kRetry;
-    GraphHash h;
-    bool have_hash = false;
-    if (guess && act.size() > 1 && !getenv("EUT_NO_SPECULATION")) {
-        std::future<GraphHash> fut = std::async(std::launch::async, hash_graph, adj, n_edges, nn, n_nn);
-        const uint64_t want_e = guess->h_edges, want_n = guess->h_nn;
-        rc = run_pipeline(guess, conc_in, n_rows, n_cols, niter, indvar, act, conc_out, [&]() {
-            h = fut.get(); have_hash = true;
-            return h.he == want_e && h.hn == want_n;
-        });
-        if (!have_hash) { h = fut.get(); have_hash = true; }      // error paths: never leave the thread behind
-        if (rc == EUT_OK) guess->stamp = ++g_stamp;
-    }
-    const double t_plan = now_ms();
-    CachedPlan *cp = guess;
-    if (rc == kRetry) {
-        if (!have_hash) h = hash_graph(adj, n_edges, nn, n_nn);
-        EUT_TRY(get_cached(h, adj, n_edges, nn, n_nn, n_rows, device, &cp));
-        rc = run_pipeline(cp, conc_in, n_rows, n_cols, niter, indvar, act, conc_out, std::function<bool()>());
-    }
-    if (rc != EUT_OK) return rc;
-    eut_field *f = cp->field;
-    // columns the call does not touch are returned as they came (src/diffChange.cpp:34, :68)
-    for (int64_t c = 0; c < n_cols; c++)
-        if (!is_act[c] && n_rows > 0)
-            memcpy(conc_out + (size_t)c * n_rows, conc_in + (size_t)c * n_rows, (size_t)n_rows * sizeof(double));
-    const double t_enq = now_ms();
-    EUT_CUDA(cudaStreamSynchronize(f->copy_stream));
-    EUT_CUDA(cudaStreamSynchronize(f->stream));
-    if (f->lane[0]) EUT_CUDA(cudaStreamSynchronize(f->lane[0]));
-    EUT_CUDA(cudaStreamSynchronize(f->down_stream));
-    if (trace)
-        fprintf(stderr, "[eut] one-shot: plan lookup%s + first chunks %.2f ms, enqueue %.2f ms, drain %.2f ms\n",
-                guess && cp == guess ? " (speculated)" : "", t_plan - t_begin, t_enq - t_plan, now_ms() - t_enq);
-    return EUT_OK;
-}
-
-}  // namespace
-
-void eut_oneshot_reset(void)
-{
-    std::lock_guard<std::mutex> lock(g_mu);
-    for (auto &c : g_cache) drop(c);
-    g_cache.clear();
-}
-
-int eut_diffchange_par(const int32_t *adjmat, int64_t n_edges, const int32_t *nneighbors,
-                       int64_t n_nn, const double *conc_in, int64_t n_rows, int64_t n_cols,
-                       const int32_t *niter, const int32_t *indvar, int64_t n_indvar, int ncores,
-                       double *conc_out, int device)
-{
-    (void)ncores;
-    clear_error();
-    return oneshot_run(adjmat, n_edges, nneighbors, n_nn, conc_in, n_rows, n_cols, niter, indvar,
-                       n_indvar, conc_out, device);
-}
-
-int eut_diffchange(const double *adjmat, int64_t n_edges, const double *nneighbors, int64_t n_nn,
-                   const double *conc_in, int64_t n_rows, int64_t n_cols, const double *niter,
-                   int64_t n_niter, double *conc_out, int device)
-{
-    clear_error();
-    if (n_edges < 0 || n_nn < 0 || n_niter < 0 || (n_edges > 0 && !adjmat) ||
-        (n_nn > 0 && !nneighbors) || (n_niter > 0 && !niter)) {
-        set_error("eut_diffchange: NULL pointer or negative size");
-        return EUT_ERR_ARG;
-    }
-    // (int) casts of src/diffChange.cpp:20,26 -- out-of-range values are where the reference's
-    // bounds check fires; they are mapped to 0 here so that plan_build reports EUT_ERR_INDEX.
-    auto to_index = [](double v) -> int32_t {
-        if (!(v > -2147483648.0 && v < 2147483648.0)) return 0;
-        return (int32_t)v;
-    };
-    std::vector<int32_t> adj((size_t)n_edges * 2), nn((size_t)n_nn * 2);
-    for (int64_t j = 0; j < 2 * n_edges; j++) adj[j] = to_index(adjmat[j]);
-    for (int64_t j = 0; j < n_nn; j++) nn[j] = to_index(nneighbors[j]);
-    // n_neighbors stays a double in the reference ((double) nn - 1, :26): require it to be an
-    // integer that int32 holds, which is what mat.out always contains
-    for (int64_t j = 0; j < n_nn; j++) {
-        double v = nneighbors[n_nn + j];
-        if (!(v == std::floor(v)) || !(std::fabs(v) < 2147483648.0)) {
-            set_error("eut_diffchange: nneighbors[%lld,2] = %g is not an integer count", (long long)j + 1, v);
-            return EUT_ERR_UNSUPPORTED;
-        }
-        nn[n_nn + j] = (int32_t)v;
-    }
-    // `for (int k = 0; k < niter(i); k++)` with a double bound (:14)
-    std::vector<int32_t> nit, iv;
-    for (int64_t i = 0; i < n_niter; i++) {
-        double v = niter[i];
-        if (!(v > 0)) continue;  // also NaN
-        if (!(v < 2147483647.0)) { set_error("eut_diffchange: niter[%lld] is not finite", (long long)i + 1); return EUT_ERR_ARG; }
-        if (i >= n_cols) { set_error("index out of bounds: niter has an entry for column %lld of a %lld-column matrix", (long long)i + 1, (long long)n_cols); return EUT_ERR_INDEX; }
-        nit.push_back((int32_t)std::ceil(v));
-        iv.push_back((int32_t)(i + 1));
-    }
-    int rc = oneshot_run(adj.data(), n_edges, nn.data(), n_nn, conc_in, n_rows, n_cols, nit.data(),
-                         iv.data(), (int64_t)iv.size(), conc_out, device);
-    if (rc != EUT_OK || iv.size() < 2) return rc;
-    // `ychg = ychg * 0` (src/diffChange.cpp:16) is not a zero fill and ychg (:10) is shared by all
-    // columns: where the last substep of one column left a non-finite change, the next column
-    // starts its inflow sum from NaN at that point.  A change is non-finite exactly where the
-    // column's result is (c + y with y = +-Inf or NaN; an overflow of the final addition alone is
-    // the one case this test cannot see).  Finite data -- every real round -- never gets past the
-    // scan; otherwise the columns after the first affected one are redone in sequence: one
-    // substep, NaN at the carried points, the remaining substeps.
-    // exponent all ones <=> adding 2^52 to the magnitude bits carries into bit 63 (integer adds and
-    // ors only: vectorises, no dependent floating-point chain); columns are scanned by a few threads
-    auto any_nonfinite = [&](const double *col) {
-        uint64_t acc = 0;
-        for (int64_t i = 0; i < n_rows; i++) {
-            uint64_t b;
-            std::memcpy(&b, col + i, sizeof b);
-            acc |= (b & 0x7fffffffffffffffull) + 0x0010000000000000ull;
-        }
-        return (acc >> 63) != 0;
-    };
-    std::vector<uint8_t> bad(iv.size(), 0);
-    {
-        const size_t work = iv.size() * (size_t)n_rows;
-        const unsigned nt = work < (1u << 22) ? 1u : std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()));
-        std::atomic<size_t> next{0};
-        auto scan = [&]() {
-            for (size_t k = next++; k < iv.size(); k = next++)
-                bad[k] = any_nonfinite(conc_out + (size_t)(iv[k] - 1) * n_rows) ? 1 : 0;
-        };
-        std::vector<std::thread> pool;
-        for (unsigned t = 1; t < nt; t++) pool.emplace_back(scan);
-        scan();
-        for (auto &th : pool) th.join();
-    }
-    size_t first = 0;
-    while (first < iv.size() && !bad[first]) first++;
-    if (first + 1 >= iv.size()) return rc;
-    std::vector<double> mid((size_t)n_rows);
-    const int32_t one = 1;
-    for (size_t j = first + 1; j < iv.size(); j++) {
-        const double *prev = conc_out + (size_t)(iv[j - 1] - 1) * n_rows;
-        double *dst = conc_out + (size_t)(iv[j] - 1) * n_rows;
-        rc = oneshot_run(adj.data(), n_edges, nn.data(), n_nn, conc_in + (size_t)(iv[j] - 1) * n_rows, n_rows, 1,
-                         &one, &one, 1, mid.data(), device);
-        if (rc != EUT_OK) return rc;
-        for (int64_t i = 0; i < n_rows; i++)
-            if (!std::isfinite(prev[i])) mid[i] = std::numeric_limits<double>::quiet_NaN();
-        const int32_t rest = nit[j] - 1;
-        if (rest > 0) {
-            rc = oneshot_run(adj.data(), n_edges, nn.data(), n_nn, mid.data(), n_rows, 1, &rest, &one, 1, dst, device);
-            if (rc != EUT_OK) return rc;
-        } else {
-            std::memcpy(dst, mid.data(), sizeof(double) * (size_t)n_rows);
-        }
-    }
-    return rc;
 }
 
 }  // extern "C"

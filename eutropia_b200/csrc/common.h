@@ -167,6 +167,7 @@ struct eut_plan {
 // field: N x C concentrations resident in HBM (two buffers, Jacobi ping-pong per column)
 // ---------------------------------------------------------------------------------------------
 constexpr int kMaxLanes = 4;
+namespace eut { struct HostStager; }
 
 struct eut_field {
     eut_plan *plan = nullptr;
@@ -204,6 +205,10 @@ struct eut_field {
     cudaEvent_t ev_stage_free[2] = {nullptr, nullptr};
     cudaEvent_t ev_stage_ready[2] = {nullptr, nullptr};
     cudaStream_t down_stream = nullptr;
+    // pageable caller memory: pinned slot rings + copier threads (hoststage.h), created on first use
+    eut::HostStager *stager = nullptr;
+    unsigned copy_threads = 0;         // threads per copier pool (0: from the host's thread budget)
+    uint64_t dn_ticket[2] = {0, 0};    // staged download job that last used each device staging slot
     cudaEvent_t ev_dstage_free[2] = {nullptr, nullptr};
     cudaEvent_t ev_dstage_ready[2] = {nullptr, nullptr};
     int64_t up_chunks = 0, down_chunks = 0;

@@ -4,6 +4,7 @@
 #include <numeric>
 
 #include "common.h"
+#include "hoststage.h"
 
 namespace eut {
 
@@ -70,6 +71,7 @@ int field_destroy(eut_field *f)
     if (f->stream) cudaStreamSynchronize(f->stream);
     for (cudaStream_t l : f->lane) if (l) cudaStreamSynchronize(l);
     if (f->copy_stream) cudaStreamSynchronize(f->copy_stream);
+    if (f->stager) { f->stager->wait_idle(); delete f->stager; f->stager = nullptr; }
     if (f->down_stream) cudaStreamSynchronize(f->down_stream);
     cudaFree(f->d_buf); cudaFree(f->d_cur); cudaFree(f->d_act); cudaFree(f->d_cols);
     cudaFree(f->d_stats); cudaFree(f->d_stage); cudaFree(f->d_stage2);
@@ -92,6 +94,19 @@ int field_destroy(eut_field *f)
     if (f->copy_stream) cudaStreamDestroy(f->copy_stream);
     if (f->down_stream) cudaStreamDestroy(f->down_stream);
     delete f;
+    return EUT_OK;
+}
+
+static int ensure_stager(eut_field *f)
+{
+    if (f->stager) return EUT_OK;
+    unsigned t = f->copy_threads;
+    if (const char *e = getenv("EUT_COPY_THREADS")) t = (unsigned)std::max(1, atoi(e));
+    if (t == 0) t = std::min(8u, std::max(1u, host_thread_budget() / 2));
+    HostStager *st = new HostStager();
+    const int rc = st->init(f->plan->device, t);
+    if (rc != EUT_OK) { delete st; return rc; }
+    f->stager = st;
     return EUT_OK;
 }
 
@@ -132,9 +147,15 @@ int field_upload(eut_field *f, const double *host, int64_t ld, const int32_t *co
         int32_t *hc = f->h_cols.data() + (size_t)slot * f->C;
         for (int64_t j = 0; j < nc; j++) hc[j] = cols ? cols[j0 + j] - 1 : (int32_t)(j0 + j);
         if (g >= 2) EUT_CUDA(cudaStreamWaitEvent(f->copy_stream, f->ev_stage_free[slot], 0));
-        EUT_CUDA(cudaMemcpy2DAsync(stage, N * sizeof(double), host + (size_t)j0 * ld,
-                                   ld * sizeof(double), N * sizeof(double), nc,
-                                   cudaMemcpyHostToDevice, f->copy_stream));
+        if (host_is_pinned(host + (size_t)j0 * ld)) {
+            EUT_CUDA(cudaMemcpy2DAsync(stage, N * sizeof(double), host + (size_t)j0 * ld,
+                                       ld * sizeof(double), N * sizeof(double), nc,
+                                       cudaMemcpyHostToDevice, f->copy_stream));
+        } else {
+            // pageable caller memory (R's REALSXP data): staged through pinned slots by copier threads
+            EUT_TRY(ensure_stager(f));
+            EUT_TRY(f->stager->upload(stage, N, host + (size_t)j0 * ld, ld, N, nc, f->copy_stream));
+        }
         EUT_CUDA(cudaEventRecord(f->ev_stage_ready[slot], f->copy_stream));
         EUT_CUDA(cudaStreamWaitEvent(f->stream, f->ev_stage_ready[slot], 0));
         int32_t *dc = f->d_cols + (size_t)slot * f->C;
@@ -166,14 +187,25 @@ int field_download_async(eut_field *f, double *host, int64_t ld, const int32_t *
         for (int64_t j = 0; j < nc; j++) hc[j] = cols ? cols[j0 + j] - 1 : (int32_t)(j0 + j);
         int32_t *dc = f->d_cols + (size_t)(2 + slot) * f->C;
         if (g >= 2) EUT_CUDA(cudaStreamWaitEvent(f->stream, f->ev_dstage_free[slot], 0));
+        if (f->dn_ticket[slot]) {                           // the slot's last user was a staged download
+            EUT_TRY(f->stager->wait_ticket(f->dn_ticket[slot]));
+            f->dn_ticket[slot] = 0;
+        }
         EUT_CUDA(cudaMemcpyAsync(dc, hc, nc * sizeof(int32_t), cudaMemcpyHostToDevice, f->stream));
         EUT_TRY(launch_permute_out(f, stage, N, dc, f->d_cur, nc, f->stream));
         EUT_CUDA(cudaEventRecord(f->ev_dstage_ready[slot], f->stream));
         EUT_CUDA(cudaStreamWaitEvent(f->down_stream, f->ev_dstage_ready[slot], 0));
-        EUT_CUDA(cudaMemcpy2DAsync(host + (size_t)j0 * ld, ld * sizeof(double), stage,
-                                   N * sizeof(double), N * sizeof(double), nc,
-                                   cudaMemcpyDeviceToHost, f->down_stream));
-        EUT_CUDA(cudaEventRecord(f->ev_dstage_free[slot], f->down_stream));
+        if (host_is_pinned(host + (size_t)j0 * ld)) {
+            EUT_CUDA(cudaMemcpy2DAsync(host + (size_t)j0 * ld, ld * sizeof(double), stage,
+                                       N * sizeof(double), N * sizeof(double), nc,
+                                       cudaMemcpyDeviceToHost, f->down_stream));
+            EUT_CUDA(cudaEventRecord(f->ev_dstage_free[slot], f->down_stream));
+        } else {
+            // pageable result matrix: the field's downloader thread moves it slot by slot (hoststage.cu)
+            EUT_TRY(ensure_stager(f));
+            HostStager::DownJob job{stage, host + (size_t)j0 * ld, N, ld, N, nc, f->ev_dstage_ready[slot], f->down_stream, 0};
+            f->dn_ticket[slot] = f->stager->download(job);
+        }
         f->down_chunks = g + 1;
     }
     return EUT_OK;
@@ -181,6 +213,7 @@ int field_download_async(eut_field *f, double *host, int64_t ld, const int32_t *
 
 int field_sync_down(eut_field *f)
 {
+    if (f->stager) EUT_TRY(f->stager->wait_idle());
     EUT_CUDA(cudaStreamSynchronize(f->down_stream));
     return EUT_OK;
 }

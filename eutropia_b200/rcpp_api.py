@@ -40,12 +40,15 @@ def diffChange(adjmat, nneighbors, conc, niter, device: int = 0):
     return out
 
 
-def diffChangePar(adjmat, nneighbors, conc, niter, indvar, ncores=1, device: int = 0):
+def diffChangePar(adjmat, nneighbors, conc, niter, indvar, ncores=1, device: int = 0, devices=None):
     """`diffChangePar(adjmat, nneighbors, conc, niter, indvar, ncores)` -- src/diffChange.cpp:38-69.
 
     `niter` / `indvar` may be doubles (R passes `ceiling(...)` results, R/growthEnvironment.R:382):
     they are truncated like Rcpp's conversion to `arma::Col<int>` (src/RcppExports.cpp:37-38).
-    `ncores` is accepted and ignored."""
+    `ncores` is accepted and ignored.  `devices`: a list of CUDA ordinals (or "all") runs the call on
+    several GPUs at once through `eut_diffchange_par_multi` -- contiguous column blocks per GPU, one
+    result matrix -- the way the reference spreads the columns of one call over OpenMP threads
+    (src/diffChange.cpp:44-45)."""
     adj = np.require(np.asarray(adjmat).reshape(-1, 2), dtype=np.int32, requirements=["F", "A"])
     nn = np.require(np.asarray(nneighbors).reshape(-1, 2), dtype=np.int32, requirements=["F", "A"])
     c = _matrix(conc)
@@ -55,6 +58,12 @@ def diffChangePar(adjmat, nneighbors, conc, niter, indvar, ncores=1, device: int
         # niter(i) with i >= niter.size(): Armadillo's bounds check (src/diffChange.cpp:48)
         raise _lib.EutropiaIndexError(_lib.ERR_INDEX, "Mat::operator(): index out of bounds (niter)")
     out = np.empty(c.shape, dtype=np.float64, order="F")
+    if devices is not None:
+        dv = None if isinstance(devices, str) else np.ascontiguousarray(devices, dtype=np.int32)
+        check(_lib.lib().eut_diffchange_par_multi(ptr(adj), adj.shape[0], ptr(nn), nn.shape[0], ptr(c), c.shape[0],
+                                                  c.shape[1], ptr(nit), ptr(iv), iv.shape[0], int(ncores),
+                                                  ptr(out), ptr(dv), 0 if dv is None else dv.shape[0]))
+        return out
     check(_lib.lib().eut_diffchange_par(ptr(adj), adj.shape[0], ptr(nn), nn.shape[0], ptr(c), c.shape[0],
                                         c.shape[1], ptr(nit), ptr(iv), iv.shape[0], int(ncores),
                                         ptr(out), int(device)))

@@ -93,6 +93,31 @@ EUT_API int eut_diffchange_par(const int32_t *adjmat, int64_t n_edges,
                                const int32_t *niter, const int32_t *indvar, int64_t n_indvar,
                                int ncores, double *conc_out, int device);
 
+/* eut_diffchange_par_multi: the same call on SEVERAL GPUs of the box from ONE process -- the
+ * counterpart of the reference's `#pragma omp parallel for num_threads(ncores)` over the compounds
+ * of one call (src/diffChange.cpp:44-45), which diffuse_compoundsPar issues once per round from the
+ * main R process (R/growthEnvironment.R:385-390).  The active columns are dealt out to the devices
+ * in contiguous blocks of about equal substep counts; one host thread per device drives that
+ * device's column pipeline (H2D | substeps | D2H); the graph is analysed and uploaded once per
+ * device and recognised afterwards by an exact byte comparison with the copy kept on the host; all
+ * results land in the caller's single conc_out (columns that do not diffuse are copied through).
+ *   devices / n_devices    CUDA ordinals, unique; NULL / 0 = every visible device
+ * Host matrices may be pageable (what R hands over) or pinned: pageable memory is staged through
+ * pinned slot rings next to each GPU by copier threads (csrc/hoststage.h), pinned memory is read
+ * and written by the DMA engines directly. */
+EUT_API int eut_diffchange_par_multi(const int32_t *adjmat, int64_t n_edges,
+                                     const int32_t *nneighbors, int64_t n_nn,
+                                     const double *conc_in, int64_t n_rows, int64_t n_cols,
+                                     const int32_t *niter, const int32_t *indvar, int64_t n_indvar,
+                                     int ncores, double *conc_out, const int *devices, int n_devices);
+
+/* How eut_diffchange_par_multi deals the columns of a call out to n_devices devices (no CUDA call;
+ * for tests and for callers that want to place data): owner[i] = index into the device list that
+ * diffuses column indvar[i], -1 when niter[i] <= 0.  Blocks are contiguous in ascending column
+ * number, hold about equal substep counts, and none is empty while columns remain. */
+EUT_API int eut_deal_columns(const int32_t *niter, const int32_t *indvar, int64_t n_indvar,
+                             int n_devices, int32_t *owner);
+
 /* Drop the cached plans / staging buffers the one-shot tier keeps between calls. */
 EUT_API void eut_oneshot_reset(void);
 
