@@ -315,7 +315,7 @@ int eut_field_set_stream(eut_field *f, void *cuda_stream)
     return EUT_OK;
 }
 
-int64_t eut_field_launch_count(const eut_field *f) { return f ? f->launches : 0; }
+int64_t eut_field_launch_count(const eut_field *f) { return f ? f->launches.load() : (int64_t)0; }
 
 int eut_field_set_option(eut_field *f, const char *name, int64_t value)
 {

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <atomic>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -208,12 +209,11 @@ struct eut_field {
     // pageable caller memory: pinned slot rings + copier threads (hoststage.h), created on first use
     eut::HostStager *stager = nullptr;
     unsigned copy_threads = 0;         // threads per copier pool (0: from the host's thread budget)
-    uint64_t dn_ticket[2] = {0, 0};    // staged download job that last used each device staging slot
     cudaEvent_t ev_dstage_free[2] = {nullptr, nullptr};
     cudaEvent_t ev_dstage_ready[2] = {nullptr, nullptr};
     int64_t up_chunks = 0, down_chunks = 0;
     double *d_stats = nullptr;         // [3][C]
-    int64_t launches = 0;
+    std::atomic<int64_t> launches{0};  // also bumped by the staged downloader thread (hoststage.cu)
     // substep loops seen before, captured as CUDA graphs (key: substep counts + options)
     std::map<uint64_t, cudaGraphExec_t> graphs;
     std::set<uint64_t> graph_seen;

@@ -104,7 +104,7 @@ static int ensure_stager(eut_field *f)
     if (const char *e = getenv("EUT_COPY_THREADS")) t = (unsigned)std::max(1, atoi(e));
     if (t == 0) t = std::min(8u, std::max(1u, host_thread_budget() / 2));
     HostStager *st = new HostStager();
-    const int rc = st->init(f->plan->device, t);
+    const int rc = st->init(f, t);
     if (rc != EUT_OK) { delete st; return rc; }
     f->stager = st;
     return EUT_OK;
@@ -179,6 +179,20 @@ int field_download_async(eut_field *f, double *host, int64_t ld, const int32_t *
     }
     EUT_TRY(ensure_device(p->device));
     const int64_t N = p->N;
+    if (!host_is_pinned(host)) {
+        // pageable result matrix: the field's downloader thread (hoststage.cu) does the rest -- it waits,
+        // stream ordered, for what has been queued on the field's stream so far, un-permutes, copies slot
+        // by slot and drains the slots into `host`; this thread does not block
+        EUT_TRY(ensure_stager(f));
+        HostStager::DownJob job;
+        job.cols.resize(n_cols);
+        for (int64_t j = 0; j < n_cols; j++) job.cols[j] = cols ? cols[j] - 1 : (int32_t)j;
+        job.h_dst = host; job.dst_ld = ld;
+        EUT_CUDA(cudaEventCreateWithFlags(&job.after, cudaEventDisableTiming));
+        EUT_CUDA(cudaEventRecord(job.after, f->stream));
+        f->stager->download(std::move(job));
+        return EUT_OK;
+    }
     for (int64_t j0 = 0, g = f->down_chunks; j0 < n_cols; j0 += f->stage_cols, g++) {
         const int slot = (int)(g & 1);
         const int64_t nc = std::min(f->stage_cols, n_cols - j0);
@@ -187,25 +201,14 @@ int field_download_async(eut_field *f, double *host, int64_t ld, const int32_t *
         for (int64_t j = 0; j < nc; j++) hc[j] = cols ? cols[j0 + j] - 1 : (int32_t)(j0 + j);
         int32_t *dc = f->d_cols + (size_t)(2 + slot) * f->C;
         if (g >= 2) EUT_CUDA(cudaStreamWaitEvent(f->stream, f->ev_dstage_free[slot], 0));
-        if (f->dn_ticket[slot]) {                           // the slot's last user was a staged download
-            EUT_TRY(f->stager->wait_ticket(f->dn_ticket[slot]));
-            f->dn_ticket[slot] = 0;
-        }
         EUT_CUDA(cudaMemcpyAsync(dc, hc, nc * sizeof(int32_t), cudaMemcpyHostToDevice, f->stream));
         EUT_TRY(launch_permute_out(f, stage, N, dc, f->d_cur, nc, f->stream));
         EUT_CUDA(cudaEventRecord(f->ev_dstage_ready[slot], f->stream));
         EUT_CUDA(cudaStreamWaitEvent(f->down_stream, f->ev_dstage_ready[slot], 0));
-        if (host_is_pinned(host + (size_t)j0 * ld)) {
-            EUT_CUDA(cudaMemcpy2DAsync(host + (size_t)j0 * ld, ld * sizeof(double), stage,
-                                       N * sizeof(double), N * sizeof(double), nc,
-                                       cudaMemcpyDeviceToHost, f->down_stream));
-            EUT_CUDA(cudaEventRecord(f->ev_dstage_free[slot], f->down_stream));
-        } else {
-            // pageable result matrix: the field's downloader thread moves it slot by slot (hoststage.cu)
-            EUT_TRY(ensure_stager(f));
-            HostStager::DownJob job{stage, host + (size_t)j0 * ld, N, ld, N, nc, f->ev_dstage_ready[slot], f->down_stream, 0};
-            f->dn_ticket[slot] = f->stager->download(job);
-        }
+        EUT_CUDA(cudaMemcpy2DAsync(host + (size_t)j0 * ld, ld * sizeof(double), stage,
+                                   N * sizeof(double), N * sizeof(double), nc,
+                                   cudaMemcpyDeviceToHost, f->down_stream));
+        EUT_CUDA(cudaEventRecord(f->ev_dstage_free[slot], f->down_stream));
         f->down_chunks = g + 1;
     }
     return EUT_OK;

@@ -123,8 +123,10 @@ void CopyPool::copy(void *dst, const void *src, size_t bytes)
 }
 
 // ---- HostStager -------------------------------------------------------------------------------
-int HostStager::init(int dev, unsigned threads_per_pool)
+int HostStager::init(eut_field *fld, unsigned threads_per_pool)
 {
+    field = fld;
+    const int dev = fld->plan->device;
     device = dev;
     size_t mb = 8;
     if (const char *e = getenv("EUT_STAGE_SLOT_MB")) mb = (size_t)std::min(256, std::max(1, atoi(e)));
@@ -145,6 +147,9 @@ int HostStager::init(int dev, unsigned threads_per_pool)
     });
     alloc.join();
     if (rc != EUT_OK) { set_error("pinned staging slots: allocation failed (%s)", cudaGetErrorString(cudaGetLastError())); return rc; }
+    const size_t nc = (size_t)std::max<int64_t>(fld->C, 1);
+    EUT_CUDA(cudaMalloc((void **)&d_cols, 2 * nc * sizeof(int32_t)));
+    EUT_CUDA(cudaHostAlloc((void **)&h_cols, 2 * nc * sizeof(int32_t), cudaHostAllocDefault));
     fill = new CopyPool(threads_per_pool, cpus);
     drain = new CopyPool(threads_per_pool, cpus);
     downloader = std::thread([this, cpus] { bind_thread(cpus); run_downloader(); });
@@ -161,6 +166,8 @@ HostStager::~HostStager()
     delete fill;
     delete drain;
     cudaSetDevice(device);
+    cudaFree(d_cols);
+    if (h_cols) cudaFreeHost(h_cols);
     for (int i = 0; i < kSlots; i++) {
         if (up_slot[i]) cudaFreeHost(up_slot[i]);
         if (dn_slot[i]) cudaFreeHost(dn_slot[i]);
@@ -181,8 +188,11 @@ int HostStager::upload(double *d_dst, int64_t dst_ld, const double *h_src, int64
         for (size_t off = 0; off < span_bytes; off += slot_bytes) {
             const size_t n = std::min(slot_bytes, span_bytes - off);
             const int slot = (int)(up_count % kSlots);
+            const double t0 = now_ms();
             if (up_used[slot]) EUT_CUDA(cudaEventSynchronize(up_ev[slot]));     // the DMA that last read the slot is done
+            const double t1 = now_ms();
             fill->copy(up_slot[slot], s + off, n);
+            ms_up_wait += t1 - t0; ms_fill += now_ms() - t1;
             EUT_CUDA(cudaMemcpyAsync(d + off, up_slot[slot], n, cudaMemcpyHostToDevice, stream));
             EUT_CUDA(cudaEventRecord(up_ev[slot], stream));
             up_used[slot] = true;
@@ -192,14 +202,23 @@ int HostStager::upload(double *d_dst, int64_t dst_ld, const double *h_src, int64
     return EUT_OK;
 }
 
-uint64_t HostStager::download(const DownJob &job)
+std::string HostStager::take_stats()
+{
+    char b[200];
+    snprintf(b, sizeof(b), "fill %.2f ms (+%.2f waiting for a slot), drain %.2f ms (+%.2f waiting for the DMA), %u+%u copier threads",
+             ms_fill, ms_up_wait, ms_drain, ms_dn_wait, fill ? fill->size() : 0, drain ? drain->size() : 0);
+    ms_fill = ms_up_wait = ms_drain = ms_dn_wait = 0;
+    return b;
+}
+
+uint64_t HostStager::download(DownJob &&job)
 {
     std::lock_guard<std::mutex> l(mu);
-    DownJob j = job;
-    j.ticket = ++issued;
-    queue.push_back(j);
+    job.ticket = ++issued;
+    const uint64_t t = job.ticket;
+    queue.push_back(std::move(job));
     cv.notify_all();
-    return j.ticket;
+    return t;
 }
 
 int HostStager::wait_ticket(uint64_t ticket)
@@ -227,37 +246,60 @@ void HostStager::run_downloader()
             std::unique_lock<std::mutex> l(mu);
             cv.wait(l, [this] { return stop || !queue.empty(); });
             if (queue.empty()) return;
-            j = queue.front();
+            j = std::move(queue.front());
             queue.pop_front();
         }
         auto fail = [&](cudaError_t e, const char *what) {
             std::lock_guard<std::mutex> l(mu);
             if (!err) { err = EUT_ERR_CUDA; err_msg = std::string("staged download: ") + what + ": " + cudaGetErrorString(e); }
         };
-        const bool dense = (j.src_ld == j.rows && j.dst_ld == j.rows);
-        const int64_t spans = dense ? 1 : j.cols;
-        const size_t span_bytes = (size_t)(dense ? j.rows * j.cols : j.rows) * sizeof(double);
+        eut_field *f = field;
+        cudaStream_t stream = f->down_stream;
+        const int64_t N = f->plan->N, C = std::max<int64_t>(f->C, 1);
+        cudaError_t e = cudaStreamWaitEvent(stream, j.after, 0);          // the substeps of these columns are done
+        if (e != cudaSuccess) fail(e, "cudaStreamWaitEvent");
+        cudaEventDestroy(j.after);
         struct Flight { int slot; char *dst; size_t n; };
         std::deque<Flight> flight;
         uint64_t piece = 0;
         auto retire = [&]() {
-            const Flight f = flight.front();
+            const Flight fl = flight.front();
             flight.pop_front();
-            const cudaError_t e = cudaEventSynchronize(dn_ev[f.slot]);
-            if (e != cudaSuccess) { fail(e, "cudaEventSynchronize"); return; }
-            drain->copy(f.dst, dn_slot[f.slot], f.n);
+            const double t0 = now_ms();
+            const cudaError_t e2 = cudaEventSynchronize(dn_ev[fl.slot]);
+            if (e2 != cudaSuccess) { fail(e2, "cudaEventSynchronize"); return; }
+            const double t1 = now_ms();
+            drain->copy(fl.dst, dn_slot[fl.slot], fl.n);
+            ms_dn_wait += t1 - t0; ms_drain += now_ms() - t1;
         };
-        for (int64_t sp = 0; sp < spans; sp++) {
-            const char *s = (const char *)(j.d_src + sp * j.src_ld);
-            char *d = (char *)(j.h_dst + sp * j.dst_ld);
-            for (size_t off = 0; off < span_bytes; off += slot_bytes) {
-                const size_t n = std::min(slot_bytes, span_bytes - off);
-                if ((int)flight.size() >= kSlots - 1) retire();        // keep a few DMAs queued while one slot drains
-                const int slot = (int)(piece++ % kSlots);
-                cudaError_t e = cudaMemcpyAsync(dn_slot[slot], s + off, n, cudaMemcpyDeviceToHost, j.stream);
-                if (e == cudaSuccess) e = cudaEventRecord(dn_ev[slot], j.stream);
-                if (e != cudaSuccess) { fail(e, "cudaMemcpyAsync"); continue; }
-                flight.push_back(Flight{slot, d + off, n});
+        const int64_t n_cols = (int64_t)j.cols.size();
+        for (int64_t j0 = 0; j0 < n_cols; j0 += f->stage_cols) {
+            // un-permute up to stage_cols columns into one half of the device staging area; the kernel and
+            // the copies out of the area are all on the download stream, so a half is never rewritten
+            // before the copies that read it have completed
+            const int64_t nc = std::min(f->stage_cols, n_cols - j0);
+            const int half = (int)(dn_chunks++ & 1);
+            double *stage = f->d_stage2 + (size_t)half * f->stage_cols * N;
+            int32_t *hc = h_cols + (size_t)half * C, *dc = d_cols + (size_t)half * C;
+            for (int64_t k = 0; k < nc; k++) hc[k] = j.cols[j0 + k];
+            e = cudaMemcpyAsync(dc, hc, nc * sizeof(int32_t), cudaMemcpyHostToDevice, stream);
+            if (e != cudaSuccess) { fail(e, "cudaMemcpyAsync"); break; }
+            if (launch_permute_out(f, stage, N, dc, f->d_cur, nc, stream) != EUT_OK) { fail(cudaGetLastError(), "un-permute launch"); break; }
+            const bool dense = (j.dst_ld == N);
+            const int64_t spans = dense ? 1 : nc;
+            const size_t span_bytes = (size_t)(dense ? N * nc : N) * sizeof(double);
+            for (int64_t sp = 0; sp < spans; sp++) {
+                const char *s = (const char *)(stage + sp * N);
+                char *d = (char *)(j.h_dst + (j0 + sp) * j.dst_ld);
+                for (size_t off = 0; off < span_bytes; off += slot_bytes) {
+                    const size_t n = std::min(slot_bytes, span_bytes - off);
+                    if ((int)flight.size() >= kSlots - 1) retire();        // keep a few DMAs queued while one slot drains
+                    const int slot = (int)(piece++ % kSlots);
+                    e = cudaMemcpyAsync(dn_slot[slot], s + off, n, cudaMemcpyDeviceToHost, stream);
+                    if (e == cudaSuccess) e = cudaEventRecord(dn_ev[slot], stream);
+                    if (e != cudaSuccess) { fail(e, "cudaMemcpyAsync"); continue; }
+                    flight.push_back(Flight{slot, d + off, n});
+                }
             }
         }
         while (!flight.empty()) retire();

@@ -5,8 +5,11 @@
 // itself: a ring of pinned slots per direction and device, filled / drained by a few copier threads
 // with non-temporal stores, the DMA of one slot overlapping the memcpy of the next.
 //   up:   caller thread: [wait slot] -> parallel memcpy(src -> slot) -> cudaMemcpyAsync(slot -> device)
-//   down: a downloader thread per field: waits for the staged result, then per slot
-//         cudaMemcpyAsync(device -> slot) -> [event] -> parallel memcpy(slot -> dst), double buffered
+//   down: a downloader thread per field takes whole download requests off the caller's hands: it waits
+//         (stream ordered) for the substeps of the columns, un-permutes them into the device staging
+//         area, then per slot cudaMemcpyAsync(device -> slot) -> [event] -> parallel memcpy(slot -> dst).
+//         The caller thread never blocks on a download, so the substep launches of the next chunk and the
+//         fills of the one after are not held up by results that are not ready yet.
 // Pinned (cudaHostAlloc / cudaHostRegister) caller memory keeps the direct path.
 #pragma once
 #include <cuda_runtime.h>
@@ -20,6 +23,8 @@
 #include <string>
 #include <thread>
 #include <vector>
+
+struct eut_field;
 
 namespace eut {
 
@@ -70,13 +75,15 @@ struct HostStager {
     CopyPool *fill = nullptr, *drain = nullptr;
     // downloader
     struct DownJob {
-        const double *d_src;      // staged columns on the device (column stride src_ld)
-        double *h_dst;
-        int64_t src_ld, dst_ld, rows, cols;
-        cudaEvent_t ready;        // recorded by the caller after the staging kernel
-        cudaStream_t stream;      // copy stream of the downloads
-        uint64_t ticket;
+        std::vector<int32_t> cols;   // field columns (0-based); host column j of h_dst receives cols[j]
+        double *h_dst = nullptr;
+        int64_t dst_ld = 0;
+        cudaEvent_t after = nullptr; // recorded by the caller on the stream that produced the columns; owned by the job
+        uint64_t ticket = 0;
     };
+    struct ::eut_field *field = nullptr;
+    int32_t *d_cols = nullptr, *h_cols = nullptr;   // [2][C] column lists of the un-permute launches (device / pinned)
+    uint64_t dn_chunks = 0;
     std::thread downloader;
     std::mutex mu;
     std::condition_variable cv, idle_cv;
@@ -85,14 +92,18 @@ struct HostStager {
     bool stop = false;
     int err = 0;
     std::string err_msg;
+    // trace counters (milliseconds since the last take_stats): caller thread blocked in fills / slot waits,
+    // downloader blocked in drains / DMA waits
+    double ms_fill = 0, ms_up_wait = 0, ms_drain = 0, ms_dn_wait = 0;
+    std::string take_stats();
 
-    int init(int device, unsigned threads_per_pool);
+    int init(struct ::eut_field *field, unsigned threads_per_pool);
     ~HostStager();
     // host (pageable) -> device, stream ordered on `stream`; returns after the last slice has been queued
     int upload(double *d_dst, int64_t dst_ld, const double *h_src, int64_t src_ld, int64_t rows, int64_t cols,
                cudaStream_t stream);
     // queue a device -> host (pageable) job; returns at once with a ticket
-    uint64_t download(const DownJob &job);
+    uint64_t download(DownJob &&job);
     int wait_ticket(uint64_t ticket);   // blocks until that job has landed in the caller's memory
     int wait_idle();
 

@@ -329,7 +329,8 @@ int oneshot_run(const int32_t *adj, int64_t n_edges, const int32_t *nn, int64_t 
         for (int e = 0; e < d; e++)
             if (devices[e] == devices[d]) { set_error("one-shot call: device %d listed twice", devices[d]); return EUT_ERR_ARG; }
     }
-    static const bool trace = getenv("EUT_TRACE") != nullptr;
+    const char *trace_env = getenv("EUT_TRACE");
+    const bool trace = trace_env && *trace_env;
     const double t_begin = now_ms();
     // active columns (validated before any work is queued), ascending column number
     std::vector<int64_t> act;
@@ -423,7 +424,9 @@ int oneshot_run(const int32_t *adj, int64_t n_edges, const int32_t *nn, int64_t 
             EUT_CUDA(cudaStreamSynchronize(f->copy_stream));
             EUT_CUDA(cudaStreamSynchronize(f->stream));
             if (f->lane[0]) EUT_CUDA(cudaStreamSynchronize(f->lane[0]));
-            return field_sync_down(f);
+            EUT_TRY(field_sync_down(f));
+            if (trace && f->stager) fprintf(stderr, "[eut] one-shot, device %d, staged transfers: %s\n", job.device, f->stager->take_stats().c_str());
+            return EUT_OK;
         };
         job.rc = body();
         if (job.rc != EUT_OK) job.err = last_error_cstr();
