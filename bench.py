@@ -462,8 +462,10 @@ def run_ours(args):
         else:
             e2e_ranks = {"value": ranks_value, "unit": UNIT, "api": f"{world} processes, each eut_diffchange_par on its own GPU and columns (max over ranks)"}
             del pin_out
-            # (b) one process, all GPUs
+            # (b) one process, all GPUs (the other ranks idle: this process may use the whole host for its
+            # copier pools, as an R session would)
             if rank == 0:
+                os.environ.pop("LOCAL_WORLD_SIZE", None)
                 ct = cpg * world
                 big_in = torch.empty((ct, n), dtype=torch.float64).pin_memory()
                 for r in range(world):

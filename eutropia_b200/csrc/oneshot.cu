@@ -373,9 +373,11 @@ int oneshot_run(const int32_t *adj, int64_t n_edges, const int32_t *nn, int64_t 
                 c->n_rows == n_rows && c->stamp >= best) { best = c->stamp; guess = c->key; }
     }
     const bool speculate = guess && !getenv("EUT_NO_SPECULATION");
+    double compare_ms = 0;
     std::shared_future<std::shared_ptr<GraphKey>> final_key;
     if (!jobs.empty()) {
         final_key = std::async(std::launch::async, [&, guess]() -> std::shared_ptr<GraphKey> {
+            struct Stamp { double &ms, t0; ~Stamp() { ms = now_ms() - t0; } } stamp{compare_ms, now_ms()};
             if (guess && same_graph(*guess, adj, n_edges, nn, n_nn)) return guess;
             std::vector<std::shared_ptr<GraphKey>> seen;
             {
@@ -421,10 +423,16 @@ int oneshot_run(const int32_t *adj, int64_t n_edges, const int32_t *nn, int64_t 
                 cp->stamp = ++g_stamp;
                 cp->last_adj = adj; cp->last_nn = nn;
             }
+            const double t_enq = now_ms();
             EUT_CUDA(cudaStreamSynchronize(f->copy_stream));
+            const double t_up = now_ms();
             EUT_CUDA(cudaStreamSynchronize(f->stream));
             if (f->lane[0]) EUT_CUDA(cudaStreamSynchronize(f->lane[0]));
+            const double t_comp = now_ms();
             EUT_TRY(field_sync_down(f));
+            if (trace)
+                fprintf(stderr, "[eut] one-shot, device %d: all queued at %.2f ms, uploads done %.2f, substeps done %.2f, results home %.2f\n",
+                        job.device, t_enq - t_begin, t_up - t_begin, t_comp - t_begin, now_ms() - t_begin);
             if (trace && f->stager) fprintf(stderr, "[eut] one-shot, device %d, staged transfers: %s\n", job.device, f->stager->take_stats().c_str());
             return EUT_OK;
         };
@@ -447,7 +455,7 @@ int oneshot_run(const int32_t *adj, int64_t n_edges, const int32_t *nn, int64_t 
     if (final_key.valid()) final_key.wait();                 // error paths: never leave the thread behind
     for (auto &j : jobs)
         if (j.rc != EUT_OK) { set_error("device %d: %s", j.device, j.err.c_str()); return j.rc; }
-    if (trace) fprintf(stderr, "[eut] one-shot: %zu device(s), %zu active columns, %.2f ms\n", jobs.size(), act.size(), now_ms() - t_begin);
+    if (trace) fprintf(stderr, "[eut] one-shot: %zu device(s), %zu active columns, %.2f ms (graph comparison %.2f ms, %u threads)\n", jobs.size(), act.size(), now_ms() - t_begin, compare_ms, std::min(16u, host_thread_budget()));
     return EUT_OK;
 }
 
