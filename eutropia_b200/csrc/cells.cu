@@ -81,6 +81,23 @@ struct eut_cells {
     uint8_t *d_const = nullptr;
     int64_t const_cap = 0;
     int64_t launches = 0;
+    // scatter, third generation: the transposed lists packed for a point-per-lane walk
+    int32_t *d_t_cell = nullptr;     // [T] cell of every transposed entry
+    double2 *d_t_af = nullptr;       // [T] (acc.prop, (dmax - dist) / fsum) of every transposed entry
+    int64_t tpack_cap = 0;
+    bool t_packed = false;
+    int32_t *d_ex_ptr32 = nullptr;   // [M+1]
+    double2 *d_exrec = nullptr;      // [X] per exchange: factor | code (column, production bit; < 0: skip)
+    int64_t exrec_cap = 0, exptr32_cap = 0;
+    // the gather's per-cell sums are the colSums the next scatter divides by (R/run_simulation.R:696 takes
+    // them from the same fmolPerField matrix): remembered with the state of the field they were taken from
+    const eut_field *fmol_field = nullptr;
+    uint64_t fmol_version = 0;
+    double fmol_vol = 0;
+    // the exchange lists of a scatter call travel on the field's copy stream, next to whatever the
+    // compute stream still has queued (the substeps of the previous round)
+    cudaEvent_t ev_ex_ready = nullptr, ev_ex_free = nullptr;
+    bool ex_in_use = false;
 };
 
 namespace eut {
@@ -164,6 +181,8 @@ static int alloc_entries(eut_cells *c, int64_t M, int64_t T)
     c->T = T;
     c->transposed = false;
     c->g_sorted = false;
+    c->t_packed = false;
+    c->fmol_field = nullptr;
     return EUT_OK;
 }
 
@@ -742,6 +761,179 @@ k_scatter_t(double *__restrict__ buf, const int64_t col_stride, const int64_t bu
     }
 }
 
+// ---- scatter, third generation ----------------------------------------------------------------------
+// The second generation walks a field point's incident cells with lanes = columns: of the 64 column
+// slots a cell visit spends instructions on, only the ~10 the cell exchanges do anything (583 M warp
+// instructions, 12 % of the HBM rate: profiles/r01_cells_v3_ncu.csv), and every visit is a chain of
+// dependent loads t_entry -> ecell -> mask -> factor row.
+// Here FOUR LANES own a field point and a warp 8 consecutive touched points.  The warp first stages its
+// 8 x COLS tile of the field in shared memory, then the lanes of a point walk ITS incident cells in
+// cell order -- cell, acc.prop and the production share come
+// packed in transposed order (k_t_pack, once per cell map) -- and, per cell, the cell's own compact
+// exchange list: one 16-byte record per exchange (factor, column, kind), i.e. only the columns the cell
+// exchanges.  Contributions are added into a per-point, per-column accumulator in shared memory
+// (column-major, bank = lane: conflict free).  Same terms, same cell order per (field, compound) sum
+// as before -- bit-identical results -- for a tenth of the instructions.  Finally NaN -> 0, add, clamp
+// on the touched entries (R/run_simulation.R:315-319) and a coalesced write of the touched rows.
+__global__ void __launch_bounds__(256)
+k_t_pack(const int32_t *__restrict__ t_entry, const int32_t *__restrict__ ecell, const double *__restrict__ acc,
+         const double *__restrict__ dist, const double *__restrict__ dmax, const double *__restrict__ fsum,
+         int32_t *__restrict__ t_cell, double2 *__restrict__ t_af, const int64_t n)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int k = t_entry[r];
+    const int i = ecell[k];
+    t_cell[r] = i;
+    t_af[r] = make_double2(acc[k], __ddiv_rn(__dsub_rn(dmax[i], dist[k]), fsum[i]));   // :729-730
+}
+
+// exchange records: factor (k_ex_colsum) | column (0-based), bit 30 = production; -1 = no contribution
+__global__ void __launch_bounds__(256)
+k_ex_pack(const int64_t *__restrict__ ex_ptr, const int32_t *__restrict__ ex_cpd, const double *__restrict__ ex_flx,
+          const double *__restrict__ ex_cs, int32_t *__restrict__ ex_ptr32, double2 *__restrict__ exrec,
+          const int n_cells, const int n_cols)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n_cells) return;
+    ex_ptr32[i] = (int32_t)ex_ptr[i];
+    if (i == n_cells) return;
+    for (int64_t e = ex_ptr[i]; e < ex_ptr[i + 1]; e++) {
+        const int c = ex_cpd[e] - 1;
+        const double ex = ex_flx[e];
+        long long code = -1;
+        if (c >= 0 && c < n_cols && ex != 0.0 && ex == ex) code = (long long)c | (ex < 0 ? 0ll : (1ll << 30));
+        exrec[e] = make_double2(ex_cs[e], __longlong_as_double(code));
+    }
+}
+
+// L = 4 lanes share a field point (lane j takes the exchanges j, j + 4, ... of the visited cell: a cell
+// lists a compound at most once, so the lanes of a point never meet in a column), a warp owns 8 touched
+// points and a CTA of 4 warps 32: 8 KB of shared memory per warp, 24 warps per SM.
+template <int COLS>
+__global__ void __launch_bounds__(128)
+k_scatter_p(double *__restrict__ buf, const int64_t col_stride, const int64_t buf_stride,
+            const int32_t *__restrict__ cur, const int32_t *__restrict__ seg_start,
+            const int32_t *__restrict__ seg_fq, const int32_t *__restrict__ t_cell,
+            const double2 *__restrict__ t_af, const int32_t *__restrict__ ex_ptr32,
+            const double2 *__restrict__ exrec, const uint8_t *__restrict__ is_const, const int n_seg,
+            const int c0, const int n_cols)
+{
+    constexpr int L = 4, P = 8, G = 3;                       // lanes per point, points per warp, exchanges in flight per lane
+    constexpr int ROWS = COLS + 1;                           // row COLS: dummy column for exchanges this pass skips
+    extern __shared__ __align__(16) double s_tile[];         // per warp [2][ROWS][P]: field values, sums
+    __shared__ long long s_base[COLS];                       // offset of column c0 + c inside buf (current buffer)
+    const unsigned full = 0xffffffffu;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = lane >> 2, j = lane & 3;
+    double *cv = s_tile + (size_t)warp * 2 * ROWS * P, *sum = cv + ROWS * P;
+    const int nc = min(COLS, n_cols - c0);
+    for (int c = threadIdx.x; c < COLS; c += blockDim.x)
+        s_base[c] = c < nc ? (long long)cur[c0 + c] * buf_stride + (long long)(c0 + c) * col_stride : 0ll;
+    __syncthreads();
+    const int t = (blockIdx.x * 4 + warp) * P + p;
+    const bool valid = t < n_seg;
+    const int q = valid ? seg_fq[t] : 0;
+    // tile cell of (column c, point p): the four lanes of a point work on different columns at the same
+    // time; the xor spreads them over the banks (c * 8 + p alone puts all even columns of a point on one bank pair)
+    auto cell = [](int c, int pp) { return c * P + (pp ^ ((c >> 1) & 7)); };
+    // tile: lane (p, j) loads the columns j, j + 4, ...
+#pragma unroll 4
+    for (int c = j; c < ROWS; c += L) {
+        double v = 0.0;
+        if (valid && c < nc) v = buf[s_base[c] + q];
+        cv[cell(c, p)] = v;
+        sum[cell(c, p)] = 0.0;
+    }
+    unsigned long long hit = 0ull;
+    const int r0 = valid ? seg_start[t] : 0, n_vis = valid ? seg_start[t + 1] - r0 : 0;
+    const int max_vis = __reduce_max_sync(full, n_vis);
+    // Software pipeline over the visits (the loads of a visit form a chain cell -> list bounds -> exchange
+    // records, and a warp issues in order): iteration v works on visit v with everything in registers, and
+    // issues the records of v + 1, the bounds of v + 2, the cell and weights of v + 3.
+    const double2 none = make_double2(0.0, __longlong_as_double(-1ll));
+    int i3 = 0, e0_2 = 0, e1_2 = 0, e0_1 = 0, e1_1 = 0;
+    double2 af3 = make_double2(0.0, 0.0), af2 = af3, af1 = af3, rec1[G];
+#pragma unroll
+    for (int u = 0; u < G; u++) rec1[u] = none;
+    auto stage1 = [&](int v) { if (v < n_vis) { i3 = __ldg(t_cell + r0 + v); af3 = __ldg(t_af + r0 + v); } };
+    auto stage2 = [&](int v) { if (v < n_vis) { e0_2 = __ldg(ex_ptr32 + i3); e1_2 = __ldg(ex_ptr32 + i3 + 1); af2 = af3; } };
+    auto stage3 = [&](int v) {
+        e0_1 = e0_2; e1_1 = (v < n_vis) ? e1_2 : e0_2; af1 = af2;
+#pragma unroll
+        for (int u = 0; u < G; u++) rec1[u] = (e0_1 + j + u * L < e1_1) ? __ldg(exrec + e0_1 + j + u * L) : none;
+    };
+    stage1(0); stage2(0); stage1(1); stage3(0); stage2(1); stage1(2);
+    __syncwarp();
+    for (int v = 0; v < max_vis; v++) {
+        const double2 af = af1;
+        const int e0 = e0_1, e1 = e1_1;
+        double2 rec[G];
+#pragma unroll
+        for (int u = 0; u < G; u++) rec[u] = rec1[u];
+        stage3(v + 1); stage2(v + 2); stage1(v + 3);
+        for (int eb = e0 + j; eb < e1; eb += L * G) {
+            if (eb != e0 + j) {                              // lists longer than L * G exchanges: not pipelined
+#pragma unroll
+                for (int u = 0; u < G; u++) rec[u] = (eb + u * L < e1) ? __ldg(exrec + eb + u * L) : none;
+            }
+            // a cell lists a compound at most once (checked on the host): the G accumulators of one group, and
+            // those of the other lanes of the point, are different cells of the tile -- independent chains
+            int a[G];
+            double sv[G], cvv[G];
+            bool prod[G];
+#pragma unroll
+            for (int u = 0; u < G; u++) {
+                const long long code = __double_as_longlong(rec[u].y);
+                int c = (int)(code & 0x3fffffffll) - c0;
+                const bool ok = code >= 0 && (unsigned)c < (unsigned)nc;
+                if (!ok) c = COLS;
+                prod[u] = (code & (1ll << 30)) != 0;
+                a[u] = cell(c, p);
+                if (ok) hit |= 1ull << c;
+            }
+#pragma unroll
+            for (int u = 0; u < G; u++) { sv[u] = sum[a[u]]; cvv[u] = cv[a[u]]; }
+#pragma unroll
+            for (int u = 0; u < G; u++) {
+                const double d = prod[u] ? __dmul_rn(af.y, rec[u].x)                          // production, :732-734
+                                         : __dmul_rn(__dmul_rn(cvv[u], af.x), rec[u].x);      // uptake, :696, :707-708
+                if (a[u] < COLS * P) sum[a[u]] = __dadd_rn(sv[u], d);
+            }
+        }
+        __syncwarp();                                        // the next cell may touch a column another lane just wrote
+    }
+    hit |= __shfl_xor_sync(full, hit, 1);
+    hit |= __shfl_xor_sync(full, hit, 2);
+    if (!valid) return;
+    for (int c = j; c < nc; c += L) {
+        if (!((hit >> c) & 1ull)) continue;
+        if (is_const && is_const[c0 + c]) continue;                      // :311-312
+        double d = sum[cell(c, p)];
+        if (d != d) d = 0.0;                                             // :315
+        double v = __dadd_rn(cv[cell(c, p)], d);                         // :318
+        if (v < 1e-12) v = 0.0;                                          // :319
+        buf[s_base[c] + q] = v;
+    }
+}
+
+// colSums from the gather that ran on this very state of the field: g per exchange without touching the field
+__global__ void __launch_bounds__(256)
+k_ex_factor(const double *__restrict__ fmol, const int64_t *__restrict__ ex_ptr, const int32_t *__restrict__ ex_cpd,
+            const double *__restrict__ ex_flx, double *__restrict__ ex_cs, const int n_cells, const double field_vol,
+            const double vol_l)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cells) return;
+    for (int64_t e = ex_ptr[i]; e < ex_ptr[i + 1]; e++) {
+        const double ex = ex_flx[e];
+        if (!(ex < 0)) { ex_cs[e] = __ddiv_rn(__ddiv_rn(ex, 1e12), vol_l); continue; }
+        const double cs = fmol[(int64_t)(ex_cpd[e] - 1) * n_cells + i];
+        const double g = __ddiv_rn(__ddiv_rn(__ddiv_rn(ex, cs), 1e12), vol_l);
+        ex_cs[e] = __ddiv_rn(__dmul_rn(g, field_vol), 1000.0);
+    }
+}
+
 // ---- chemotaxis moments (R/run_simulation.R:260-291) -------------------------------------------------
 // Per cell and chemotaxis compound the reference takes, over the cell's field list, the weighted mean of
 // the normalised offsets (dx, dy) = (field.xy - cell.xy) / (size/2 + scavengeDist) with weights
@@ -896,6 +1088,9 @@ int eut_cells_destroy(eut_cells *c)
     cudaFree(c->d_fmol); cudaFree(c->d_tfield); cudaFree(c->d_exd); cudaFree(c->d_exmask);
     cudaFree(c->d_pxy); cudaFree(c->d_mom); cudaFree(c->d_cxy); cudaFree(c->d_ex_ptr); cudaFree(c->d_ex_cpd); cudaFree(c->d_ex_flx);
     cudaFree(c->d_ex_cs); cudaFree(c->d_const); cudaFree(c->d_g_idx); cudaFree(c->d_cell_order);
+    cudaFree(c->d_t_cell); cudaFree(c->d_t_af); cudaFree(c->d_ex_ptr32); cudaFree(c->d_exrec);
+    if (c->ev_ex_ready) cudaEventDestroy(c->ev_ex_ready);
+    if (c->ev_ex_free) cudaEventDestroy(c->ev_ex_free);
     delete c;
     return EUT_OK;
 }
@@ -1026,6 +1221,8 @@ int eut_cells_claim_rescale(eut_cells *c)
     EUT_TRY(ensure_device(c->plan->device));
     cudaStream_t s = 0;
     EUT_TRY(build_transposed(c, s));
+    c->t_packed = false;                 // acc.prop changes below
+    c->fmol_field = nullptr;
     if (c->n_seg > 0) {
         k_claim<<<(unsigned)((c->n_seg + 255) / 256), 256, 0, s>>>(c->d_seg_start, c->d_t_entry, c->d_acc, (int)c->n_seg);
         c->launches++;
@@ -1086,6 +1283,7 @@ int eut_cells_gather(eut_cells *c, eut_field *f, double field_vol, double *fmol_
         f->launches += 2;
     }
     EUT_CUDA(cudaGetLastError());
+    c->fmol_field = f; c->fmol_version = f->version; c->fmol_vol = field_vol;
     if (fmol_host) {
         EUT_CUDA(cudaMemcpyAsync(fmol_host, c->d_fmol, n * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
         EUT_CUDA(cudaStreamSynchronize(f->stream));
@@ -1168,23 +1366,86 @@ int eut_cells_scatter(eut_cells *c, eut_field *f, double field_vol, const uint8_
         EUT_CUDA(cudaMalloc((void **)&c->d_ex_cs, n * sizeof(double)));
         c->ex_cap = n;
     }
-    EUT_CUDA(cudaMemcpyAsync(c->d_ex_ptr, ex_ptr, (M + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-    EUT_CUDA(cudaMemcpyAsync(c->d_ex_cpd, ex_cpd, X * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    EUT_CUDA(cudaMemcpyAsync(c->d_ex_flx, ex_flx, X * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (!c->ev_ex_ready) {
+        EUT_CUDA(cudaEventCreateWithFlags(&c->ev_ex_ready, cudaEventDisableTiming));
+        EUT_CUDA(cudaEventCreateWithFlags(&c->ev_ex_free, cudaEventDisableTiming));
+    }
+    cudaStream_t up = f->copy_stream;
+    if (c->ex_in_use) EUT_CUDA(cudaStreamWaitEvent(up, c->ev_ex_free, 0));      // the previous scatter has read its lists
+    EUT_CUDA(cudaMemcpyAsync(c->d_ex_ptr, ex_ptr, (M + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, up));
+    EUT_CUDA(cudaMemcpyAsync(c->d_ex_cpd, ex_cpd, X * sizeof(int32_t), cudaMemcpyHostToDevice, up));
+    EUT_CUDA(cudaMemcpyAsync(c->d_ex_flx, ex_flx, X * sizeof(double), cudaMemcpyHostToDevice, up));
     const uint8_t *d_const = nullptr;
     if (is_constant) {
         EUT_TRY(grow(&c->d_const, &c->const_cap, f->C));
-        EUT_CUDA(cudaMemcpyAsync(c->d_const, is_constant, f->C, cudaMemcpyHostToDevice, s));
+        EUT_CUDA(cudaMemcpyAsync(c->d_const, is_constant, f->C, cudaMemcpyHostToDevice, up));
         d_const = c->d_const;
     }
+    EUT_CUDA(cudaEventRecord(c->ev_ex_ready, up));
+    EUT_CUDA(cudaStreamWaitEvent(s, c->ev_ex_ready, 0));
+    struct Release {                                         // whatever path the kernels take below
+        eut_cells *c; cudaStream_t s;
+        ~Release() { cudaEventRecord(c->ev_ex_free, s); c->ex_in_use = true; }
+    } release{c, s};
     const int64_t bs = f->C * c->plan->Np;
-    k_ex_colsum<<<(unsigned)((M * 32 + 255) / 256), 256, 0, s>>>(f->d_buf, c->plan->Np, bs, f->d_cur, c->d_cell_ptr,
-                                                                c->d_fq, c->d_acc, field_vol, c->d_ex_ptr,
-                                                                c->d_ex_cpd, c->d_ex_flx, c->d_ex_cs, (int)M,
-                                                                field_vol / 1e15);
+    // generation of the scatter kernels (EUT_SCATTER_GEN=1 / 2: the earlier ones, kept as cross-checks)
+    int gen = 3;
+    if (const char *e = getenv("EUT_SCATTER_GEN")) gen = std::min(3, std::max(1, atoi(e)));
+    if (getenv("EUT_SCATTER_V1")) gen = 1;
+    if (X >= INT32_MAX) gen = std::min(gen, 2);
+    // colSums(fmolPerField) per uptake (R/run_simulation.R:696): when the last gather of these cells ran on
+    // exactly this state of the field, its per-cell sums ARE those colSums (the reference takes both from
+    // the same fmolPerField matrix, R/scavenge_compounds.R:17-22) -- no second pass over the field
+    const bool reuse = gen == 3 && c->fmol_field == f && c->fmol_version == f->version && c->fmol_vol == field_vol &&
+                       c->d_fmol && !getenv("EUT_SCATTER_COLSUM");
+    if (reuse)
+        k_ex_factor<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(c->d_fmol, c->d_ex_ptr, c->d_ex_cpd, c->d_ex_flx, c->d_ex_cs, (int)M,
+                                                              field_vol, field_vol / 1e15);
+    else
+        k_ex_colsum<<<(unsigned)((M * 32 + 255) / 256), 256, 0, s>>>(f->d_buf, c->plan->Np, bs, f->d_cur, c->d_cell_ptr,
+                                                                    c->d_fq, c->d_acc, field_vol, c->d_ex_ptr,
+                                                                    c->d_ex_cpd, c->d_ex_flx, c->d_ex_cs, (int)M,
+                                                                    field_vol / 1e15);
     f->launches++;
-    static const bool old_scatter = getenv("EUT_SCATTER_V1") != nullptr;
-    if (!old_scatter) {
+    f->version++;
+    c->fmol_field = nullptr;
+    if (gen == 3) {
+        if (!c->t_packed) {
+            if (c->T > c->tpack_cap || !c->d_t_cell) {
+                cudaFree(c->d_t_cell); cudaFree(c->d_t_af);
+                c->d_t_cell = nullptr; c->d_t_af = nullptr;
+                const int64_t n = c->T + c->T / 8 + 16;
+                EUT_CUDA(cudaMalloc((void **)&c->d_t_cell, n * sizeof(int32_t)));
+                EUT_CUDA(cudaMalloc((void **)&c->d_t_af, n * sizeof(double2)));
+                c->tpack_cap = n;
+            }
+            k_t_pack<<<(unsigned)((c->T + 255) / 256), 256, 0, s>>>(c->d_t_entry, c->d_ecell, c->d_acc, c->d_dist, c->d_dmax, c->d_fsum,
+                                                                   c->d_t_cell, c->d_t_af, c->T);
+            f->launches++;
+            c->t_packed = true;
+        }
+        EUT_TRY(grow(&c->d_ex_ptr32, &c->exptr32_cap, M + 1));
+        EUT_TRY(grow(&c->d_exrec, &c->exrec_cap, X));
+        k_ex_pack<<<(unsigned)((M + 1 + 255) / 256), 256, 0, s>>>(c->d_ex_ptr, c->d_ex_cpd, c->d_ex_flx, c->d_ex_cs, c->d_ex_ptr32,
+                                                                 c->d_exrec, (int)M, (int)f->C);
+        f->launches++;
+        const unsigned nb = (unsigned)((c->n_seg + 31) / 32);              // 4 warps x 8 points per CTA
+        for (int c0 = 0; c0 < f->C; c0 += 64) {
+            const int left = (int)f->C - c0;
+#define EUT_SCATTER_P(COLS)                                                                                              \
+    k_scatter_p<COLS><<<nb, 128, 4 * 2 * (COLS + 1) * 8 * sizeof(double), s>>>(f->d_buf, c->plan->Np, bs, f->d_cur, c->d_seg_start,  \
+                                                                     c->d_seg_fq, c->d_t_cell, c->d_t_af, c->d_ex_ptr32,     \
+                                                                     c->d_exrec, d_const, (int)c->n_seg, c0, (int)f->C)
+            if (left <= 16) EUT_SCATTER_P(16);
+            else if (left <= 32) EUT_SCATTER_P(32);
+            else EUT_SCATTER_P(64);
+#undef EUT_SCATTER_P
+            f->launches++;
+        }
+        EUT_CUDA(cudaGetLastError());
+        return EUT_OK;
+    }
+    if (gen == 2) {
         const int ldc = (int)((f->C + 63) / 64 * 64);
         EUT_TRY(grow(&c->d_exd, &c->exd_cap, M * (int64_t)ldc));
         EUT_TRY(grow(&c->d_exmask, &c->exmask_cap, M * (int64_t)(ldc / 64) * 2));

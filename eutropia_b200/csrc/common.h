@@ -213,6 +213,7 @@ struct eut_field {
     cudaEvent_t ev_dstage_ready[2] = {nullptr, nullptr};
     int64_t up_chunks = 0, down_chunks = 0;
     double *d_stats = nullptr;         // [3][C]
+    uint64_t version = 0;              // bumped by everything that changes field values (cells.cu: is a gather still current?)
     std::atomic<int64_t> launches{0};  // also bumped by the staged downloader thread (hoststage.cu)
     // substep loops seen before, captured as CUDA graphs (key: substep counts + options)
     std::map<uint64_t, cudaGraphExec_t> graphs;

@@ -55,6 +55,8 @@ int field_create(eut_field **out, eut_plan *plan, int64_t n_cols)
     eut_field *f = new eut_field();
     f->plan = plan;
     f->C = n_cols;
+    static std::atomic<uint64_t> epoch{0};
+    f->version = (++epoch) << 32;                  // never equal to a version of an earlier field at the same address
     int rc = field_alloc(f);
     if (rc != EUT_OK) {
         field_destroy(f);
@@ -139,6 +141,7 @@ int field_upload(eut_field *f, const double *host, int64_t ld, const int32_t *co
         return EUT_ERR_ARG;
     }
     EUT_TRY(ensure_device(p->device));
+    f->version++;
     const int64_t N = p->N;
     for (int64_t j0 = 0, g = f->up_chunks; j0 < n_cols; j0 += f->stage_cols, g++) {
         const int slot = (int)(g & 1);
@@ -254,6 +257,7 @@ int field_diffuse(eut_field *f, const int32_t *niter, const int32_t *indvar, int
     for (int64_t i = 0; i < n_indvar; i++)
         if (niter[i] > 0) order.push_back(i);
     if (order.empty()) return EUT_OK;
+    f->version++;
     std::stable_sort(order.begin(), order.end(),
                      [&](int64_t a, int64_t b) { return niter[a] > niter[b]; });
     const int n_tot = (int)order.size();
@@ -408,6 +412,7 @@ int field_stream_columns(eut_field *f, const double *h_in, double *h_out, int64_
     const int64_t N = p->N;
     const int n = (int)n64;
     if (n == 0 || N == 0) return EUT_OK;
+    f->version++;
     constexpr int kRing = 16;
     static const int kInFlight = [] { const char *e = getenv("EUT_STREAM_DEPTH"); return std::min(12, std::max(1, e ? atoi(e) : 6)); }();
     static const int G = [] { const char *e = getenv("EUT_STREAM_GROUP"); return std::max(1, e ? atoi(e) : 4); }();

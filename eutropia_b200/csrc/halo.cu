@@ -149,6 +149,7 @@ int eut_field_halo_unpack(eut_field *f, const int32_t *cols, int64_t n_cols, con
     EUT_TRY(ensure_device(f->plan->device));
     int32_t *d_cols = nullptr;
     EUT_TRY(upload_cols(f, cols, n_cols, &d_cols));
+    f->version++;
     dim3 grid((unsigned)((f->n_halo_recv + 255) / 256), (unsigned)n_cols, 1);
     k_halo_unpack<<<grid, 256, 0, f->halo_stream ? f->halo_stream : f->stream>>>(f->d_buf, f->plan->Np, f->C * f->plan->Np, f->d_cur, d_cols,
                                                f->d_halo_recv, (int)f->n_halo_recv, (const double *)dev_in);

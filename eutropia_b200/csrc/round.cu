@@ -91,6 +91,7 @@ int field_exoenzyme_catalysis(eut_field *cf, eut_field *ef, int32_t exo_col, dou
 {
     const eut_plan *p = cf->plan;
     if (p->N == 0) return EUT_OK;
+    cf->version++;
     MetArgs m;
     m.n = 0;
     const int64_t bs = cf->C * p->Np;
@@ -126,6 +127,7 @@ int field_scale_column(eut_field *f, int32_t col0, double factor)
 {
     const eut_plan *p = f->plan;
     if (p->N == 0) return EUT_OK;
+    f->version++;
     double *dst = f->d_buf + (int64_t)f->cur[col0] * f->C * p->Np + (int64_t)col0 * p->Np;
     k_scale<<<(unsigned)((p->Np + 255) / 256), 256, 0, f->stream>>>(dst, factor, (int)p->Np);
     f->launches++;

@@ -272,6 +272,7 @@ int launch_fill_column(eut_field *f, int32_t col0, double value)
 {
     const eut_plan *p = f->plan;
     if (p->N == 0) return EUT_OK;
+    f->version++;
     double *dst = f->d_buf + (int64_t)f->cur[col0] * f->C * p->Np + (int64_t)col0 * p->Np;
     k_fill<<<(unsigned)((p->Np + 255) / 256), 256, 0, f->stream>>>(dst, value, (int)p->Np);
     f->launches++;

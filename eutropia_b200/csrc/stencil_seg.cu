@@ -370,6 +370,10 @@ static int launch_seg_t(eut_field *f, int n_act, int substep)
     const int64_t want = (f->in_lanes ? 2ll : 6ll) * 148 * MINB;
     const int min_cols = f->in_lanes ? 32 : 16;
     while ((int64_t)n_tiles * slices < want && slices < n_act && (n_act + slices) / (slices + 1) >= min_cols) slices++;
+    // Small fields (configs[1]: 73 tiles): not even one wave of CTAs, so a launch lasts as long as its
+    // longest CTA and most SMs idle -- split the columns further, down to 4 per CTA (100 k points x 16
+    // columns: 19.4 -> 10.5 us per substep, profiles/r02_square_sweep.txt)
+    while ((int64_t)n_tiles * slices < 148ll * MINB && slices < n_act && (n_act + slices) / (slices + 1) >= 4) slices++;
     if (f->opt_cpt > 0) slices = (n_act + f->opt_cpt - 1) / f->opt_cpt;
     slices = std::max(slices, (n_act + kTileMaxCols - 1) / kTileMaxCols);
     const int cols_per_cta = (n_act + slices - 1) / slices;

@@ -235,3 +235,49 @@ def test_chemotaxis_shift_matches_oracle(small_mesh):
     scale = max(np.abs(ref[0]).max(), np.abs(ref[1]).max(), 1e-300)
     assert np.all(np.abs(got[0] - ref[0]) <= REL * scale) and np.all(np.abs(got[1] - ref[1]) <= REL * scale)
     assert np.any(ref[0] != 0) and np.any(ref[0] == 0)       # both branches are exercised
+
+
+@pytest.mark.parametrize("n_cols", [5, 30, 70])
+def test_scatter_generations_agree(harbor_mesh, n_cols, monkeypatch):
+    """The point-per-lane scatter (default) against the two earlier generations: the same terms in the same
+    cell order per (field, compound) sum, so the fields must be equal bit for bit; 70 columns take two
+    passes (64 + 6).  With the colSums taken over from a gather of the same field state (instead of a
+    second pass over the field) the result stays inside the 1e-12 bar."""
+    m = harbor_mesh
+    rng = np.random.default_rng(60 + n_cols)
+    conc = synth.synthetic_concentrations(m.field_pts, n_cols, seed=61)
+    conc[rng.uniform(size=conc.shape) < 0.02] = 0.0
+    n_cells = 400
+    cx, cy, size, scv = synth.place_cells(m, n_cells, seed=62)
+    ex_ptr, ex_cpd, ex_flx = synth.synthetic_exchanges(n_cells, n_cols, min(9, n_cols), seed=63)
+    ex_flx *= 1e-3
+    ex_flx[::17] = 0.0                                   # exchanges without a contribution
+    is_const = np.zeros(n_cols, bool); is_const[2] = True
+    plan = eb.Plan(m.mat_in, m.mat_out)
+    cells = eb.Cells(plan)
+    cells.build_lists(m.field_pts, cx, cy, size, scv)
+    cells.claim_rescale()
+    out = {}
+    for gen in ("1", "2", "3"):
+        monkeypatch.setenv("EUT_SCATTER_GEN", gen)
+        field = eb.Field(plan, n_cols)
+        field.upload(conc)
+        cells.scatter(field, m.field_vol, is_const, ex_ptr, ex_cpd, ex_flx)
+        out[gen] = field.download()
+        field.close()
+    assert np.array_equal(out["3"], out["2"]) and np.array_equal(out["3"], out["1"])
+    assert np.any(out["3"] != conc)
+    monkeypatch.delenv("EUT_SCATTER_GEN")
+    field = eb.Field(plan, n_cols)
+    field.upload(conc)
+    cells.gather(field, m.field_vol)                     # colSums of the next scatter
+    cells.scatter(field, m.field_vol, is_const, ex_ptr, ex_cpd, ex_flx)
+    again = field.download()
+    assert close(again, out["3"], absol=1e-12 * np.abs(conc).max())
+    assert np.array_equal(again == 0.0, out["3"] == 0.0)
+    # a field that changed after the gather must not use its sums
+    field.upload(conc * 2.0)
+    cells.scatter(field, m.field_vol, is_const, ex_ptr, ex_cpd, ex_flx)
+    ptr, fid, fd, acc = cells.get_lists()
+    ref = oracle.scatter(conc * 2.0, is_const, ptr, fid, fd, acc, m.field_vol, ex_ptr, ex_cpd, ex_flx)
+    assert close(field.download(), ref, absol=1e-12 * np.abs(conc).max() * 2)
