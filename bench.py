@@ -278,6 +278,56 @@ def square100k_leg(eb, torch, dev, peak):
             "parity": dict(par, against=kind, columns=2, substeps=s)}
 
 
+def slab_leg(eb, torch, world, peak, points_per_gpu=2_000_000, cols=64, substeps=60):
+    """BASELINE.json configs[4] in shape: ONE field of 2 M points per GPU x 64 compounds sharded by spatial
+    slab over all GPUs of the box, driven by this process through eut_slab_* (halo values stored straight
+    into the neighbours' ghost cells over NVLink peer mappings).  Wall clock around the asynchronous
+    diffuse call plus the closing synchronize; 2 columns are checked bit for bit against the unsharded
+    field on one GPU."""
+    from eutropia_b200 import synth
+    t0 = time.perf_counter()
+    mesh = synth.config_mesh(f"square:{points_per_gpu * world}", on_device=True, device=0)
+    n = mesh.nfields
+    t_mesh = time.perf_counter() - t0
+    rng = np.random.default_rng(5)
+    conc = np.empty((n, cols), order="F")
+    for c in range(cols):
+        conc[:, c] = rng.uniform(0, 25, n)
+    sf = eb.SlabField(mesh.mat_in, mesh.mat_out, cols, list(range(world)))
+    info = sf.info
+    sf.upload(conc)
+    iv = np.arange(1, cols + 1, dtype=np.int32)
+    sf.diffuse(np.full(cols, 5, np.int32), iv)
+    sf.sync()
+    sf.upload(conc)
+    l0 = sf.launch_count
+    t0 = time.perf_counter()
+    sf.diffuse(np.full(cols, substeps, np.int32), iv)
+    sf.sync()
+    dt = time.perf_counter() - t0
+    launches = sf.launch_count - l0
+    got = sf.download()[:, :2]
+    sf.close()
+    plan = eb.Plan(mesh.mat_in, mesh.mat_out, device=0)
+    f = eb.Field(plan, 2)
+    f.upload(conc[:, :2])
+    f.diffuse(np.full(2, substeps, np.int32), iv[:2])
+    same = bool(np.array_equal(f.download(), got))
+    f.close(); plan.close()
+    if not same:
+        raise SystemExit("bench.py: the slab-sharded field differs from the unsharded one")
+    value = n * cols * substeps / dt
+    gbps = BYTES_PER_UPDATE * value / world / 1e9
+    return {"workload": f"slab: one field of {n} points x {cols} compounds x {substeps} substeps, sharded by spatial slab over "
+                        f"{world} GPUs from one process (configs[4] shape: 2 M points per GPU)",
+            "value": value, "unit": UNIT, "ms_per_substep": dt * 1e3 / substeps, "n_gpus": world,
+            "algorithmic_GBps_per_gpu": gbps, "frac_of_hbm_peak_per_gpu": gbps / peak,
+            "halo_points_per_substep": int(info.halo_points), "nvlink_bytes_per_substep": int(info.halo_points) * cols * 8,
+            "links": int(info.n_links), "gpu_launches": int(launches), "bit_identical_to_unsharded": same,
+            "segment_kernel_on_every_slab": bool(info.segmented), "setup_s": {"mesh": t_mesh, "partition_and_plans": info.build_ms / 1e3},
+            "timer": "host wall clock around eut_slab_diffuse + eut_slab_sync"}
+
+
 def run_reference(args):
     """--impl reference: the reference's own diffChangePar (src/diffChange.cpp compiled into
     oracle/_ref; the oracle port if that library is absent) on this box's host cores, same config
@@ -504,6 +554,9 @@ def run_ours(args):
     extra = {}
     if rank == 0 and not args.no_extra:
         extra["square100k"] = square100k_leg(eb, torch, dev, peak)
+        if world > 1:
+            # the other ranks idle on the host barrier below; their GPUs are driven from here
+            extra["slab"] = slab_leg(eb, torch, world, peak)
     if world > 1:
         host_barrier()
 

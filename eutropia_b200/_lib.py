@@ -43,6 +43,12 @@ class PlanInfo(C.Structure):
     ]
 
 
+class SlabInfo(C.Structure):
+    _fields_ = [("n_points", C.c_int64), ("n_cols", C.c_int64), ("n_slabs", C.c_int32), ("n_links", C.c_int32),
+                ("max_local", C.c_int64), ("halo_points", C.c_int64), ("max_link", C.c_int64), ("pushes", C.c_int64),
+                ("segmented", C.c_int32), ("build_ms", C.c_double)]
+
+
 _lib = None
 
 
@@ -92,6 +98,15 @@ def lib() -> C.CDLL:
         "eut_field_set_halo_stream": (C.c_int, [vp, vp]),
         "eut_field_halo_pack": (C.c_int, [vp, vp, i64, vp]),
         "eut_field_halo_unpack": (C.c_int, [vp, vp, i64, vp]),
+        "eut_slab_create": (C.c_int, [C.POINTER(vp), vp, vp, i64, vp, vp, i64, i64, i64, vp, C.c_int]),
+        "eut_slab_destroy": (C.c_int, [vp]),
+        "eut_slab_get_info": (C.c_int, [vp, C.POINTER(SlabInfo)]),
+        "eut_slab_part": (C.c_int, [vp, C.c_int, C.POINTER(i32), C.POINTER(i64), C.POINTER(i64), C.POINTER(vp)]),
+        "eut_slab_upload": (C.c_int, [vp, vp, i64]),
+        "eut_slab_download": (C.c_int, [vp, vp, i64]),
+        "eut_slab_diffuse": (C.c_int, [vp, vp, vp, i64]),
+        "eut_slab_sync": (C.c_int, [vp]),
+        "eut_slab_launch_count": (i64, [vp]),
         "eut_cells_create": (C.c_int, [C.POINTER(vp), vp]),
         "eut_cells_destroy": (C.c_int, [vp]),
         "eut_cells_set_lists": (C.c_int, [vp, i64, vp, vp, vp, vp]),
@@ -119,6 +134,8 @@ EXPORTS = (
     "eut_field_launch_count eut_field_set_option eut_field_column_stats eut_field_fill_column "
     "eut_field_exoenzyme_catalysis eut_field_scale_column "
     "eut_field_halo_set eut_field_set_halo_stream eut_field_halo_pack eut_field_halo_unpack "
+    "eut_slab_create eut_slab_destroy eut_slab_get_info eut_slab_part eut_slab_upload eut_slab_download "
+    "eut_slab_diffuse eut_slab_sync eut_slab_launch_count "
     "eut_cells_create eut_cells_destroy eut_cells_set_lists eut_cells_build_lists "
     "eut_cells_claim_rescale eut_cells_num_entries eut_cells_get_lists eut_cells_gather "
     "eut_cells_scatter eut_cells_chemotaxis_moments"

@@ -1,0 +1,425 @@
+// Spatial slab sharding of ONE field over several GPUs of the box, driven from ONE process
+// (BASELINE.json configs[4]; SURVEY 8e "by spatial slab").  The reference has no counterpart -- it runs
+// on one host -- and its `diffChange` signature carries no coordinates, so the slabs are derived from
+// the graph: the tile planner's internal order (compact tiles ordered by coarse level band) is cut into
+// contiguous ranges, one per slab.  Slab r then works on a LOCAL graph = its own points plus ghost
+// copies of the remote in-neighbours:
+//   * local ids follow ascending global id, so raster rows stay runs of consecutive ids and the local
+//     plan tiles like the global one;
+//   * local mat.in = the rows of the global mat.in whose `to` is owned, in the global row order: every
+//     owned point sums exactly the same values in exactly the same order as in the unsharded run, so
+//     the result is bit-identical to it;
+//   * ghosts have no in-edges and n_neighbors = 1 (outflow weight 0): a local substep copies them
+//     forward unchanged, the halo exchange overwrites them with the owner's new value.
+// Halo exchange: no pack / send / recv / unpack.  After a substep the OWNER of a boundary point stores
+// its new value straight into the ghost cell of the neighbour's field through a peer-mapped pointer
+// (NVLink P2P inside one process, cudaDeviceEnablePeerAccess): one small kernel per ordered pair of
+// neighbouring slabs, ordered against the two substep kernels it sits between by CUDA events.
+// (eutropia_b200/slab.py is the same partition with one process per GPU and NCCL send / recv.)
+#include <algorithm>
+#include <numeric>
+#include <thread>
+
+#include "common.h"
+#include "hoststage.h"
+
+namespace eut {
+
+__global__ void __launch_bounds__(256)
+k_halo_push(const double *__restrict__ src, const int64_t src_cs, const int64_t src_bs, double *__restrict__ dst,
+            const int64_t dst_cs, const int64_t dst_bs, const int32_t *__restrict__ cur,
+            const int32_t *__restrict__ cols, const int32_t *__restrict__ spos, const int32_t *__restrict__ dpos,
+            const int n)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int c = cols[blockIdx.y];
+    const int64_t b = cur[c];                    // every slab is at the same substep: same buffer on both sides
+    dst[b * dst_bs + (int64_t)c * dst_cs + dpos[k]] = src[b * src_bs + (int64_t)c * src_cs + spos[k]];
+}
+
+}  // namespace eut
+
+using namespace eut;
+
+struct eut_slab {
+    struct Link {                                // values of `n` points travel from part `src` to part `dst`
+        int src = 0, dst = 0;
+        int64_t n = 0;
+        std::vector<int32_t> src_local, dst_local;   // local ids (0-based) on either side, ascending global id
+        int32_t *d_spos = nullptr, *d_dpos = nullptr;  // internal positions, resident on the SOURCE device
+        cudaEvent_t done = nullptr;
+    };
+    struct Part {
+        int device = 0;
+        int64_t n_local = 0, n_own = 0;
+        std::vector<int32_t> local_global;       // local id -> global id (0-based), ascending
+        std::vector<uint8_t> is_own;
+        eut_plan *plan = nullptr;
+        eut_field *field = nullptr;
+        int32_t *d_order = nullptr;              // [C] columns of the current diffuse call, most substeps first
+        cudaEvent_t stepped = nullptr;
+    };
+    int64_t N = 0, C = 0;
+    std::vector<Part> parts;
+    std::vector<Link> links;
+    std::vector<int32_t> h_order;
+    int64_t pushes = 0;
+    double build_ms = 0;
+};
+
+namespace {
+
+void slab_free(eut_slab *s)
+{
+    for (auto &l : s->links) {
+        cudaSetDevice(s->parts[l.src].device);
+        cudaFree(l.d_spos); cudaFree(l.d_dpos);
+        if (l.done) cudaEventDestroy(l.done);
+    }
+    for (auto &p : s->parts) {
+        if (p.field) field_destroy(p.field);
+        if (p.plan) { plan_free(p.plan); delete p.plan; }
+        cudaSetDevice(p.device);
+        cudaFree(p.d_order);
+        if (p.stepped) cudaEventDestroy(p.stepped);
+    }
+    delete s;
+}
+
+int upload_i32(int device, const std::vector<int32_t> &h, int32_t **d)
+{
+    EUT_TRY(ensure_device(device));
+    EUT_CUDA(cudaMalloc((void **)d, std::max<size_t>(h.size(), 1) * sizeof(int32_t)));
+    if (!h.empty()) EUT_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    return EUT_OK;
+}
+
+// current values of the first n_act columns of the call's order travel along every link
+int push_halos(eut_slab *s, int n_act)
+{
+    for (auto &l : s->links) {
+        eut_slab::Part &a = s->parts[l.src], &b = s->parts[l.dst];
+        if (l.n == 0 || n_act == 0) continue;
+        EUT_TRY(ensure_device(a.device));
+        // the destination's substep has copied its ghost cells forward (a push that lands earlier would be
+        // overwritten with the stale value); the source's own substep precedes the push on its stream
+        EUT_CUDA(cudaStreamWaitEvent(a.field->stream, b.stepped, 0));
+        dim3 grid((unsigned)((l.n + 255) / 256), (unsigned)n_act, 1);
+        k_halo_push<<<grid, 256, 0, a.field->stream>>>(a.field->d_buf, a.plan->Np, a.field->C * a.plan->Np, b.field->d_buf,
+                                                        b.plan->Np, b.field->C * b.plan->Np, a.field->d_cur, a.d_order,
+                                                        l.d_spos, l.d_dpos, (int)l.n);
+        EUT_CUDA(cudaGetLastError());
+        EUT_CUDA(cudaEventRecord(l.done, a.field->stream));
+        a.field->launches++;
+        s->pushes++;
+    }
+    // nobody reads its ghost cells before they have arrived
+    for (auto &l : s->links) {
+        if (l.n == 0 || n_act == 0) continue;
+        eut_slab::Part &b = s->parts[l.dst];
+        EUT_TRY(ensure_device(b.device));
+        EUT_CUDA(cudaStreamWaitEvent(b.field->stream, l.done, 0));
+        b.field->version++;
+    }
+    return EUT_OK;
+}
+
+int mark_stepped(eut_slab *s)
+{
+    for (auto &p : s->parts) {
+        EUT_TRY(ensure_device(p.device));
+        EUT_CUDA(cudaEventRecord(p.stepped, p.field->stream));
+    }
+    return EUT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int eut_slab_create(eut_slab **out, const int32_t *from, const int32_t *to, int64_t n_edges, const int32_t *nn_id,
+                    const int32_t *nn_cnt, int64_t n_nn, int64_t n_points, int64_t n_cols, const int *devices,
+                    int n_devices)
+{
+    clear_error();
+    if (!out) { set_error("eut_slab_create: out is NULL"); return EUT_ERR_ARG; }
+    *out = nullptr;
+    if (n_devices < 1 || n_devices > 64 || !devices || n_cols < 1 || n_points < 1 || n_edges < 0 || n_nn < 0 ||
+        (n_edges > 0 && (!from || !to)) || (n_nn > 0 && (!nn_id || !nn_cnt))) {
+        set_error("eut_slab_create: bad argument");
+        return EUT_ERR_ARG;
+    }
+    const double t0 = now_ms();
+    const int W = n_devices;
+    const int64_t N = n_points;
+    for (int d = 0; d < W; d++) EUT_TRY(ensure_device(devices[d]));
+    // peer access between the devices of neighbouring slabs (a device may hold several slabs: the tests
+    // run three slabs on one GPU)
+    for (int a = 0; a < W; a++)
+        for (int b = 0; b < W; b++) {
+            if (devices[a] == devices[b]) continue;
+            int can = 0;
+            EUT_CUDA(cudaDeviceCanAccessPeer(&can, devices[a], devices[b]));
+            if (!can) { set_error("eut_slab_create: device %d cannot access device %d (no peer-to-peer path)", devices[a], devices[b]); return EUT_ERR_UNSUPPORTED; }
+            EUT_CUDA(cudaSetDevice(devices[a]));
+            const cudaError_t e = cudaDeviceEnablePeerAccess(devices[b], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { set_error("cudaDeviceEnablePeerAccess(%d -> %d): %s", devices[a], devices[b], cudaGetErrorString(e)); return EUT_ERR_CUDA; }
+            (void)cudaGetLastError();
+        }
+    // global internal order: the tile planner's (host analysis only)
+    std::vector<int32_t> owner(N);
+    {
+        eut_plan g;
+        const int rc = plan_build(&g, from, to, n_edges, nn_id, nn_cnt, n_nn, N, devices[0], EUT_ORDER_TILED | EUT_PLAN_HOST_ONLY);
+        if (rc != EUT_OK) return rc;
+        std::vector<int64_t> bounds(W + 1);
+        for (int r = 0; r <= W; r++) bounds[r] = (int64_t)std::llround((double)N * r / W);
+        // positions of a tiled plan may exceed N (padding): rank them first
+        std::vector<int32_t> by_pos(N);
+        std::iota(by_pos.begin(), by_pos.end(), 0);
+        std::sort(by_pos.begin(), by_pos.end(), [&](int32_t a, int32_t b) { return g.perm[a] < g.perm[b]; });
+        int r = 0;
+        for (int64_t k = 0; k < N; k++) {
+            while (k >= bounds[r + 1]) r++;
+            owner[by_pos[k]] = r;
+        }
+    }
+    std::vector<int32_t> nn_by_id(N, 1);
+    for (int64_t j = 0; j < n_nn; j++) {
+        if (nn_id[j] < 1 || nn_id[j] > N) { set_error("index out of bounds: mat.out row %lld id = %d", (long long)j + 1, nn_id[j]); return EUT_ERR_INDEX; }
+        nn_by_id[nn_id[j] - 1] = nn_cnt[j];
+    }
+    eut_slab *s = new eut_slab();
+    s->N = N; s->C = n_cols;
+    s->parts.resize(W);
+    std::vector<int> rcs(W, EUT_OK);
+    std::vector<std::string> errs(W);
+    // per slab: local graph, plan, field -- one host thread each
+    std::vector<std::vector<int32_t>> g2l(W);
+    auto build_part = [&](int r) -> int {
+        eut_slab::Part &P = s->parts[r];
+        P.device = devices[r];
+        std::vector<uint8_t> mark(N, 0);             // 1 own, 2 ghost
+        for (int64_t i = 0; i < N; i++) mark[i] = owner[i] == r ? 1 : 0;
+        int64_t n_in = 0;
+        for (int64_t j = 0; j < n_edges; j++)
+            if (owner[to[j] - 1] == r) { n_in++; if (!mark[from[j] - 1]) mark[from[j] - 1] = 2; }
+        std::vector<int32_t> &map = g2l[r];
+        map.assign(N, -1);
+        for (int64_t i = 0; i < N; i++)
+            if (mark[i]) { map[i] = (int32_t)P.local_global.size(); P.local_global.push_back((int32_t)i); P.is_own.push_back(mark[i] == 1); }
+        P.n_local = (int64_t)P.local_global.size();
+        P.n_own = std::count(P.is_own.begin(), P.is_own.end(), (uint8_t)1);
+        std::vector<int32_t> lf(n_in), lt(n_in), id(P.n_local), cnt(P.n_local);
+        int64_t o = 0;
+        for (int64_t j = 0; j < n_edges; j++)
+            if (owner[to[j] - 1] == r) { lf[o] = map[from[j] - 1] + 1; lt[o] = map[to[j] - 1] + 1; o++; }
+        for (int64_t k = 0; k < P.n_local; k++) { id[k] = (int32_t)k + 1; cnt[k] = P.is_own[k] ? nn_by_id[P.local_global[k]] : 1; }
+        P.plan = new eut_plan();
+        EUT_TRY(plan_build(P.plan, lf.data(), lt.data(), n_in, id.data(), cnt.data(), P.n_local, P.n_local, P.device, EUT_ORDER_AUTO));
+        EUT_TRY(field_create(&P.field, P.plan, n_cols));
+        P.field->copy_threads = std::max(1u, std::min(8u, host_thread_budget() / (2u * (unsigned)W)));
+        EUT_CUDA(cudaMalloc((void **)&P.d_order, std::max<int64_t>(n_cols, 1) * sizeof(int32_t)));
+        EUT_CUDA(cudaEventCreateWithFlags(&P.stepped, cudaEventDisableTiming));
+        return EUT_OK;
+    };
+    {
+        std::vector<std::thread> th;
+        for (int r = 0; r < W; r++)
+            th.emplace_back([&, r] { rcs[r] = build_part(r); if (rcs[r] != EUT_OK) errs[r] = last_error_cstr(); });
+        for (auto &t : th) t.join();
+    }
+    for (int r = 0; r < W; r++)
+        if (rcs[r] != EUT_OK) { set_error("slab %d: %s", r, errs[r].c_str()); const int rc = rcs[r]; slab_free(s); return rc; }
+    // links: for every ordered pair (a -> b) the points a owns that b keeps a ghost of, ascending global id
+    for (int a = 0; a < W; a++)
+        for (int b = 0; b < W; b++) {
+            if (a == b) continue;
+            eut_slab::Link L;
+            L.src = a; L.dst = b;
+            const eut_slab::Part &B = s->parts[b];
+            for (int64_t k = 0; k < B.n_local; k++)
+                if (!B.is_own[k] && owner[B.local_global[k]] == a) {
+                    L.dst_local.push_back((int32_t)k);
+                    L.src_local.push_back(g2l[a][B.local_global[k]]);
+                }
+            L.n = (int64_t)L.dst_local.size();
+            if (L.n == 0) continue;
+            std::vector<int32_t> sp(L.n), dp(L.n);
+            for (int64_t k = 0; k < L.n; k++) {
+                if (L.src_local[k] < 0) { set_error("eut_slab_create: ghost without an owner copy"); slab_free(s); return EUT_ERR_UNSUPPORTED; }
+                sp[k] = s->parts[a].plan->perm[L.src_local[k]];
+                dp[k] = B.plan->perm[L.dst_local[k]];
+            }
+            int rc = upload_i32(s->parts[a].device, sp, &L.d_spos);
+            if (rc == EUT_OK) rc = upload_i32(s->parts[a].device, dp, &L.d_dpos);
+            if (rc == EUT_OK && cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming) != cudaSuccess) rc = EUT_ERR_CUDA;
+            if (rc != EUT_OK) { slab_free(s); return rc; }
+            s->links.push_back(std::move(L));
+        }
+    s->build_ms = now_ms() - t0;
+    *out = s;
+    return EUT_OK;
+}
+
+int eut_slab_destroy(eut_slab *s)
+{
+    if (s) slab_free(s);
+    return EUT_OK;
+}
+
+int eut_slab_get_info(const eut_slab *s, eut_slab_info *info)
+{
+    if (!s || !info) { set_error("eut_slab_get_info: NULL argument"); return EUT_ERR_ARG; }
+    info->n_points = s->N; info->n_cols = s->C; info->n_slabs = (int32_t)s->parts.size();
+    info->n_links = (int32_t)s->links.size();
+    info->max_local = 0; info->halo_points = 0; info->max_link = 0; info->segmented = 1;
+    for (auto &p : s->parts) { info->max_local = std::max(info->max_local, p.n_local); info->segmented &= p.plan->segmented ? 1 : 0; }
+    for (auto &l : s->links) { info->halo_points += l.n; info->max_link = std::max(info->max_link, l.n); }
+    info->pushes = s->pushes;
+    info->build_ms = s->build_ms;
+    return EUT_OK;
+}
+
+int eut_slab_part(const eut_slab *s, int slab, int32_t *device, int64_t *n_local, int64_t *n_own, void **stream)
+{
+    if (!s || slab < 0 || slab >= (int)s->parts.size()) { set_error("eut_slab_part: bad slab index"); return EUT_ERR_ARG; }
+    const auto &p = s->parts[slab];
+    if (device) *device = p.device;
+    if (n_local) *n_local = p.n_local;
+    if (n_own) *n_own = p.n_own;
+    if (stream) *stream = (void *)p.field->stream;
+    return EUT_OK;
+}
+
+// host (N x C, column-major, leading dimension ld) -> every slab's rows (own + ghosts)
+int eut_slab_upload(eut_slab *s, const double *host, int64_t ld)
+{
+    clear_error();
+    if (!s || !host || ld < s->N) { set_error("eut_slab_upload: NULL pointer or ld < N"); return EUT_ERR_ARG; }
+    const int W = (int)s->parts.size();
+    std::vector<int> rcs(W, EUT_OK);
+    std::vector<std::string> errs(W);
+    auto one = [&](int r) -> int {
+        eut_slab::Part &P = s->parts[r];
+        const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(s->C, (64ll << 20) / std::max<int64_t>(P.n_local, 1)));
+        std::vector<double> tmp((size_t)chunk * P.n_local);
+        std::vector<int32_t> cols(chunk);
+        for (int64_t c0 = 0; c0 < s->C; c0 += chunk) {
+            const int64_t nc = std::min(chunk, s->C - c0);
+            for (int64_t c = 0; c < nc; c++) {
+                const double *src = host + (size_t)(c0 + c) * ld;
+                double *dst = tmp.data() + (size_t)c * P.n_local;
+                for (int64_t k = 0; k < P.n_local; k++) dst[k] = src[P.local_global[k]];
+                cols[c] = (int32_t)(c0 + c + 1);
+            }
+            EUT_TRY(field_upload(P.field, tmp.data(), P.n_local, cols.data(), nc));
+            EUT_CUDA(cudaStreamSynchronize(P.field->copy_stream));
+        }
+        EUT_CUDA(cudaStreamSynchronize(P.field->stream));
+        return EUT_OK;
+    };
+    std::vector<std::thread> th;
+    for (int r = 0; r < W; r++) th.emplace_back([&, r] { rcs[r] = one(r); if (rcs[r] != EUT_OK) errs[r] = last_error_cstr(); });
+    for (auto &t : th) t.join();
+    for (int r = 0; r < W; r++)
+        if (rcs[r] != EUT_OK) { set_error("slab %d: %s", r, errs[r].c_str()); return rcs[r]; }
+    return EUT_OK;
+}
+
+// every slab's OWN rows -> host (N x C)
+int eut_slab_download(eut_slab *s, double *host, int64_t ld)
+{
+    clear_error();
+    if (!s || !host || ld < s->N) { set_error("eut_slab_download: NULL pointer or ld < N"); return EUT_ERR_ARG; }
+    const int W = (int)s->parts.size();
+    std::vector<int> rcs(W, EUT_OK);
+    std::vector<std::string> errs(W);
+    auto one = [&](int r) -> int {
+        eut_slab::Part &P = s->parts[r];
+        const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(s->C, (64ll << 20) / std::max<int64_t>(P.n_local, 1)));
+        std::vector<double> tmp((size_t)chunk * P.n_local);
+        std::vector<int32_t> cols(chunk);
+        for (int64_t c0 = 0; c0 < s->C; c0 += chunk) {
+            const int64_t nc = std::min(chunk, s->C - c0);
+            for (int64_t c = 0; c < nc; c++) cols[c] = (int32_t)(c0 + c + 1);
+            EUT_TRY(field_download_async(P.field, tmp.data(), P.n_local, cols.data(), nc));
+            EUT_TRY(field_sync_down(P.field));
+            for (int64_t c = 0; c < nc; c++) {
+                double *dst = host + (size_t)(c0 + c) * ld;
+                const double *src = tmp.data() + (size_t)c * P.n_local;
+                for (int64_t k = 0; k < P.n_local; k++)
+                    if (P.is_own[k]) dst[P.local_global[k]] = src[k];
+            }
+        }
+        return EUT_OK;
+    };
+    std::vector<std::thread> th;
+    for (int r = 0; r < W; r++) th.emplace_back([&, r] { rcs[r] = one(r); if (rcs[r] != EUT_OK) errs[r] = last_error_cstr(); });
+    for (auto &t : th) t.join();
+    for (int r = 0; r < W; r++)
+        if (rcs[r] != EUT_OK) { set_error("slab %d: %s", r, errs[r].c_str()); return rcs[r]; }
+    return EUT_OK;
+}
+
+// diffChangePar semantics on the sharded field: niter[i] substeps on column indvar[i]; after every substep
+// the boundary values of the columns that moved travel to the neighbours' ghost cells
+int eut_slab_diffuse(eut_slab *s, const int32_t *niter, const int32_t *indvar, int64_t n_indvar)
+{
+    clear_error();
+    if (!s || n_indvar < 0 || (n_indvar > 0 && (!niter || !indvar))) { set_error("eut_slab_diffuse: bad argument"); return EUT_ERR_ARG; }
+    std::vector<uint8_t> seen(s->C, 0);
+    std::vector<int64_t> order;
+    for (int64_t i = 0; i < n_indvar; i++) {
+        if (niter[i] <= 0) continue;                 // never dereferenced by the reference (src/diffChange.cpp:48-54)
+        if (indvar[i] < 1 || indvar[i] > s->C) { set_error("index out of bounds: indvar[%lld] = %d, field has %lld columns", (long long)i + 1, indvar[i], (long long)s->C); return EUT_ERR_INDEX; }
+        if (seen[indvar[i] - 1]) { set_error("eut_slab_diffuse: column %d listed twice in indvar", indvar[i]); return EUT_ERR_ARG; }
+        seen[indvar[i] - 1] = 1;
+        order.push_back(i);
+    }
+    if (order.empty()) return EUT_OK;
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return niter[a] > niter[b]; });
+    const int n_tot = (int)order.size();
+    s->h_order.resize(n_tot);
+    std::vector<int32_t> cols1(n_tot), ones(n_tot, 1);
+    for (int a = 0; a < n_tot; a++) { s->h_order[a] = indvar[order[a]] - 1; cols1[a] = indvar[order[a]]; }
+    for (auto &p : s->parts) {
+        EUT_TRY(ensure_device(p.device));
+        EUT_CUDA(cudaMemcpyAsync(p.d_order, s->h_order.data(), n_tot * sizeof(int32_t), cudaMemcpyHostToDevice, p.field->stream));
+    }
+    // ghosts up to date before the first substep (an upload or anything else may have changed owned values)
+    EUT_TRY(mark_stepped(s));
+    EUT_TRY(push_halos(s, n_tot));
+    const int max_it = niter[order[0]];
+    int n_act = n_tot;
+    for (int it = 0; it < max_it; it++) {
+        while (n_act > 0 && niter[order[n_act - 1]] <= it) n_act--;
+        if (n_act == 0) break;
+        for (auto &p : s->parts) EUT_TRY(field_diffuse(p.field, ones.data(), cols1.data(), n_act));
+        EUT_TRY(mark_stepped(s));
+        EUT_TRY(push_halos(s, n_act));
+    }
+    return EUT_OK;
+}
+
+int eut_slab_sync(eut_slab *s)
+{
+    if (!s) return EUT_ERR_ARG;
+    for (auto &p : s->parts) {
+        EUT_TRY(ensure_device(p.device));
+        EUT_CUDA(cudaStreamSynchronize(p.field->copy_stream));
+        EUT_CUDA(cudaStreamSynchronize(p.field->stream));
+        EUT_TRY(field_sync_down(p.field));
+    }
+    return EUT_OK;
+}
+
+int64_t eut_slab_launch_count(const eut_slab *s)
+{
+    int64_t n = 0;
+    if (s) for (auto &p : s->parts) n += p.field->launches.load();
+    return n;
+}
+
+}  // extern "C"

@@ -13,7 +13,7 @@ import numpy as np
 from . import _lib
 from ._lib import check, ptr
 
-__all__ = ["Plan", "Field", "Cells"]
+__all__ = ["Plan", "Field", "Cells", "SlabField"]
 
 
 def _i32(a):
@@ -273,3 +273,65 @@ class Cells:
         ec, ef = _i32(ex_cpd), _f64c(ex_flx)
         check(_lib.lib().eut_cells_scatter(self._h, field._h, float(field_vol), ptr(isc), ptr(ep),
                                            ptr(ec), ptr(ef)))
+
+
+class SlabField:
+    """One N x C field sharded by spatial slab over `devices` (one process, NVLink peer stores for the
+    halo): `eut_slab_*`.  Bit-identical to the unsharded `Field`."""
+
+    def __init__(self, mat_in, mat_out, n_cols: int, devices, n_points=None):
+        mat_in = np.asarray(mat_in).reshape(-1, 2)
+        mat_out = np.asarray(mat_out).reshape(-1, 2)
+        frm, to = _i32(mat_in[:, 0]), _i32(mat_in[:, 1])
+        nid, cnt = _i32(mat_out[:, 0]), _i32(mat_out[:, 1])
+        self.n_points = int(mat_out.shape[0]) if n_points is None else int(n_points)
+        self.n_cols = int(n_cols)
+        dv = np.ascontiguousarray(devices, dtype=np.int32)
+        h = C.c_void_p()
+        check(_lib.lib().eut_slab_create(C.byref(h), ptr(frm), ptr(to), frm.shape[0], ptr(nid), ptr(cnt), nid.shape[0],
+                                         self.n_points, self.n_cols, ptr(dv), dv.shape[0]))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().eut_slab_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @property
+    def info(self) -> _lib.SlabInfo:
+        inf = _lib.SlabInfo()
+        check(_lib.lib().eut_slab_get_info(self._h, C.byref(inf)))
+        return inf
+
+    def part(self, index: int):
+        """(device, points held, points owned, cudaStream_t) of one slab."""
+        dev, nl, no, st = C.c_int32(), C.c_int64(), C.c_int64(), C.c_void_p()
+        check(_lib.lib().eut_slab_part(self._h, int(index), C.byref(dev), C.byref(nl), C.byref(no), C.byref(st)))
+        return dev.value, nl.value, no.value, int(st.value or 0)
+
+    def upload(self, conc):
+        a = _colmajor(conc)
+        if a.shape != (self.n_points, self.n_cols):
+            raise ValueError("conc must be N x C")
+        check(_lib.lib().eut_slab_upload(self._h, ptr(a), max(self.n_points, 1)))
+
+    def download(self):
+        out = np.empty((self.n_points, self.n_cols), dtype=np.float64, order="F")
+        check(_lib.lib().eut_slab_download(self._h, ptr(out), max(self.n_points, 1)))
+        return out
+
+    def diffuse(self, niter, indvar):
+        ni = _i32(np.trunc(np.asarray(niter, dtype=np.float64)))
+        iv = _i32(np.trunc(np.asarray(indvar, dtype=np.float64)))
+        if ni.shape[0] < iv.shape[0]:
+            raise _lib.EutropiaIndexError(_lib.ERR_INDEX, "niter is shorter than indvar")
+        check(_lib.lib().eut_slab_diffuse(self._h, ptr(ni), ptr(iv), iv.shape[0]))
+
+    def sync(self):
+        check(_lib.lib().eut_slab_sync(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(_lib.lib().eut_slab_launch_count(self._h))

@@ -283,6 +283,44 @@ EUT_API int eut_field_halo_set(eut_field *field, const int32_t *send_ids, int64_
 EUT_API int eut_field_halo_pack(eut_field *field, const int32_t *cols, int64_t n_cols, void *dev_out);
 EUT_API int eut_field_halo_unpack(eut_field *field, const int32_t *cols, int64_t n_cols, const void *dev_in);
 
+/* ---- session tier: one field sharded by spatial slab over several GPUs, one process -----------
+ * For fields larger than one GPU (BASELINE.json configs[4]).  The reference has no counterpart (one
+ * host, one matrix); the contract is diffChangePar's: the sharded run is bit-identical to the
+ * unsharded one.  The slabs are derived from the graph alone (contiguous ranges of the tile planner's
+ * internal order); every slab holds its own points plus ghost copies of the remote in-neighbours and
+ * its own plan over that local graph.  After every substep the owner of a boundary point stores the
+ * new value straight into the neighbour's ghost cell through a peer-mapped pointer (NVLink P2P
+ * within the process, one small kernel per ordered pair of neighbouring slabs) -- no pack / send /
+ * recv / unpack.  `devices` may name a device more than once (several slabs on one GPU).
+ * (eutropia_b200/slab.py drives the same partition with one process per GPU and NCCL send / recv
+ * through eut_field_halo_*.) */
+typedef struct eut_slab eut_slab;
+typedef struct eut_slab_info {
+    int64_t n_points, n_cols;
+    int32_t n_slabs, n_links;   /* links: ordered pairs of slabs that exchange points */
+    int64_t max_local;          /* most points (own + ghost) of any slab */
+    int64_t halo_points;        /* points that travel per substep and column, summed over all links */
+    int64_t max_link;           /* most points of any link */
+    int64_t pushes;             /* halo kernels launched so far */
+    int32_t segmented;          /* 1: every slab runs the segment kernel */
+    double  build_ms;
+} eut_slab_info;
+EUT_API int eut_slab_create(eut_slab **out, const int32_t *from, const int32_t *to, int64_t n_edges,
+                            const int32_t *nn_id, const int32_t *nn_cnt, int64_t n_nn, int64_t n_points,
+                            int64_t n_cols, const int *devices, int n_devices);
+EUT_API int eut_slab_destroy(eut_slab *slab);
+EUT_API int eut_slab_get_info(const eut_slab *slab, eut_slab_info *info);
+/* Device, point counts and cudaStream_t of one slab (any pointer may be NULL). */
+EUT_API int eut_slab_part(const eut_slab *slab, int index, int32_t *device, int64_t *n_local, int64_t *n_own,
+                          void **stream);
+/* host <-> slabs: the global N x C matrix, column-major, leading dimension ld. */
+EUT_API int eut_slab_upload(eut_slab *slab, const double *host, int64_t ld);
+EUT_API int eut_slab_download(eut_slab *slab, double *host, int64_t ld);
+/* niter[i] substeps on column indvar[i] (diffChangePar contract), asynchronous on the slabs' streams. */
+EUT_API int eut_slab_diffuse(eut_slab *slab, const int32_t *niter, const int32_t *indvar, int64_t n_indvar);
+EUT_API int eut_slab_sync(eut_slab *slab);
+EUT_API int64_t eut_slab_launch_count(const eut_slab *slab);
+
 /* ---- session tier: cells = ragged cell -> field lists + gather / scatter ----------------------
  * Lists follow get_cellFieldEnv_ex's output (R/run_simulation.R:591-624): per cell the field ids
  * (1-based), the cell-field distances and the accessible proportions, in CSR form. */

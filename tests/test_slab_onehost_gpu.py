@@ -1,0 +1,86 @@
+"""eut_slab_*: one field sharded by spatial slab, driven from one process, halo values stored straight
+into the neighbour's ghost cells.  The contract is diffChangePar's: bit-identical to the unsharded run and
+to the oracle.  On a one-GPU box the slabs share the device (the exchange logic is the same; the stores
+just do not cross NVLink); with two GPUs they are spread over both."""
+import numpy as np
+import pytest
+
+import oracle
+import eutropia_b200 as eb
+from eutropia_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(m, conc, niter, indvar, devices, rounds=1):
+    sf = eb.SlabField(m.mat_in, m.mat_out, conc.shape[1], devices)
+    inf = sf.info
+    assert inf.n_slabs == len(devices) and inf.n_points == m.nfields
+    own = sum(sf.part(i)[2] for i in range(len(devices)))
+    assert own == m.nfields                                      # every point has exactly one owner
+    sf.upload(conc)
+    for _ in range(rounds):
+        sf.diffuse(niter, indvar)
+    out = sf.download()
+    info = sf.info
+    sf.close()
+    return out, info
+
+
+@pytest.mark.parametrize("devices", [[0], [0, 0], [0, 0, 0, 0, 0]])
+def test_slabs_on_one_device_match_oracle(harbor_mesh, devices):
+    m = harbor_mesh
+    rng = np.random.default_rng(31)
+    conc = np.asfortranarray(rng.uniform(0, 25, (m.nfields, 6)) * 10.0 ** rng.integers(-5, 4, (m.nfields, 6)))
+    niter, indvar = [14, 0, 5, 14, 9], [6, 2, 1, 3, 4]           # column 5 never listed, column 2 with zero substeps
+    ref = oracle.diffChangePar(m.mat_in, m.mat_out, conc, niter, indvar, 2)
+    got, info = _run(m, conc, niter, indvar, devices)
+    assert np.array_equal(got, ref)
+    if len(devices) > 1:
+        assert info.n_links >= 2 * (len(devices) - 1) and info.halo_points > 0 and info.pushes > 0
+    # a second round on the resident slabs == two rounds of the oracle
+    got2, _ = _run(m, conc, niter, indvar, devices, rounds=2)
+    assert np.array_equal(got2, oracle.diffChangePar(m.mat_in, m.mat_out, ref, niter, indvar, 2))
+
+
+def test_slabs_match_the_unsharded_field_on_a_large_mesh():
+    from eutropia_b200 import synth
+    m = synth.config_mesh("harbor:300000")
+    conc = synth.synthetic_concentrations(m.field_pts, 8, seed=32)
+    niter, indvar = np.full(8, 12), np.arange(1, 9)
+    plan = eb.Plan(m.mat_in, m.mat_out)
+    f = eb.Field(plan, 8)
+    f.upload(conc)
+    f.diffuse(niter, indvar)
+    whole = f.download()
+    f.close(); plan.close()
+    n_dev = _lib.lib().eut_device_count()
+    got, info = _run(m, conc, niter, indvar, [k % n_dev for k in range(4)])
+    assert np.array_equal(got, whole)
+    assert info.segmented == 1
+
+
+def test_slabs_on_two_devices_match_oracle(harbor_mesh):
+    if _lib.lib().eut_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    m = harbor_mesh
+    rng = np.random.default_rng(33)
+    conc = np.asfortranarray(rng.uniform(0, 25, (m.nfields, 5)))
+    niter, indvar = [11, 7, 11, 3, 11], [1, 2, 3, 4, 5]
+    ref = oracle.diffChangePar(m.mat_in, m.mat_out, conc, niter, indvar, 2)
+    for devices in ([0, 1], [1, 0, 1]):
+        got, _ = _run(m, conc, niter, indvar, devices)
+        assert np.array_equal(got, ref)
+
+
+def test_slab_errors_mirror_the_field(harbor_mesh):
+    m = harbor_mesh
+    sf = eb.SlabField(m.mat_in, m.mat_out, 3, [0, 0])
+    with pytest.raises(eb.EutropiaIndexError):
+        sf.diffuse([2], [4])                                     # column outside 1..C
+    with pytest.raises(eb.EutropiaError):
+        sf.diffuse([2, 2], [1, 1])                               # duplicate column
+    sf.diffuse([0], [99])                                        # never dereferenced with zero substeps
+    sf.close()
+    with pytest.raises(eb.EutropiaError):
+        eb.SlabField(m.mat_in, m.mat_out, 3, [0, 77])
