@@ -191,6 +191,7 @@ struct eut_field {
     cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
     bool in_lanes = false;             // a lane launch is being issued (stencil_seg.cu slices the columns coarser)
     bool no_split = false;             // set by the one-shot pipeline, which uses lane[0] itself
+    bool lane_shape = false;           // the caller runs column groups side by side itself (slab.cu): slice the columns as inside lanes
     // the tables the substep launch reads (default: d_act; the column-streaming pipeline points them
     // at a ring of per-launch tables)
     const int32_t *act_col = nullptr, *act_par = nullptr;

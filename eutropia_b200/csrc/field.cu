@@ -328,7 +328,7 @@ int field_diffuse(eut_field *f, const int32_t *niter, const int32_t *indvar, int
         }
         int n_act[kMaxLanes];
         for (int l = 0; l < L; l++) n_act[l] = lane_begin[l + 1] - lane_begin[l];
-        f->in_lanes = L > 1;
+        f->in_lanes = L > 1 || f->lane_shape;
         for (int s = 0; s < max_it; s++) {
             for (int l = 0; l < L; l++) {
                 const int b = lane_begin[l];

@@ -48,7 +48,7 @@ struct eut_slab {
         int64_t n = 0;
         std::vector<int32_t> src_local, dst_local;   // local ids (0-based) on either side, ascending global id
         int32_t *d_spos = nullptr, *d_dpos = nullptr;  // internal positions, resident on the SOURCE device
-        cudaEvent_t done = nullptr;
+        cudaEvent_t done[2] = {nullptr, nullptr};      // per column group
     };
     struct Part {
         int device = 0;
@@ -57,8 +57,9 @@ struct eut_slab {
         std::vector<uint8_t> is_own;
         eut_plan *plan = nullptr;
         eut_field *field = nullptr;
-        int32_t *d_order = nullptr;              // [C] columns of the current diffuse call, most substeps first
-        cudaEvent_t stepped = nullptr;
+        int32_t *d_order = nullptr;              // [C] columns of the current diffuse call: group 0, then group 1, most substeps first
+        cudaEvent_t stepped[2] = {nullptr, nullptr}, fork = nullptr, join = nullptr;
+        cudaStream_t gs[2] = {nullptr, nullptr}; // the stream of either column group (the field's own, its first lane)
     };
     int64_t N = 0, C = 0;
     std::vector<Part> parts;
@@ -75,14 +76,16 @@ void slab_free(eut_slab *s)
     for (auto &l : s->links) {
         cudaSetDevice(s->parts[l.src].device);
         cudaFree(l.d_spos); cudaFree(l.d_dpos);
-        if (l.done) cudaEventDestroy(l.done);
+        for (cudaEvent_t e : l.done) if (e) cudaEventDestroy(e);
     }
     for (auto &p : s->parts) {
         if (p.field) field_destroy(p.field);
         if (p.plan) { plan_free(p.plan); delete p.plan; }
         cudaSetDevice(p.device);
         cudaFree(p.d_order);
-        if (p.stepped) cudaEventDestroy(p.stepped);
+        for (cudaEvent_t e : p.stepped) if (e) cudaEventDestroy(e);
+        if (p.fork) cudaEventDestroy(p.fork);
+        if (p.join) cudaEventDestroy(p.join);
     }
     delete s;
 }
@@ -95,41 +98,42 @@ int upload_i32(int device, const std::vector<int32_t> &h, int32_t **d)
     return EUT_OK;
 }
 
-// current values of the first n_act columns of the call's order travel along every link
-int push_halos(eut_slab *s, int n_act)
+// current values of the first n_act columns of group g (table offset `first`) travel along every link
+int push_halos(eut_slab *s, int g, int first, int n_act)
 {
+    if (n_act == 0) return EUT_OK;
     for (auto &l : s->links) {
         eut_slab::Part &a = s->parts[l.src], &b = s->parts[l.dst];
-        if (l.n == 0 || n_act == 0) continue;
+        if (l.n == 0) continue;
         EUT_TRY(ensure_device(a.device));
         // the destination's substep has copied its ghost cells forward (a push that lands earlier would be
         // overwritten with the stale value); the source's own substep precedes the push on its stream
-        EUT_CUDA(cudaStreamWaitEvent(a.field->stream, b.stepped, 0));
+        EUT_CUDA(cudaStreamWaitEvent(a.gs[g], b.stepped[g], 0));
         dim3 grid((unsigned)((l.n + 255) / 256), (unsigned)n_act, 1);
-        k_halo_push<<<grid, 256, 0, a.field->stream>>>(a.field->d_buf, a.plan->Np, a.field->C * a.plan->Np, b.field->d_buf,
-                                                        b.plan->Np, b.field->C * b.plan->Np, a.field->d_cur, a.d_order,
-                                                        l.d_spos, l.d_dpos, (int)l.n);
+        k_halo_push<<<grid, 256, 0, a.gs[g]>>>(a.field->d_buf, a.plan->Np, a.field->C * a.plan->Np, b.field->d_buf,
+                                                b.plan->Np, b.field->C * b.plan->Np, a.field->d_cur, a.d_order + first,
+                                                l.d_spos, l.d_dpos, (int)l.n);
         EUT_CUDA(cudaGetLastError());
-        EUT_CUDA(cudaEventRecord(l.done, a.field->stream));
+        EUT_CUDA(cudaEventRecord(l.done[g], a.gs[g]));
         a.field->launches++;
         s->pushes++;
     }
     // nobody reads its ghost cells before they have arrived
     for (auto &l : s->links) {
-        if (l.n == 0 || n_act == 0) continue;
+        if (l.n == 0) continue;
         eut_slab::Part &b = s->parts[l.dst];
         EUT_TRY(ensure_device(b.device));
-        EUT_CUDA(cudaStreamWaitEvent(b.field->stream, l.done, 0));
+        EUT_CUDA(cudaStreamWaitEvent(b.gs[g], l.done[g], 0));
         b.field->version++;
     }
     return EUT_OK;
 }
 
-int mark_stepped(eut_slab *s)
+int mark_stepped(eut_slab *s, int g)
 {
     for (auto &p : s->parts) {
         EUT_TRY(ensure_device(p.device));
-        EUT_CUDA(cudaEventRecord(p.stepped, p.field->stream));
+        EUT_CUDA(cudaEventRecord(p.stepped[g], p.gs[g]));
     }
     return EUT_OK;
 }
@@ -221,7 +225,11 @@ int eut_slab_create(eut_slab **out, const int32_t *from, const int32_t *to, int6
         EUT_TRY(field_create(&P.field, P.plan, n_cols));
         P.field->copy_threads = std::max(1u, std::min(8u, host_thread_budget() / (2u * (unsigned)W)));
         EUT_CUDA(cudaMalloc((void **)&P.d_order, std::max<int64_t>(n_cols, 1) * sizeof(int32_t)));
-        EUT_CUDA(cudaEventCreateWithFlags(&P.stepped, cudaEventDisableTiming));
+        for (int g = 0; g < 2; g++) EUT_CUDA(cudaEventCreateWithFlags(&P.stepped[g], cudaEventDisableTiming));
+        EUT_CUDA(cudaEventCreateWithFlags(&P.fork, cudaEventDisableTiming));
+        EUT_CUDA(cudaEventCreateWithFlags(&P.join, cudaEventDisableTiming));
+        if (!P.field->lane[0]) EUT_CUDA(cudaStreamCreateWithFlags(&P.field->lane[0], cudaStreamNonBlocking));
+        P.gs[0] = P.field->stream; P.gs[1] = P.field->lane[0];
         return EUT_OK;
     };
     {
@@ -254,7 +262,8 @@ int eut_slab_create(eut_slab **out, const int32_t *from, const int32_t *to, int6
             }
             int rc = upload_i32(s->parts[a].device, sp, &L.d_spos);
             if (rc == EUT_OK) rc = upload_i32(s->parts[a].device, dp, &L.d_dpos);
-            if (rc == EUT_OK && cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming) != cudaSuccess) rc = EUT_ERR_CUDA;
+            for (int g = 0; g < 2 && rc == EUT_OK; g++)
+                if (cudaEventCreateWithFlags(&L.done[g], cudaEventDisableTiming) != cudaSuccess) rc = EUT_ERR_CUDA;
             if (rc != EUT_OK) { slab_free(s); return rc; }
             s->links.push_back(std::move(L));
         }
@@ -381,25 +390,58 @@ int eut_slab_diffuse(eut_slab *s, const int32_t *niter, const int32_t *indvar, i
     if (order.empty()) return EUT_OK;
     std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return niter[a] > niter[b]; });
     const int n_tot = (int)order.size();
+    // Two column groups with independent substep -> halo -> substep pipelines on two streams per slab: a
+    // substep of one group cannot start before its halo has arrived, and meanwhile the other group's
+    // substep keeps the SMs busy (it also fills the partial last wave of CTAs, like the lanes of a plain
+    // field).  Columns are dealt out round robin, so each group keeps the descending substep counts.
+    const char *ge = getenv("EUT_SLAB_GROUPS");
+    const int G = (n_tot >= 32 && !(ge && atoi(ge) == 1)) ? 2 : 1;
+    int gbeg[3] = {0, (n_tot + G - 1) / G, n_tot};
+    if (G == 1) gbeg[1] = n_tot;
+    std::vector<int64_t> dealt;
+    for (int g = 0; g < G; g++)
+        for (int a = g; a < n_tot; a += G) dealt.push_back(order[a]);
     s->h_order.resize(n_tot);
     std::vector<int32_t> cols1(n_tot), ones(n_tot, 1);
-    for (int a = 0; a < n_tot; a++) { s->h_order[a] = indvar[order[a]] - 1; cols1[a] = indvar[order[a]]; }
+    for (int a = 0; a < n_tot; a++) { s->h_order[a] = indvar[dealt[a]] - 1; cols1[a] = indvar[dealt[a]]; }
     for (auto &p : s->parts) {
         EUT_TRY(ensure_device(p.device));
-        EUT_CUDA(cudaMemcpyAsync(p.d_order, s->h_order.data(), n_tot * sizeof(int32_t), cudaMemcpyHostToDevice, p.field->stream));
+        EUT_CUDA(cudaMemcpyAsync(p.d_order, s->h_order.data(), n_tot * sizeof(int32_t), cudaMemcpyHostToDevice, p.gs[0]));
+        if (G == 2) {                                // group 1's stream starts after whatever the field's stream holds
+            EUT_CUDA(cudaEventRecord(p.fork, p.gs[0]));
+            EUT_CUDA(cudaStreamWaitEvent(p.gs[1], p.fork, 0));
+        }
     }
+    struct Restore {                                 // the fields run on their own stream outside this call
+        eut_slab *s;
+        ~Restore() { for (auto &p : s->parts) { p.field->stream = p.gs[0]; p.field->act_base = 0; p.field->no_split = false; p.field->lane_shape = false; } }
+    } restore{s};
     // ghosts up to date before the first substep (an upload or anything else may have changed owned values)
-    EUT_TRY(mark_stepped(s));
-    EUT_TRY(push_halos(s, n_tot));
-    const int max_it = niter[order[0]];
-    int n_act = n_tot;
-    for (int it = 0; it < max_it; it++) {
-        while (n_act > 0 && niter[order[n_act - 1]] <= it) n_act--;
-        if (n_act == 0) break;
-        for (auto &p : s->parts) EUT_TRY(field_diffuse(p.field, ones.data(), cols1.data(), n_act));
-        EUT_TRY(mark_stepped(s));
-        EUT_TRY(push_halos(s, n_act));
+    for (int g = 0; g < G; g++) {
+        EUT_TRY(mark_stepped(s, g));
+        EUT_TRY(push_halos(s, g, gbeg[g], gbeg[g + 1] - gbeg[g]));
     }
+    const int max_it = niter[dealt[0]];
+    int n_act[2] = {gbeg[1] - gbeg[0], gbeg[2] - gbeg[1]};
+    for (int it = 0; it < max_it; it++) {
+        for (int g = 0; g < G; g++) {
+            while (n_act[g] > 0 && niter[dealt[gbeg[g] + n_act[g] - 1]] <= it) n_act[g]--;
+            if (n_act[g] == 0) continue;
+            for (auto &p : s->parts) {
+                eut_field *f = p.field;
+                f->stream = p.gs[g]; f->act_base = gbeg[g]; f->no_split = true; f->lane_shape = (G == 2);
+                EUT_TRY(field_diffuse(f, ones.data(), cols1.data() + gbeg[g], n_act[g]));
+            }
+            EUT_TRY(mark_stepped(s, g));
+            EUT_TRY(push_halos(s, g, gbeg[g], n_act[g]));
+        }
+    }
+    if (G == 2)
+        for (auto &p : s->parts) {
+            EUT_TRY(ensure_device(p.device));
+            EUT_CUDA(cudaEventRecord(p.join, p.gs[1]));
+            EUT_CUDA(cudaStreamWaitEvent(p.gs[0], p.join, 0));
+        }
     return EUT_OK;
 }
 

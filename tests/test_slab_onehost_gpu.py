@@ -60,6 +60,24 @@ def test_slabs_match_the_unsharded_field_on_a_large_mesh():
     assert info.segmented == 1
 
 
+def test_two_column_groups_pipeline_matches_oracle(harbor_mesh):
+    """From 32 columns on, the slab driver runs two column groups as independent substep -> halo ->
+    substep pipelines on two streams per slab; mixed substep counts make the groups shrink at different times."""
+    m = harbor_mesh
+    rng = np.random.default_rng(34)
+    c = 40
+    conc = np.asfortranarray(rng.uniform(0, 25, (m.nfields, c)))
+    niter = rng.integers(0, 9, c).astype(np.int32)
+    niter[:4] = [8, 8, 1, 0]
+    indvar = rng.permutation(c).astype(np.int32) + 1
+    ref = oracle.diffChangePar(m.mat_in, m.mat_out, conc, niter, indvar, 4)
+    n_dev = _lib.lib().eut_device_count()
+    got, info = _run(m, conc, niter, indvar, [k % n_dev for k in range(3)])
+    assert np.array_equal(got, ref)
+    got, _ = _run(m, conc, niter, indvar, [0], rounds=1)
+    assert np.array_equal(got, ref)
+
+
 def test_slabs_on_two_devices_match_oracle(harbor_mesh):
     if _lib.lib().eut_device_count() < 2:
         pytest.skip("needs two GPUs")
