@@ -27,14 +27,16 @@ namespace eut {
 
 __global__ void __launch_bounds__(256)
 k_halo_push(const double *__restrict__ src, const int64_t src_cs, const int64_t src_bs, double *__restrict__ dst,
-            const int64_t dst_cs, const int64_t dst_bs, const int32_t *__restrict__ cur,
-            const int32_t *__restrict__ cols, const int32_t *__restrict__ spos, const int32_t *__restrict__ dpos,
-            const int n)
+            const int64_t dst_cs, const int64_t dst_bs, const int32_t *__restrict__ par,
+            const int32_t *__restrict__ cols, const int steps_done, const int32_t *__restrict__ spos,
+            const int32_t *__restrict__ dpos, const int n)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const int c = cols[blockIdx.y];
-    const int64_t b = cur[c];                    // every slab is at the same substep: same buffer on both sides
+    // buffer that holds the column after `steps_done` substeps of this call (table: buffer at the start);
+    // every slab is at the same substep, so it is the same buffer on both sides
+    const int64_t b = (par[blockIdx.y] + steps_done) & 1;
     dst[b * dst_bs + (int64_t)c * dst_cs + dpos[k]] = src[b * src_bs + (int64_t)c * src_cs + spos[k]];
 }
 
@@ -57,17 +59,22 @@ struct eut_slab {
         std::vector<uint8_t> is_own;
         eut_plan *plan = nullptr;
         eut_field *field = nullptr;
-        int32_t *d_order = nullptr;              // [C] columns of the current diffuse call: group 0, then group 1, most substeps first
         cudaEvent_t stepped[2] = {nullptr, nullptr}, fork = nullptr, join = nullptr;
         cudaStream_t gs[2] = {nullptr, nullptr}; // the stream of either column group (the field's own, its first lane)
     };
     int64_t N = 0, C = 0;
     std::vector<Part> parts;
     std::vector<Link> links;
-    std::vector<int32_t> h_order;
     int64_t pushes = 0;
     double build_ms = 0;
+    // substep loops seen before, captured as ONE CUDA graph over all slabs, streams and devices
+    std::map<uint64_t, cudaGraphExec_t> graphs;
+    std::map<uint64_t, int64_t> graph_launches;   // kernels one replay stands for
+    std::set<uint64_t> graph_seen;
+    cudaEvent_t ev_origin = nullptr;
 };
+
+extern "C" int64_t eut_slab_launch_count(const eut_slab *s);
 
 namespace {
 
@@ -82,11 +89,12 @@ void slab_free(eut_slab *s)
         if (p.field) field_destroy(p.field);
         if (p.plan) { plan_free(p.plan); delete p.plan; }
         cudaSetDevice(p.device);
-        cudaFree(p.d_order);
         for (cudaEvent_t e : p.stepped) if (e) cudaEventDestroy(e);
         if (p.fork) cudaEventDestroy(p.fork);
         if (p.join) cudaEventDestroy(p.join);
     }
+    for (auto &g : s->graphs) if (g.second) cudaGraphExecDestroy(g.second);
+    if (s->ev_origin) cudaEventDestroy(s->ev_origin);
     delete s;
 }
 
@@ -99,7 +107,7 @@ int upload_i32(int device, const std::vector<int32_t> &h, int32_t **d)
 }
 
 // current values of the first n_act columns of group g (table offset `first`) travel along every link
-int push_halos(eut_slab *s, int g, int first, int n_act)
+int push_halos(eut_slab *s, int g, int first, int n_act, int steps_done)
 {
     if (n_act == 0) return EUT_OK;
     for (auto &l : s->links) {
@@ -110,9 +118,10 @@ int push_halos(eut_slab *s, int g, int first, int n_act)
         // overwritten with the stale value); the source's own substep precedes the push on its stream
         EUT_CUDA(cudaStreamWaitEvent(a.gs[g], b.stepped[g], 0));
         dim3 grid((unsigned)((l.n + 255) / 256), (unsigned)n_act, 1);
-        k_halo_push<<<grid, 256, 0, a.gs[g]>>>(a.field->d_buf, a.plan->Np, a.field->C * a.plan->Np, b.field->d_buf,
-                                                b.plan->Np, b.field->C * b.plan->Np, a.field->d_cur, a.d_order + first,
-                                                l.d_spos, l.d_dpos, (int)l.n);
+        const eut_field *fa = a.field;
+        k_halo_push<<<grid, 256, 0, a.gs[g]>>>(fa->d_buf, a.plan->Np, fa->C * a.plan->Np, b.field->d_buf, b.plan->Np,
+                                                b.field->C * b.plan->Np, fa->d_act + fa->act_cap + first, fa->d_act + first,
+                                                steps_done, l.d_spos, l.d_dpos, (int)l.n);
         EUT_CUDA(cudaGetLastError());
         EUT_CUDA(cudaEventRecord(l.done[g], a.gs[g]));
         a.field->launches++;
@@ -124,7 +133,6 @@ int push_halos(eut_slab *s, int g, int first, int n_act)
         eut_slab::Part &b = s->parts[l.dst];
         EUT_TRY(ensure_device(b.device));
         EUT_CUDA(cudaStreamWaitEvent(b.gs[g], l.done[g], 0));
-        b.field->version++;
     }
     return EUT_OK;
 }
@@ -224,7 +232,6 @@ int eut_slab_create(eut_slab **out, const int32_t *from, const int32_t *to, int6
         EUT_TRY(plan_build(P.plan, lf.data(), lt.data(), n_in, id.data(), cnt.data(), P.n_local, P.n_local, P.device, EUT_ORDER_AUTO));
         EUT_TRY(field_create(&P.field, P.plan, n_cols));
         P.field->copy_threads = std::max(1u, std::min(8u, host_thread_budget() / (2u * (unsigned)W)));
-        EUT_CUDA(cudaMalloc((void **)&P.d_order, std::max<int64_t>(n_cols, 1) * sizeof(int32_t)));
         for (int g = 0; g < 2; g++) EUT_CUDA(cudaEventCreateWithFlags(&P.stepped[g], cudaEventDisableTiming));
         EUT_CUDA(cudaEventCreateWithFlags(&P.fork, cudaEventDisableTiming));
         EUT_CUDA(cudaEventCreateWithFlags(&P.join, cudaEventDisableTiming));
@@ -267,6 +274,7 @@ int eut_slab_create(eut_slab **out, const int32_t *from, const int32_t *to, int6
             if (rc != EUT_OK) { slab_free(s); return rc; }
             s->links.push_back(std::move(L));
         }
+    if (ensure_device(s->parts[0].device) != EUT_OK || cudaEventCreateWithFlags(&s->ev_origin, cudaEventDisableTiming) != cudaSuccess) { slab_free(s); return EUT_ERR_CUDA; }
     s->build_ms = now_ms() - t0;
     *out = s;
     return EUT_OK;
@@ -401,47 +409,130 @@ int eut_slab_diffuse(eut_slab *s, const int32_t *niter, const int32_t *indvar, i
     std::vector<int64_t> dealt;
     for (int g = 0; g < G; g++)
         for (int a = g; a < n_tot; a += G) dealt.push_back(order[a]);
-    s->h_order.resize(n_tot);
-    std::vector<int32_t> cols1(n_tot), ones(n_tot, 1);
-    for (int a = 0; a < n_tot; a++) { s->h_order[a] = indvar[dealt[a]] - 1; cols1[a] = indvar[dealt[a]]; }
+    // launch tables of every slab (as field_diffuse: column, buffer at the start, buffer at the end), rows at
+    // [0, n_tot) in the dealt order -- read by the kernels, so a captured loop does not depend on them
     for (auto &p : s->parts) {
+        eut_field *f = p.field;
         EUT_TRY(ensure_device(p.device));
-        EUT_CUDA(cudaMemcpyAsync(p.d_order, s->h_order.data(), n_tot * sizeof(int32_t), cudaMemcpyHostToDevice, p.gs[0]));
-        if (G == 2) {                                // group 1's stream starts after whatever the field's stream holds
-            EUT_CUDA(cudaEventRecord(p.fork, p.gs[0]));
-            EUT_CUDA(cudaStreamWaitEvent(p.gs[1], p.fork, 0));
+        if (n_tot > f->act_cap) { set_error("eut_slab_diffuse: table range out of bounds"); return EUT_ERR_ARG; }
+        for (int a = 0; a < n_tot; a++) {
+            const int c = indvar[dealt[a]] - 1;
+            f->h_act[a] = c;
+            f->h_act[f->act_cap + a] = f->cur[c];
+            f->h_act[2 * f->act_cap + a] = (f->cur[c] + niter[dealt[a]]) & 1;
         }
+        for (int r = 0; r < 3; r++)
+            EUT_CUDA(cudaMemcpyAsync(f->d_act + r * f->act_cap, f->h_act.data() + r * f->act_cap, n_tot * sizeof(int32_t),
+                                     cudaMemcpyHostToDevice, p.gs[0]));
+        // group 1's stream, and the first slab's stream (every other stream starts behind it, and a captured
+        // loop is launched into it): after the tables and whatever this field's stream holds
+        EUT_CUDA(cudaEventRecord(p.fork, p.gs[0]));
+        EUT_CUDA(cudaStreamWaitEvent(p.gs[1], p.fork, 0));
+        if (p.gs[0] != s->parts[0].gs[0]) EUT_CUDA(cudaStreamWaitEvent(s->parts[0].gs[0], p.fork, 0));
     }
     struct Restore {                                 // the fields run on their own stream outside this call
         eut_slab *s;
-        ~Restore() { for (auto &p : s->parts) { p.field->stream = p.gs[0]; p.field->act_base = 0; p.field->no_split = false; p.field->lane_shape = false; } }
+        ~Restore() { for (auto &p : s->parts) { p.field->stream = p.gs[0]; p.field->act_col = p.field->d_act; p.field->act_par = p.field->d_act + p.field->act_cap; p.field->in_lanes = false; } }
     } restore{s};
-    // ghosts up to date before the first substep (an upload or anything else may have changed owned values)
-    for (int g = 0; g < G; g++) {
-        EUT_TRY(mark_stepped(s, g));
-        EUT_TRY(push_halos(s, g, gbeg[g], gbeg[g + 1] - gbeg[g]));
-    }
     const int max_it = niter[dealt[0]];
-    int n_act[2] = {gbeg[1] - gbeg[0], gbeg[2] - gbeg[1]};
-    for (int it = 0; it < max_it; it++) {
+    cudaStream_t origin = s->parts[0].gs[0];
+    auto run_loop = [&]() -> int {
+        // every stream starts behind the first slab's stream (in a capture: joins it) ...
+        EUT_TRY(ensure_device(s->parts[0].device));
+        EUT_CUDA(cudaEventRecord(s->ev_origin, origin));
+        for (auto &p : s->parts)
+            for (int g = 0; g < 2; g++)
+                if (p.gs[g] != origin) EUT_CUDA(cudaStreamWaitEvent(p.gs[g], s->ev_origin, 0));
+        // ghosts up to date before the first substep (an upload or anything else may have changed owned values)
         for (int g = 0; g < G; g++) {
-            while (n_act[g] > 0 && niter[dealt[gbeg[g] + n_act[g] - 1]] <= it) n_act[g]--;
-            if (n_act[g] == 0) continue;
-            for (auto &p : s->parts) {
-                eut_field *f = p.field;
-                f->stream = p.gs[g]; f->act_base = gbeg[g]; f->no_split = true; f->lane_shape = (G == 2);
-                EUT_TRY(field_diffuse(f, ones.data(), cols1.data() + gbeg[g], n_act[g]));
-            }
             EUT_TRY(mark_stepped(s, g));
-            EUT_TRY(push_halos(s, g, gbeg[g], n_act[g]));
+            EUT_TRY(push_halos(s, g, gbeg[g], gbeg[g + 1] - gbeg[g], 0));
         }
-    }
-    if (G == 2)
+        int n_act[2] = {gbeg[1] - gbeg[0], gbeg[2] - gbeg[1]};
+        for (int it = 0; it < max_it; it++) {
+            for (int g = 0; g < G; g++) {
+                while (n_act[g] > 0 && niter[dealt[gbeg[g] + n_act[g] - 1]] <= it) n_act[g]--;
+                if (n_act[g] == 0) continue;
+                for (auto &p : s->parts) {
+                    eut_field *f = p.field;
+                    EUT_TRY(ensure_device(p.device));
+                    f->stream = p.gs[g]; f->in_lanes = (G == 2);
+                    f->act_col = f->d_act + gbeg[g]; f->act_par = f->d_act + f->act_cap + gbeg[g];
+                    EUT_TRY(launch_substep(f, n_act[g], it));
+                }
+                EUT_TRY(mark_stepped(s, g));
+                EUT_TRY(push_halos(s, g, gbeg[g], n_act[g], it + 1));
+            }
+        }
+        // ... and ends in it: device mirror of "which buffer holds column c", then the joins
         for (auto &p : s->parts) {
+            eut_field *f = p.field;
             EUT_TRY(ensure_device(p.device));
+            f->stream = p.gs[0];
             EUT_CUDA(cudaEventRecord(p.join, p.gs[1]));
             EUT_CUDA(cudaStreamWaitEvent(p.gs[0], p.join, 0));
+            EUT_TRY(launch_set_cur(f, f->d_act, f->d_act + 2 * f->act_cap, n_tot));
+            if (p.gs[0] != origin) {
+                EUT_CUDA(cudaEventRecord(p.stepped[0], p.gs[0]));
+                EUT_CUDA(cudaStreamWaitEvent(origin, p.stepped[0], 0));
+            }
         }
+        return EUT_OK;
+    };
+    // A loop shape that comes back (R diffuses the same columns every round) is captured the second time it
+    // is seen -- one graph over all slabs, both streams of each and all devices -- and replayed from then
+    // on: one thread issuing ~60 launches, event records and waits per substep for eight GPUs is slower
+    // than the GPUs are.
+    static const bool no_graphs = getenv("EUT_NO_GRAPHS") != nullptr;
+    uint64_t key = 0xcbf29ce484222325ull;
+    auto mix = [&](uint64_t v) { key = (key ^ v) * 0x100000001b3ull; };
+    for (int a = 0; a < n_tot; a++) mix((uint64_t)niter[dealt[a]]);
+    mix((uint64_t)G);
+    for (auto &p : s->parts) { mix((uint64_t)p.field->opt_cpt); mix((uint64_t)p.field->opt_variant); mix((uint64_t)p.field->opt_shape); mix((uint64_t)p.field->opt_debug); }
+    const auto hit = s->graphs.find(key);
+    EUT_TRY(ensure_device(s->parts[0].device));
+    if (hit != s->graphs.end() && hit->second) {
+        EUT_CUDA(cudaGraphLaunch(hit->second, origin));
+        s->parts[0].field->launches += s->graph_launches[key];
+    } else if (hit == s->graphs.end() && !no_graphs && max_it >= 4 && s->graph_seen.count(key) && s->graphs.size() < 16) {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        const int64_t l0 = eut_slab_launch_count(s);
+        EUT_CUDA(cudaStreamBeginCapture(origin, cudaStreamCaptureModeThreadLocal));
+        const int rc = run_loop();
+        s->graph_launches[key] = eut_slab_launch_count(s) - l0;
+        EUT_TRY(ensure_device(s->parts[0].device));
+        const cudaError_t ce = cudaStreamEndCapture(origin, &graph);
+        bool ok = rc == EUT_OK && ce == cudaSuccess && graph;
+        if (ok && cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) ok = false;
+        if (graph) cudaGraphDestroy(graph);
+        if (!ok) {
+            (void)cudaGetLastError();
+            s->graphs[key] = nullptr;                        // do not try again
+            EUT_TRY(run_loop());
+        } else {
+            s->graphs[key] = exec;
+            EUT_CUDA(cudaGraphLaunch(exec, origin));
+        }
+    } else {
+        s->graph_seen.insert(key);
+        EUT_TRY(run_loop());
+    }
+    // what the slabs' own streams are given next (a download, the next call's tables) comes after the loop,
+    // which ends in the first slab's stream
+    EUT_TRY(ensure_device(s->parts[0].device));
+    EUT_CUDA(cudaEventRecord(s->ev_origin, origin));
+    for (auto &p : s->parts)
+        if (p.gs[0] != origin) EUT_CUDA(cudaStreamWaitEvent(p.gs[0], s->ev_origin, 0));
+    for (auto &p : s->parts) {
+        eut_field *f = p.field;
+        for (int a = 0; a < n_tot; a++) {
+            const int c = indvar[dealt[a]] - 1;
+            f->cur[c] = (uint8_t)((f->cur[c] + niter[dealt[a]]) & 1);
+            f->h_cur32[c] = f->cur[c];
+        }
+        f->version++;
+    }
     return EUT_OK;
 }
 

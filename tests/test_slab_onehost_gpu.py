@@ -76,6 +76,12 @@ def test_two_column_groups_pipeline_matches_oracle(harbor_mesh):
     assert np.array_equal(got, ref)
     got, _ = _run(m, conc, niter, indvar, [0], rounds=1)
     assert np.array_equal(got, ref)
+    # the same call three times: plain launches, then captured as one graph over all slabs and streams, then replayed
+    ref3 = ref
+    for _ in range(2):
+        ref3 = oracle.diffChangePar(m.mat_in, m.mat_out, ref3, niter, indvar, 4)
+    got3, info3 = _run(m, conc, niter, indvar, [k % n_dev for k in range(3)], rounds=3)
+    assert np.array_equal(got3, ref3)
 
 
 def test_slabs_on_two_devices_match_oracle(harbor_mesh):
