@@ -87,6 +87,7 @@ static int decode_seg_tables(const eut_plan *p, const std::vector<int32_t> &meta
     row_ptr[0] = 0;
     for (int64_t i = 0; i < N; i++) {
         const int64_t q = p->perm[i];
+        if (!done[q] && !p->dead.empty() && p->dead[i]) { row_ptr[i + 1] = row_ptr[i]; deg[q] = 0; continue; }   // a ghost: no work by design
         if (!done[q] || deg[q] > 12) { set_error("eut_plan_get_csr: point %lld is not produced by any segment", (long long)i + 1); return EUT_ERR_UNSUPPORTED; }
         row_ptr[i + 1] = row_ptr[i] + deg[q];
     }

@@ -150,6 +150,9 @@ struct eut_plan {
     std::vector<int32_t> col;
     std::vector<int32_t> perm;   // reference id (0-based) -> internal position
     std::vector<int32_t> iperm;  // internal position -> reference id (0-based), -1 for padding
+    // points nobody computes (set before plan_build by slab.cu: ghost copies of a neighbour slab's points,
+    // overwritten after every substep): the segment planner gives them a cell but no work
+    std::vector<uint8_t> dead;
 
     // device, internal order
     int32_t *d_nbr = nullptr;    // [ell_w][Np] internal ids of in-neighbours, mat.in order

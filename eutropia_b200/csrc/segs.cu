@@ -402,6 +402,9 @@ int build_segs(eut_plan *p, const SegParams &sp)
     struct Rec { int cls; uint16_t w[24]; };
     std::vector<Rec> recs;
     std::vector<int32_t> tgens;
+    // dead points (ghosts of a slab) keep their cell -- neighbours read it -- but get neither a segment nor a
+    // generic record: their result cell stays +0.0 like a gap cell, and the halo exchange fills it in
+    auto is_dead = [&](int32_t i) { return !p->dead.empty() && p->dead[i] != 0; };
     auto emit = [&](int32_t g, int32_t s, int32_t len) {
         if ((g ^ s) & 1) {      // parities differ: no 16-byte aligned pairing exists
             for (int32_t k = 0; k < len; k++) single.push_back({g + k, s + k});
@@ -566,7 +569,7 @@ int build_segs(eut_plan *p, const SegParams &sp)
                     if (!placed) len--;
                 }
                 if (placed) { recs.push_back(rec); S.seg_points += len; i += len; }
-                else { tgens.push_back(i); i++; }
+                else { if (!is_dead(i)) tgens.push_back(i); i++; }
             }
         }
         // Lane assignment.  Lanes of a warp should run the same stream set (class), and the 16 lanes of
@@ -614,7 +617,7 @@ int build_segs(eut_plan *p, const SegParams &sp)
         while ((int32_t)recs.size() > sp.max_tile_segs) {
             const Rec &rc = recs.back();
             const int32_t q0 = t0 + (rc.w[7] & 0xfff) - (t0 & 1), len = rc.w[7] >> 12;
-            for (int32_t j = 0; j < len; j++) tgens.push_back(p->iperm[q0 + j]);
+            for (int32_t j = 0; j < len; j++) if (!is_dead(p->iperm[q0 + j])) tgens.push_back(p->iperm[q0 + j]);
             S.seg_points -= len;
             recs.pop_back();
         }

@@ -110,6 +110,9 @@ int upload_i32(int device, const std::vector<int32_t> &h, int32_t **d)
 int push_halos(eut_slab *s, int g, int first, int n_act, int steps_done)
 {
     if (n_act == 0) return EUT_OK;
+    // timing experiments only (results are wrong): 1 = no halo kernels, 2 = no waits between slabs either
+    static const int dbg = [] { const char *e = getenv("EUT_SLAB_DEBUG"); return e ? atoi(e) : 0; }();
+    if (dbg & 2) return EUT_OK;
     for (auto &l : s->links) {
         eut_slab::Part &a = s->parts[l.src], &b = s->parts[l.dst];
         if (l.n == 0) continue;
@@ -119,7 +122,7 @@ int push_halos(eut_slab *s, int g, int first, int n_act, int steps_done)
         EUT_CUDA(cudaStreamWaitEvent(a.gs[g], b.stepped[g], 0));
         dim3 grid((unsigned)((l.n + 255) / 256), (unsigned)n_act, 1);
         const eut_field *fa = a.field;
-        k_halo_push<<<grid, 256, 0, a.gs[g]>>>(fa->d_buf, a.plan->Np, fa->C * a.plan->Np, b.field->d_buf, b.plan->Np,
+        if (!(dbg & 1)) k_halo_push<<<grid, 256, 0, a.gs[g]>>>(fa->d_buf, a.plan->Np, fa->C * a.plan->Np, b.field->d_buf, b.plan->Np,
                                                 b.field->C * b.plan->Np, fa->d_act + fa->act_cap + first, fa->d_act + first,
                                                 steps_done, l.d_spos, l.d_dpos, (int)l.n);
         EUT_CUDA(cudaGetLastError());
@@ -229,6 +232,10 @@ int eut_slab_create(eut_slab **out, const int32_t *from, const int32_t *to, int6
             if (owner[to[j] - 1] == r) { lf[o] = map[from[j] - 1] + 1; lt[o] = map[to[j] - 1] + 1; o++; }
         for (int64_t k = 0; k < P.n_local; k++) { id[k] = (int32_t)k + 1; cnt[k] = P.is_own[k] ? nn_by_id[P.local_global[k]] : 1; }
         P.plan = new eut_plan();
+        if (!getenv("EUT_SLAB_LIVE_GHOSTS")) {               // ghosts are overwritten after every substep: no work for them
+            P.plan->dead.resize(P.n_local);
+            for (int64_t k = 0; k < P.n_local; k++) P.plan->dead[k] = P.is_own[k] ? 0 : 1;
+        }
         EUT_TRY(plan_build(P.plan, lf.data(), lt.data(), n_in, id.data(), cnt.data(), P.n_local, P.n_local, P.device, EUT_ORDER_AUTO));
         EUT_TRY(field_create(&P.field, P.plan, n_cols));
         P.field->copy_threads = std::max(1u, std::min(8u, host_thread_budget() / (2u * (unsigned)W)));
@@ -435,6 +442,8 @@ int eut_slab_diffuse(eut_slab *s, const int32_t *niter, const int32_t *indvar, i
         ~Restore() { for (auto &p : s->parts) { p.field->stream = p.gs[0]; p.field->act_col = p.field->d_act; p.field->act_par = p.field->d_act + p.field->act_cap; p.field->in_lanes = false; } }
     } restore{s};
     const int max_it = niter[dealt[0]];
+    const char *se = getenv("EUT_SLAB_STAGGER");
+    const bool stagger = se && atoi(se) == 1;
     cudaStream_t origin = s->parts[0].gs[0];
     auto run_loop = [&]() -> int {
         // every stream starts behind the first slab's stream (in a capture: joins it) ...
@@ -456,7 +465,10 @@ int eut_slab_diffuse(eut_slab *s, const int32_t *niter, const int32_t *indvar, i
                 for (auto &p : s->parts) {
                     eut_field *f = p.field;
                     EUT_TRY(ensure_device(p.device));
-                    f->stream = p.gs[g]; f->in_lanes = (G == 2);
+                    // staggered groups: this group's substep starts when the other group's has finished, so the
+                    // halo exchange of one group runs under the substep of the other
+                    if (stagger && G == 2) EUT_CUDA(cudaStreamWaitEvent(p.gs[g], p.stepped[g ^ 1], 0));
+                    f->stream = p.gs[g]; f->in_lanes = (G == 2) && !stagger;
                     f->act_col = f->d_act + gbeg[g]; f->act_par = f->d_act + f->act_cap + gbeg[g];
                     EUT_TRY(launch_substep(f, n_act[g], it));
                 }
@@ -487,7 +499,7 @@ int eut_slab_diffuse(eut_slab *s, const int32_t *niter, const int32_t *indvar, i
     uint64_t key = 0xcbf29ce484222325ull;
     auto mix = [&](uint64_t v) { key = (key ^ v) * 0x100000001b3ull; };
     for (int a = 0; a < n_tot; a++) mix((uint64_t)niter[dealt[a]]);
-    mix((uint64_t)G);
+    mix((uint64_t)G); mix((uint64_t)stagger);
     for (auto &p : s->parts) { mix((uint64_t)p.field->opt_cpt); mix((uint64_t)p.field->opt_variant); mix((uint64_t)p.field->opt_shape); mix((uint64_t)p.field->opt_debug); }
     const auto hit = s->graphs.find(key);
     EUT_TRY(ensure_device(s->parts[0].device));

@@ -4,7 +4,7 @@
 // diffuse_compoundsPar / run_simulation keep `concentrations` on the GPU between rounds and pull
 // only what R reads.  External pointers own the C handles; R's GC releases them.
 //
-// Not compiled in this repository's image (no R / Rcpp here).
+// Compiled here against the stand-in rcpp/ref_shim/Rcpp.h (rcpp/Makefile); with R it builds against the real Rcpp.
 #include <Rcpp.h>
 
 #include <eutropia_b200.h>
@@ -33,13 +33,17 @@ SEXP eutb_field(SEXP plan, Rcpp::NumericMatrix conc)
 {
     eut_field *f = nullptr;
     check(eut_field_create(&f, PlanPtr(plan).get(), conc.ncol()));
-    check(eut_field_upload(f, conc.begin(), conc.nrow(), nullptr, conc.ncol()));
-    return FieldPtr(f, true);
+    const int rc = eut_field_upload(f, conc.begin(), conc.nrow(), nullptr, conc.ncol());
+    if (rc != EUT_OK) { eut_field_destroy(f); check(rc); }
+    // the field refers to the plan: the plan's external pointer sits in the prot slot, so R cannot
+    // finalise it before the field (eut_field_destroy dereferences the plan)
+    return FieldPtr(f, true, R_NilValue, plan);
 }
 
 // [[Rcpp::export]]
 void eutb_diffuse(SEXP field, Rcpp::IntegerVector niter, Rcpp::IntegerVector indvar)
 {
+    if (niter.size() < indvar.size()) Rcpp::stop("Mat::operator(): index out of bounds");   // niter(i), src/diffChange.cpp:48
     check(eut_field_diffuse(FieldPtr(field).get(), niter.begin(), indvar.begin(), indvar.size()));
 }
 
