@@ -25,13 +25,16 @@
 
 namespace eut {
 
-__global__ void __launch_bounds__(256)
+// Small blocks on purpose: a substep CTA of the other column group fills an SM's shared memory and all but
+// ~5 k of its registers, and the halo kernel has to slip in NEXT to it (64 threads x <= 32 registers do);
+// with 256-thread blocks it waited for a substep CTA to retire -- 25 us per substep on a 4-GPU run.
+__global__ void __launch_bounds__(64, 8)
 k_halo_push(const double *__restrict__ src, const int64_t src_cs, const int64_t src_bs, double *__restrict__ dst,
             const int64_t dst_cs, const int64_t dst_bs, const int32_t *__restrict__ par,
             const int32_t *__restrict__ cols, const int steps_done, const int32_t *__restrict__ spos,
             const int32_t *__restrict__ dpos, const int n)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.x * 64 + threadIdx.x;
     if (k >= n) return;
     const int c = cols[blockIdx.y];
     // buffer that holds the column after `steps_done` substeps of this call (table: buffer at the start);
@@ -44,13 +47,15 @@ k_halo_push(const double *__restrict__ src, const int64_t src_cs, const int64_t 
 
 using namespace eut;
 
+constexpr int kSlabGroups = 4;
+
 struct eut_slab {
     struct Link {                                // values of `n` points travel from part `src` to part `dst`
         int src = 0, dst = 0;
         int64_t n = 0;
         std::vector<int32_t> src_local, dst_local;   // local ids (0-based) on either side, ascending global id
         int32_t *d_spos = nullptr, *d_dpos = nullptr;  // internal positions, resident on the SOURCE device
-        cudaEvent_t done[2] = {nullptr, nullptr};      // per column group
+        cudaEvent_t done[kSlabGroups] = {};            // per column group
     };
     struct Part {
         int device = 0;
@@ -59,8 +64,9 @@ struct eut_slab {
         std::vector<uint8_t> is_own;
         eut_plan *plan = nullptr;
         eut_field *field = nullptr;
-        cudaEvent_t stepped[2] = {nullptr, nullptr}, fork = nullptr, join = nullptr;
-        cudaStream_t gs[2] = {nullptr, nullptr}; // the stream of either column group (the field's own, its first lane)
+        cudaEvent_t stepped[kSlabGroups] = {}, fork = nullptr, join[kSlabGroups] = {};
+        cudaStream_t gs[kSlabGroups] = {};       // the stream of every column group (the field's own, its lanes)
+        cudaStream_t ps[kSlabGroups] = {};       // high-priority streams of the halo kernels this slab sends
     };
     int64_t N = 0, C = 0;
     std::vector<Part> parts;
@@ -90,8 +96,9 @@ void slab_free(eut_slab *s)
         if (p.plan) { plan_free(p.plan); delete p.plan; }
         cudaSetDevice(p.device);
         for (cudaEvent_t e : p.stepped) if (e) cudaEventDestroy(e);
+        for (cudaStream_t st : p.ps) if (st) cudaStreamDestroy(st);
         if (p.fork) cudaEventDestroy(p.fork);
-        if (p.join) cudaEventDestroy(p.join);
+        for (cudaEvent_t e : p.join) if (e) cudaEventDestroy(e);
     }
     for (auto &g : s->graphs) if (g.second) cudaGraphExecDestroy(g.second);
     if (s->ev_origin) cudaEventDestroy(s->ev_origin);
@@ -117,25 +124,29 @@ int push_halos(eut_slab *s, int g, int first, int n_act, int steps_done)
         eut_slab::Part &a = s->parts[l.src], &b = s->parts[l.dst];
         if (l.n == 0) continue;
         EUT_TRY(ensure_device(a.device));
-        // the destination's substep has copied its ghost cells forward (a push that lands earlier would be
-        // overwritten with the stale value); the source's own substep precedes the push on its stream
-        EUT_CUDA(cudaStreamWaitEvent(a.gs[g], b.stepped[g], 0));
-        dim3 grid((unsigned)((l.n + 255) / 256), (unsigned)n_act, 1);
+        // the source's substep has produced the values; the destination's substep has written its ghost cells
+        // (a push that lands earlier would be overwritten)
+        EUT_CUDA(cudaStreamWaitEvent(a.ps[g], a.stepped[g], 0));
+        EUT_CUDA(cudaStreamWaitEvent(a.ps[g], b.stepped[g], 0));
+        dim3 grid((unsigned)((l.n + 63) / 64), (unsigned)n_act, 1);
         const eut_field *fa = a.field;
-        if (!(dbg & 1)) k_halo_push<<<grid, 256, 0, a.gs[g]>>>(fa->d_buf, a.plan->Np, fa->C * a.plan->Np, b.field->d_buf, b.plan->Np,
+        if (!(dbg & 1)) k_halo_push<<<grid, 64, 0, a.ps[g]>>>(fa->d_buf, a.plan->Np, fa->C * a.plan->Np, b.field->d_buf, b.plan->Np,
                                                 b.field->C * b.plan->Np, fa->d_act + fa->act_cap + first, fa->d_act + first,
                                                 steps_done, l.d_spos, l.d_dpos, (int)l.n);
         EUT_CUDA(cudaGetLastError());
-        EUT_CUDA(cudaEventRecord(l.done[g], a.gs[g]));
+        EUT_CUDA(cudaEventRecord(l.done[g], a.ps[g]));
         a.field->launches++;
         s->pushes++;
     }
-    // nobody reads its ghost cells before they have arrived
+    // nobody reads its ghost cells before they have arrived; and the sender does not run ahead of its own
+    // halo kernels (two substeps on it would overwrite the buffer they read)
     for (auto &l : s->links) {
         if (l.n == 0) continue;
-        eut_slab::Part &b = s->parts[l.dst];
+        eut_slab::Part &a = s->parts[l.src], &b = s->parts[l.dst];
         EUT_TRY(ensure_device(b.device));
         EUT_CUDA(cudaStreamWaitEvent(b.gs[g], l.done[g], 0));
+        EUT_TRY(ensure_device(a.device));
+        EUT_CUDA(cudaStreamWaitEvent(a.gs[g], l.done[g], 0));
     }
     return EUT_OK;
 }
@@ -239,11 +250,19 @@ int eut_slab_create(eut_slab **out, const int32_t *from, const int32_t *to, int6
         EUT_TRY(plan_build(P.plan, lf.data(), lt.data(), n_in, id.data(), cnt.data(), P.n_local, P.n_local, P.device, EUT_ORDER_AUTO));
         EUT_TRY(field_create(&P.field, P.plan, n_cols));
         P.field->copy_threads = std::max(1u, std::min(8u, host_thread_budget() / (2u * (unsigned)W)));
-        for (int g = 0; g < 2; g++) EUT_CUDA(cudaEventCreateWithFlags(&P.stepped[g], cudaEventDisableTiming));
+        for (int g = 0; g < kSlabGroups; g++) {
+            EUT_CUDA(cudaEventCreateWithFlags(&P.stepped[g], cudaEventDisableTiming));
+            EUT_CUDA(cudaEventCreateWithFlags(&P.join[g], cudaEventDisableTiming));
+        }
         EUT_CUDA(cudaEventCreateWithFlags(&P.fork, cudaEventDisableTiming));
-        EUT_CUDA(cudaEventCreateWithFlags(&P.join, cudaEventDisableTiming));
-        if (!P.field->lane[0]) EUT_CUDA(cudaStreamCreateWithFlags(&P.field->lane[0], cudaStreamNonBlocking));
-        P.gs[0] = P.field->stream; P.gs[1] = P.field->lane[0];
+        P.gs[0] = P.field->stream;
+        for (int g = 1; g < kSlabGroups; g++) {
+            if (!P.field->lane[g - 1]) EUT_CUDA(cudaStreamCreateWithFlags(&P.field->lane[g - 1], cudaStreamNonBlocking));
+            P.gs[g] = P.field->lane[g - 1];
+        }
+        int lo = 0, hi = 0;
+        EUT_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        for (int g = 0; g < kSlabGroups; g++) EUT_CUDA(cudaStreamCreateWithPriority(&P.ps[g], cudaStreamNonBlocking, hi));
         return EUT_OK;
     };
     {
@@ -276,7 +295,7 @@ int eut_slab_create(eut_slab **out, const int32_t *from, const int32_t *to, int6
             }
             int rc = upload_i32(s->parts[a].device, sp, &L.d_spos);
             if (rc == EUT_OK) rc = upload_i32(s->parts[a].device, dp, &L.d_dpos);
-            for (int g = 0; g < 2 && rc == EUT_OK; g++)
+            for (int g = 0; g < kSlabGroups && rc == EUT_OK; g++)
                 if (cudaEventCreateWithFlags(&L.done[g], cudaEventDisableTiming) != cudaSuccess) rc = EUT_ERR_CUDA;
             if (rc != EUT_OK) { slab_free(s); return rc; }
             s->links.push_back(std::move(L));
@@ -410,9 +429,11 @@ int eut_slab_diffuse(eut_slab *s, const int32_t *niter, const int32_t *indvar, i
     // substep keeps the SMs busy (it also fills the partial last wave of CTAs, like the lanes of a plain
     // field).  Columns are dealt out round robin, so each group keeps the descending substep counts.
     const char *ge = getenv("EUT_SLAB_GROUPS");
-    const int G = (n_tot >= 32 && !(ge && atoi(ge) == 1)) ? 2 : 1;
-    int gbeg[3] = {0, (n_tot + G - 1) / G, n_tot};
-    if (G == 1) gbeg[1] = n_tot;
+    int G = n_tot >= 32 ? 2 : 1;
+    if (ge) G = std::max(1, std::min(std::min(kSlabGroups, atoi(ge)), n_tot / 8 > 0 ? n_tot / 8 : 1));
+    int gbeg[kSlabGroups + 1];
+    gbeg[0] = 0;
+    for (int g = 0; g < G; g++) gbeg[g + 1] = gbeg[g] + (n_tot - g + G - 1) / G;
     std::vector<int64_t> dealt;
     for (int g = 0; g < G; g++)
         for (int a = g; a < n_tot; a += G) dealt.push_back(order[a]);
@@ -434,7 +455,7 @@ int eut_slab_diffuse(eut_slab *s, const int32_t *niter, const int32_t *indvar, i
         // group 1's stream, and the first slab's stream (every other stream starts behind it, and a captured
         // loop is launched into it): after the tables and whatever this field's stream holds
         EUT_CUDA(cudaEventRecord(p.fork, p.gs[0]));
-        EUT_CUDA(cudaStreamWaitEvent(p.gs[1], p.fork, 0));
+        for (int g = 1; g < kSlabGroups; g++) EUT_CUDA(cudaStreamWaitEvent(p.gs[g], p.fork, 0));
         if (p.gs[0] != s->parts[0].gs[0]) EUT_CUDA(cudaStreamWaitEvent(s->parts[0].gs[0], p.fork, 0));
     }
     struct Restore {                                 // the fields run on their own stream outside this call
@@ -450,14 +471,15 @@ int eut_slab_diffuse(eut_slab *s, const int32_t *niter, const int32_t *indvar, i
         EUT_TRY(ensure_device(s->parts[0].device));
         EUT_CUDA(cudaEventRecord(s->ev_origin, origin));
         for (auto &p : s->parts)
-            for (int g = 0; g < 2; g++)
+            for (int g = 0; g < kSlabGroups; g++)
                 if (p.gs[g] != origin) EUT_CUDA(cudaStreamWaitEvent(p.gs[g], s->ev_origin, 0));
         // ghosts up to date before the first substep (an upload or anything else may have changed owned values)
         for (int g = 0; g < G; g++) {
             EUT_TRY(mark_stepped(s, g));
             EUT_TRY(push_halos(s, g, gbeg[g], gbeg[g + 1] - gbeg[g], 0));
         }
-        int n_act[2] = {gbeg[1] - gbeg[0], gbeg[2] - gbeg[1]};
+        int n_act[kSlabGroups] = {};
+        for (int g = 0; g < G; g++) n_act[g] = gbeg[g + 1] - gbeg[g];
         for (int it = 0; it < max_it; it++) {
             for (int g = 0; g < G; g++) {
                 while (n_act[g] > 0 && niter[dealt[gbeg[g] + n_act[g] - 1]] <= it) n_act[g]--;
@@ -467,8 +489,8 @@ int eut_slab_diffuse(eut_slab *s, const int32_t *niter, const int32_t *indvar, i
                     EUT_TRY(ensure_device(p.device));
                     // staggered groups: this group's substep starts when the other group's has finished, so the
                     // halo exchange of one group runs under the substep of the other
-                    if (stagger && G == 2) EUT_CUDA(cudaStreamWaitEvent(p.gs[g], p.stepped[g ^ 1], 0));
-                    f->stream = p.gs[g]; f->in_lanes = (G == 2) && !stagger;
+                    if (stagger && G >= 2) EUT_CUDA(cudaStreamWaitEvent(p.gs[g], p.stepped[(g + G - 1) % G], 0));
+                    f->stream = p.gs[g]; f->in_lanes = (G >= 2) && !stagger;
                     f->act_col = f->d_act + gbeg[g]; f->act_par = f->d_act + f->act_cap + gbeg[g];
                     EUT_TRY(launch_substep(f, n_act[g], it));
                 }
@@ -481,8 +503,10 @@ int eut_slab_diffuse(eut_slab *s, const int32_t *niter, const int32_t *indvar, i
             eut_field *f = p.field;
             EUT_TRY(ensure_device(p.device));
             f->stream = p.gs[0];
-            EUT_CUDA(cudaEventRecord(p.join, p.gs[1]));
-            EUT_CUDA(cudaStreamWaitEvent(p.gs[0], p.join, 0));
+            for (int g = 1; g < kSlabGroups; g++) {
+                EUT_CUDA(cudaEventRecord(p.join[g], p.gs[g]));
+                EUT_CUDA(cudaStreamWaitEvent(p.gs[0], p.join[g], 0));
+            }
             EUT_TRY(launch_set_cur(f, f->d_act, f->d_act + 2 * f->act_cap, n_tot));
             if (p.gs[0] != origin) {
                 EUT_CUDA(cudaEventRecord(p.stepped[0], p.gs[0]));

@@ -11,9 +11,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     r = bench.slab_leg(eb, torch, torch.cuda.device_count(), peak)
     print(json.dumps({k: r[k] for k in ("value", "ms_per_substep", "frac_of_hbm_peak_per_gpu", "gpu_launches", "bit_identical_to_unsharded")}))
     sys.exit(0)
-VARIANTS = [("default", {}), ("stagger", {"EUT_SLAB_STAGGER": "1"}), ("live ghosts", {"EUT_SLAB_LIVE_GHOSTS": "1"}),
-            ("one group", {"EUT_SLAB_GROUPS": "1"}), ("no halo kernels (timing only)", {"EUT_SLAB_DEBUG": "1", "EUT_SKIP_CHECK": "1"}),
-            ("no waits between slabs (timing only)", {"EUT_SLAB_DEBUG": "2", "EUT_SKIP_CHECK": "1"}), ("no graphs", {"EUT_NO_GRAPHS": "1"})]
+VARIANTS = [("two groups (default)", {}), ("three groups", {"EUT_SLAB_GROUPS": "3"}), ("four groups", {"EUT_SLAB_GROUPS": "4"}),
+            ("four groups, staggered", {"EUT_SLAB_GROUPS": "4", "EUT_SLAB_STAGGER": "1"})]
 for name, env in VARIANTS:
     r = subprocess.run([sys.executable, __file__, "child"], env=dict(os.environ, **env), capture_output=True, text=True)
     line = [l for l in r.stdout.strip().splitlines() if l.startswith("{")]
