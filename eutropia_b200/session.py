@@ -52,7 +52,7 @@ class Plan:
         self.device = int(device)
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and getattr(_lib, "lib", None):     # module globals are gone at interpreter exit
             _lib.lib().eut_plan_destroy(self._h)
             self._h = None
 
@@ -114,7 +114,7 @@ class Field:
         self._h = h
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and getattr(_lib, "lib", None):
             _lib.lib().eut_field_destroy(self._h)
             self._h = None
 
@@ -219,7 +219,7 @@ class Cells:
         self.n_cells = 0
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and getattr(_lib, "lib", None):
             _lib.lib().eut_cells_destroy(self._h)
             self._h = None
 
@@ -293,7 +293,7 @@ class SlabField:
         self._h = h
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and getattr(_lib, "lib", None):
             _lib.lib().eut_slab_destroy(self._h)
             self._h = None
 
