@@ -109,6 +109,7 @@ k_substep_seg(double *__restrict__ buf, const int64_t col_stride, const int64_t 
     __shared__ long long s_src[kTileMaxCols], s_dst[kTileMaxCols];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");    // the next launch of the stream may start its prologue
     const int tile = tile_list ? __ldg(tile_list + blockIdx.x) : (int)blockIdx.x;
     const int a_begin = blockIdx.y * cols_per_cta;
     const int n_cols = min(n_act, a_begin + cols_per_cta) - a_begin;
@@ -148,6 +149,10 @@ k_substep_seg(double *__restrict__ buf, const int64_t col_stride, const int64_t 
     }
     s_fence_async();                                       // generic-proxy zero fill before async-proxy copies
     __syncthreads();
+    // Programmatic dependent launch: this CTA may have started while the previous substep's last CTAs
+    // were still running (everything above reads only this kernel's own tables); the field itself is
+    // touched -- by the producer's copies and stores -- only after the previous grid has completed.
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
 
     if (tid >= CTHREADS) {
         // ======================= producer warp =================================================
@@ -384,9 +389,20 @@ static int launch_seg_t(eut_field *f, int n_act, int substep)
         EUT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
         attr_set[p->device & 63] = true;
     }
-    kern<<<grid, (CWARPS + 1) * 32, smem, f->stream>>>(f->d_buf, p->Np, f->C * p->Np, p->d_seg_meta, p->d_copies,
-                                                       p->d_segs, p->d_gens, p->d_w, f->act_col, f->act_par,
-                                                       n_act, substep, img_bytes, out_bytes, cols_per_cta, f->opt_debug, tile_list);
+    // programmatic dependent launch (EUT_PDL=0 turns it off): the next substep's CTAs are placed as soon as
+    // SMs fall free and run their prologue (tables, zero fill, mbarrier init) under this launch's tail;
+    // they wait in griddepcontrol.wait until this grid has completed before they touch the field
+    static const bool pdl = [] { const char *e = getenv("EUT_PDL"); return !e || atoi(e) != 0; }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3((CWARPS + 1) * 32, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = f->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    const int64_t col_stride = p->Np, buf_stride = f->C * p->Np;
+    EUT_CUDA(cudaLaunchKernelEx(&cfg, kern, f->d_buf, col_stride, buf_stride, (const int32_t *)p->d_seg_meta, (const int2 *)p->d_copies,
+                                (const uint4 *)p->d_segs, (const uint4 *)p->d_gens, (const double *)p->d_w, f->act_col, f->act_par,
+                                n_act, substep, img_bytes, out_bytes, cols_per_cta, f->opt_debug, tile_list));
     return EUT_OK;
 }
 
