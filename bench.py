@@ -35,6 +35,9 @@ WORKLOADS = {
     "harbor1m": ("harbor1m", 64, 60, 50_000, 10),
     "square100k": ("square100k", 16, 1000, 0, 0),
     "harbor250k": ("harbor:250000", 64, 60, 12_500, 10),
+    # configs[2] on the reference's own polygon, Kiel_1712 (999 393 points); needs the reference's kiel.csv or the
+    # point cache of tools/cache_kiel_points.py -- the default stays harbor1m, which needs neither
+    "kiel1m": ("kiel1m", 64, 60, 50_000, 10),
     "tiny": ("harbor:20000", 8, 10, 500, 4),
 }
 

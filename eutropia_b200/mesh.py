@@ -15,6 +15,7 @@ reference's rules exactly, including its one-sided snapping quirk.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -49,7 +50,36 @@ def universe_polygon_preset(name: str) -> np.ndarray:
         return np.array([[x, y], [x, -y], [-x, -y], [-x, y]], dtype=np.float64)
     if low.startswith("harbor_"):
         return harbor_polygon(float(name.split("_")[1]))
+    if low.startswith("kiel_"):
+        return kiel_polygon(float(name.split("_")[1]))
     raise ValueError(f'The polygon preset "{name}" does not exist / is not yet supported.')
+
+
+def kiel_csv_path() -> str | None:
+    """Where the reference's `inst/extdata/kiel.csv` can be read from: $EUTROPIA_EXTDATA/kiel.csv, an
+    installed R package is not looked for; /root/reference in the build container.  The file is
+    reference data and is not copied into this repository: where it is absent (the GPU box), `Harbor_<w>`
+    stands in for it."""
+    for d in (os.environ.get("EUTROPIA_EXTDATA"), "/root/reference/inst/extdata"):
+        if d and os.path.exists(os.path.join(d, "kiel.csv")):
+            return os.path.join(d, "kiel.csv")
+    return None
+
+
+def kiel_polygon(size: float) -> np.ndarray:
+    """`Kiel_<size>` (R/growthSimulation.R:202-214): the vertices of kiel.csv divided by their largest x,
+    times (size / 2) / 2; sizes below 20 are refused (`x < 10` after the halving, :210-211)."""
+    path = kiel_csv_path()
+    if path is None:
+        raise FileNotFoundError("Kiel_<L> needs the reference's inst/extdata/kiel.csv (set EUTROPIA_EXTDATA); "
+                                "Harbor_<w> is this repository's own non-convex stand-in")
+    kiel = np.loadtxt(path, delimiter=",", skiprows=1, dtype=np.float64)
+    kiel = kiel / kiel[:, 0].max()
+    x = float(size) / 2
+    kiel = kiel * x / 2
+    if x < 10:
+        raise ValueError("Kiel latitude dimension too small (min 10 um).")
+    return kiel
 
 
 def harbor_polygon(width: float) -> np.ndarray:

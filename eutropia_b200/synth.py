@@ -32,6 +32,24 @@ def harbor_width_for(n_points: int, layers: int = 3, field_size: float = 1.0) ->
     return math.sqrt(n_points / layers * field_size ** 2 / area)
 
 
+def _kiel_mesh(size: int):
+    """`Kiel_<size>`, 3 layers: from the reference's inst/extdata/kiel.csv where that file exists (the build
+    container, mesh.kiel_csv_path), else from field points written there by tools/cache_kiel_points.py into
+    the git-ignored directory $EUT_MESH_CACHE (default <repo>/mesh_cache) -- derived points, not the
+    reference's file, which is never copied -- so that the configuration can be measured on the GPU box."""
+    import os
+    if _mesh.kiel_csv_path() is not None:
+        return _mesh.make_mesh(f"Kiel_{size}", 1.0, 3)
+    cache = os.environ.get("EUT_MESH_CACHE") or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "mesh_cache")
+    path = os.path.join(cache, f"kiel_{size}_pts.npz")
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"Kiel_{size}: neither the reference's kiel.csv nor {path} is here; use harbor1m")
+    z = np.load(path)
+    pts = np.ascontiguousarray(z["pts"], dtype=np.float64)
+    mat_in, mat_out = _mesh.build_dcm(pts, 1.0)
+    return _mesh.FieldMesh(pts, mat_in, mat_out, 1.0, 3, _mesh.field_volume(1.0), z["polygon"])
+
+
 def config_mesh(name: str, on_device: bool = False, device: int = 0):
     """The BASELINE.json configs as meshes (`on_device`: neighbour maps by eut_build_dcm)."""
     if on_device:
@@ -46,6 +64,8 @@ def config_mesh(name: str, on_device: bool = False, device: int = 0):
         return _mesh.make_mesh("Rectangle_181_181", 1.0, 3)
     if name == "harbor1m":        # config 3/4: non-convex polygon, ~1e6 points, 3 layers
         return _mesh.make_mesh(_mesh.harbor_polygon(harbor_width_for(1_000_000)), 1.0, 3)
+    if name == "kiel1m":          # config 3 on the reference's own polygon, `Kiel_1712` (~1e6 points at 3 layers)
+        return _kiel_mesh(1712)
     if name == "petri80":         # config 1 (vignette): Petri_80, 6 layers
         return _mesh.make_mesh("Petri_80", 1.0, 6)
     if name == "square16m":       # config 5

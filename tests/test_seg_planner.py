@@ -168,3 +168,23 @@ def test_segment_tables_decode_to_mat_in(name, layers):
     assert plan.info.segmented == 1
     rp, col = plan.csr()
     assert np.array_equal(rp, row_ptr) and np.array_equal(col, frm[order])
+
+
+@pytest.mark.skipif(mesh.kiel_csv_path() is None, reason="the reference's inst/extdata/kiel.csv is not on this machine")
+def test_kiel_polygon_of_the_reference():
+    """BASELINE.json configs[2] names the reference's own non-convex polygon, `Kiel_<L>` (inst/extdata/kiel.csv
+    scaled as R/growthSimulation.R:202-214).  The file is reference data and is not copied into this
+    repository, so this runs where /root/reference exists (the build container): the scaling rule, the
+    mesh, and the segment kernel's tables replayed bit for bit on that mesh; `Harbor_<w>` is the
+    travelling stand-in of the bench."""
+    raw = np.loadtxt(mesh.kiel_csv_path(), delimiter=",", skiprows=1)
+    poly = mesh.universe_polygon_preset("Kiel_240")
+    assert np.array_equal(poly, raw / raw[:, 0].max() * (240 / 2) / 2)           # :204-208
+    assert poly[:, 0].max() == 60.0
+    with pytest.raises(ValueError):
+        mesh.universe_polygon_preset("Kiel_19")                                     # :210-211
+    m = mesh.make_mesh("Kiel_240", 1.0, 3)
+    assert 15000 < m.nfields < 30000
+    plan = eb.Plan(m.mat_in, m.mat_out, order=_lib.ORDER_SEGMENTS, host_only=True)
+    inf = replay(m, plan)
+    assert inf.n_seg_covered + inf.n_generic == m.nfields
