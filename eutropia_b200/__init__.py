@@ -6,6 +6,7 @@ cell<->field exchange path, behind the reference's own call surface.
   environment  GrowthEnvironment.diffuse_compoundsPar / diffuse_compounds / exoenzyme_activity
                (R/growthEnvironment.R:280-437, R/run_simulation.R:337-371)
   exchange     scavenge_compounds / adjust_uptake   (R/scavenge_compounds.R, R/adjust_uptake.R)
+  recording    record_compounds / global_concentrations + RDS writer (R/run_simulation.R:480-526)
   mesh         field points + mat.in / mat.out in the reference's format (setup, host)
   synth        synthetic inputs for tests and the bench
 
@@ -17,8 +18,8 @@ from .rcpp_api import diffChange, diffChangePar
 from .session import Cells, Field, Plan, SlabField
 from .environment import Exoenzyme, GrowthEnvironment, diffusion_niter
 from .exchange import adjust_uptake, scavenge_compounds
-from . import mesh, synth
+from . import mesh, recording, synth
 
 __all__ = ["diffChange", "diffChangePar", "Plan", "Field", "Cells", "SlabField", "GrowthEnvironment", "Exoenzyme",
-           "diffusion_niter", "adjust_uptake", "scavenge_compounds", "mesh", "synth", "EutropiaError", "EutropiaIndexError"]
+           "diffusion_niter", "adjust_uptake", "scavenge_compounds", "mesh", "recording", "synth", "EutropiaError", "EutropiaIndexError"]
 __version__ = "0.1.0"

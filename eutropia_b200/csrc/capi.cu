@@ -287,6 +287,21 @@ int eut_field_download(eut_field *f, double *host, int64_t ld, const int32_t *co
     return field_sync_down(f);
 }
 
+int eut_field_record(eut_field *f, double *host, int64_t ld, const int32_t *cols, int64_t n_cols, int digits)
+{
+    clear_error();
+    if (!f) { set_error("eut_field_record: field is NULL"); return EUT_ERR_ARG; }
+    if (digits < 1 || digits > 15) { set_error("eut_field_record: digits = %d, expected 1..15", digits); return EUT_ERR_ARG; }
+    EUT_TRY(field_sync_down(f));                       // no download of this field in flight with the other setting
+    double p10 = 1.0;
+    for (int k = 0; k < digits; k++) p10 *= 10.0;      // exact up to 1e22
+    f->round_p10 = p10;
+    int rc = field_download_async(f, host, ld, cols, n_cols);
+    const int rc2 = field_sync_down(f);
+    f->round_p10 = 0.0;
+    return rc != EUT_OK ? rc : rc2;
+}
+
 int eut_field_diffuse(eut_field *f, const int32_t *niter, const int32_t *indvar, int64_t n_indvar)
 {
     clear_error();

@@ -238,6 +238,7 @@ struct eut_field {
     // slab overlap: tiles that hold points a neighbour reads (boundary) and the rest (interior)
     int32_t *d_tiles_b = nullptr, *d_tiles_i = nullptr;
     int n_tiles_b = 0, n_tiles_i = 0;
+    double round_p10 = 0.0;  // > 0: downloads round to log10(round_p10) decimals on the way out (eut_field_record)
     int opt_phase = 0;       // 0: all tiles; 1: boundary tiles, then flip; 2: interior tiles of the substep just flipped
 };
 

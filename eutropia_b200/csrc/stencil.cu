@@ -155,16 +155,57 @@ k_permute_in(double *__restrict__ buf, const int64_t col_stride, const int64_t b
         (i >= 0) ? stage[(int64_t)j * ld + i] : 0.0;
 }
 
+// round(x, digits) as base R (>= 4.0.0) does it for digits > 0 (nmath/fround.c, restated from its published
+// description -- base R is not part of the reference tree): of the two decimal neighbours
+// floor(|x| * 10^d) / 10^d and ceil(|x| * 10^d) / 10^d the one closer to x AS REPRESENTED, ties to the even
+// integer; values with more than 15 significant digits before the cut (and NaN / Inf) are returned as they
+// are.  R compares the two distances in long double; here they are compared through an exact quotient
+// (double-double, Dekker products without FMA): round(0.15, 1) = 0.1, round(0.45, 1) = 0.5 as ?Round
+// documents.  The host mirror (recording.r_round) runs the same IEEE operations and gives the same bits.
+// Used by the concentration recording, R/run_simulation.R:514.
+__device__ __forceinline__ void r_two_prod(const double a, const double b, double &p, double &e)
+{
+    p = __dmul_rn(a, b);
+    const double c = 134217729.0;                           // 2^27 + 1
+    double t = __dmul_rn(c, a);
+    const double ah = __dsub_rn(t, __dsub_rn(t, a)), al = __dsub_rn(a, ah);
+    t = __dmul_rn(c, b);
+    const double bh = __dsub_rn(t, __dsub_rn(t, b)), bl = __dsub_rn(b, bh);
+    e = __dadd_rn(__dadd_rn(__dadd_rn(__dsub_rn(__dmul_rn(ah, bh), p), __dmul_rn(ah, bl)), __dmul_rn(al, bh)), __dmul_rn(al, bl));
+}
+__device__ __forceinline__ void r_exact_quotient(const double n, const double d, double &hi, double &lo)
+{
+    hi = __ddiv_rn(n, d);
+    double p, e;
+    r_two_prod(hi, d, p, e);
+    lo = __ddiv_rn(__dsub_rn(__dsub_rn(n, p), e), d);
+}
+__device__ __forceinline__ double r_round_digits(const double x, const double p10)
+{
+    const double ax = fabs(x);
+    if (!(ax < 1e15 / p10)) return x;
+    const double x10 = __dmul_rn(p10, ax), i10 = floor(x10), c10 = ceil(x10);
+    double xd, xd_lo, xu, xu_lo;
+    r_exact_quotient(i10, p10, xd, xd_lo);
+    r_exact_quotient(c10, p10, xu, xu_lo);
+    const double dd = __dsub_rn(__dsub_rn(ax, xd), xd_lo), du = __dadd_rn(__dsub_rn(xu, ax), xu_lo);
+    const bool even = fmod(i10, 2.0) == 0.0;
+    return copysign((dd < du || (dd == du && even)) ? xd : xu, x);
+}
+
 __global__ void __launch_bounds__(256)
 k_permute_out(const double *__restrict__ buf, const int64_t col_stride, const int64_t buf_stride,
               double *__restrict__ stage, const int64_t ld, const int32_t *__restrict__ perm,
-              const int32_t *__restrict__ cols, const int32_t *__restrict__ cur, const int n_points)
+              const int32_t *__restrict__ cols, const int32_t *__restrict__ cur, const int n_points,
+              const double round_p10)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_points) return;
     const int j = blockIdx.y;
     const int c = cols[j];
-    stage[(int64_t)j * ld + i] = buf[(int64_t)cur[c] * buf_stride + (int64_t)c * col_stride + perm[i]];
+    double v = buf[(int64_t)cur[c] * buf_stride + (int64_t)c * col_stride + perm[i]];
+    if (round_p10 > 0.0) v = r_round_digits(v, round_p10);
+    stage[(int64_t)j * ld + i] = v;
 }
 
 int launch_permute_in(eut_field *f, const double *d_stage, int64_t ld, const int32_t *d_cols,
@@ -187,7 +228,7 @@ int launch_permute_out(eut_field *f, double *d_stage, int64_t ld, const int32_t 
     if (n_cols <= 0 || p->N == 0) return EUT_OK;
     dim3 grid((unsigned)((p->N + 255) / 256), (unsigned)n_cols, 1);
     k_permute_out<<<grid, 256, 0, s>>>(f->d_buf, p->Np, f->C * p->Np, d_stage, ld, p->d_perm, d_cols,
-                                       d_cur, (int)p->N);
+                                       d_cur, (int)p->N, f->round_p10);
     f->launches++;
     EUT_CUDA(cudaGetLastError());
     return EUT_OK;

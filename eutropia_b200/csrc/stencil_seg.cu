@@ -254,6 +254,8 @@ k_substep_seg(double *__restrict__ buf, const int64_t col_stride, const int64_t 
         lo_mask |= (__any_sync(0xffffffffu, (so[s][1] | so[s][2] | rd[s][1] | rd[s][2]) != 0u) ? 1u : 0u) << s;
         up_mask |= (__any_sync(0xffffffffu, (so[s][5] | so[s][6] | rd[s][3] | rd[s][4]) != 0u) ? 1u : 0u) << s;
     }
+    if (dbg & 512) up_mask = 0;                            // ablation: no upper-layer streams (16 of 55 loads less)
+    if (dbg & 1024) lo_mask = 0;                           // ablation: no lower-layer streams
     auto s_lds = [](const unsigned char *a) { return *reinterpret_cast<const double *>(a); };
     auto s_sts = [](unsigned char *a, double v) { *reinterpret_cast<double *>(a) = v; };
     for (int j = 0; j < n_cols; j++) {

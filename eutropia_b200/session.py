@@ -142,6 +142,16 @@ class Field:
         check(_lib.lib().eut_field_download(self._h, ptr(out), max(npts, 1), ptr(c), n))
         return out
 
+    def record(self, cols=None, digits: int = 7):
+        """Columns rounded to `digits` decimals on the device on their way out (`round(COI.rec, digits = 7)`,
+        R/run_simulation.R:514); base R's rounding rule, see eut_field_record."""
+        c = None if cols is None else _i32(cols)
+        n = self.n_cols if c is None else c.shape[0]
+        npts = self.plan.n_points
+        out = np.empty((npts, n), dtype=np.float64, order="F")
+        check(_lib.lib().eut_field_record(self._h, ptr(out), max(npts, 1), ptr(c), n, int(digits)))
+        return out
+
     def download_ptr(self, host_ptr: int, ld: int, cols=None, n_cols=None):
         c = None if cols is None else _i32(cols)
         n = int(n_cols) if c is None else c.shape[0]

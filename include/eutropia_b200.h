@@ -243,6 +243,12 @@ EUT_API int eut_field_set_stream(eut_field *field, void *cuda_stream);
 EUT_API int64_t eut_field_launch_count(const eut_field *field);
 /* Kernel variant selection for experiments: see DESIGN.md ("kernel variants"). */
 EUT_API int eut_field_set_option(eut_field *field, const char *name, int64_t value);
+/* Concentration recording (R/run_simulation.R:511-514, `round(COI.rec, digits = 7)`): like
+ * eut_field_download, with every value rounded to `digits` (1..15) decimals on the device on its way out, by
+ * base R's rule (the decimal neighbour closer to the represented value, ties to even).  The RDS file itself
+ * (`saveRDS`, :517) is written on the host: eutropia_b200/recording.py. */
+EUT_API int eut_field_record(eut_field *field, double *host, int64_t ld, const int32_t *cols, int64_t n_cols,
+                             int digits);
 /* Per-column reductions on the device (diffuse_compoundsPar's column selection and D = Inf rule,
  * R/growthEnvironment.R:372, :393-401): writes min, max, mean of every column (arrays of n_cols). */
 EUT_API int eut_field_column_stats(eut_field *field, double *col_min, double *col_max,
