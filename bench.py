@@ -363,7 +363,7 @@ def run_reference(args):
                                    f"the full step extrapolated from it)"},
             "cpu_baseline": dict(sample, value=v),
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args):
@@ -609,12 +609,46 @@ def run_ours(args):
         if e2e_ranks is not None:
             line["e2e_ranks"] = e2e_ranks
         line.update(extra)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+class QuietStdout:
+    """stdout carries exactly one JSON line (the driver parses it).  Libraries print there too -- NCCL's version
+    banner comes out at the first collective whatever NCCL_DEBUG says on some builds -- so file descriptor 1
+    points at stderr for the whole run and the line is written to the saved descriptor at the end."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text: str):
+        sys.stdout.flush()
+        os.write(self.saved, (text.rstrip("\n") + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
+OUT = None
+
+
+def emit(line: dict):
+    text = json.dumps(line)
+    if OUT is not None:
+        OUT.emit(text)
+    else:
+        print(text, flush=True)
+
+
 def main():
+    global OUT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -630,10 +664,13 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    with QuietStdout() as out:
+        OUT = out
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+        OUT = None
 
 
 if __name__ == "__main__":
