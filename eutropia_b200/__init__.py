@@ -15,11 +15,11 @@ All compute is in libeutropia_b200.so (eutropia_b200/csrc); there is no CPU fall
 from . import _lib
 from ._lib import EutropiaError, EutropiaIndexError
 from .rcpp_api import diffChange, diffChangePar
-from .session import Cells, Field, Plan, SlabField
+from .session import Cells, Field, Plan, SlabCells, SlabField
 from .environment import Exoenzyme, GrowthEnvironment, diffusion_niter
 from .exchange import adjust_uptake, scavenge_compounds
 from . import mesh, recording, synth
 
-__all__ = ["diffChange", "diffChangePar", "Plan", "Field", "Cells", "SlabField", "GrowthEnvironment", "Exoenzyme",
+__all__ = ["diffChange", "diffChangePar", "Plan", "Field", "Cells", "SlabField", "SlabCells", "GrowthEnvironment", "Exoenzyme",
            "diffusion_niter", "adjust_uptake", "scavenge_compounds", "mesh", "recording", "synth", "EutropiaError", "EutropiaIndexError"]
 __version__ = "0.1.0"

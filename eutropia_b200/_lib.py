@@ -108,6 +108,14 @@ def lib() -> C.CDLL:
         "eut_slab_diffuse": (C.c_int, [vp, vp, vp, i64]),
         "eut_slab_sync": (C.c_int, [vp]),
         "eut_slab_launch_count": (i64, [vp]),
+        "eut_slab_cells_create": (C.c_int, [C.POINTER(vp), vp]),
+        "eut_slab_cells_destroy": (C.c_int, [vp]),
+        "eut_slab_cells_build_lists": (C.c_int, [vp, vp, i64, i64, vp, vp, vp, vp, i64, C.c_int]),
+        "eut_slab_cells_claim_rescale": (C.c_int, [vp]),
+        "eut_slab_cells_num_entries": (i64, [vp]),
+        "eut_slab_cells_get_lists": (C.c_int, [vp, C.c_int, C.POINTER(i64), vp, vp, vp, vp]),
+        "eut_slab_cells_gather": (C.c_int, [vp, C.c_double, vp]),
+        "eut_slab_cells_scatter": (C.c_int, [vp, C.c_double, vp, vp, vp, vp]),
         "eut_cells_create": (C.c_int, [C.POINTER(vp), vp]),
         "eut_cells_destroy": (C.c_int, [vp]),
         "eut_cells_set_lists": (C.c_int, [vp, i64, vp, vp, vp, vp]),
@@ -137,6 +145,8 @@ EXPORTS = (
     "eut_field_halo_set eut_field_set_halo_stream eut_field_halo_pack eut_field_halo_unpack "
     "eut_slab_create eut_slab_destroy eut_slab_get_info eut_slab_part eut_slab_upload eut_slab_download "
     "eut_slab_diffuse eut_slab_sync eut_slab_launch_count "
+    "eut_slab_cells_create eut_slab_cells_destroy eut_slab_cells_build_lists eut_slab_cells_claim_rescale "
+    "eut_slab_cells_num_entries eut_slab_cells_get_lists eut_slab_cells_gather eut_slab_cells_scatter "
     "eut_cells_create eut_cells_destroy eut_cells_set_lists eut_cells_build_lists "
     "eut_cells_claim_rescale eut_cells_num_entries eut_cells_get_lists eut_cells_gather "
     "eut_cells_scatter eut_cells_chemotaxis_moments"

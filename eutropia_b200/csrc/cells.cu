@@ -1061,6 +1061,74 @@ k_cellmap(const double *__restrict__ gx, const double *__restrict__ gy,
 
 using namespace eut;
 
+// ---- hooks for cells on a slab-sharded field (slab.cu) ---------------------------------------------------
+// A slab's eut_cells holds, of every cell, only the entries that fall on the slab's own points.  What the
+// scatter needs per CELL -- the largest distance and sum(max - dist) of the production shares
+// (R/run_simulation.R:729-730), the colSums of the uptake shares (:696) -- spans all slabs a cell touches:
+// the slab driver combines the partial values and hands the global ones back through these.
+namespace eut {
+
+__global__ void __launch_bounds__(256)
+k_cell_fsum(const int64_t *__restrict__ cell_ptr, const double *__restrict__ dist, const double *__restrict__ dmax,
+            double *__restrict__ fsum, const int n_cells)
+{
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n_cells) return;
+    const double m = dmax[w];
+    dd s{0.0, 0.0};
+    for (int64_t k = cell_ptr[w] + lane; k < cell_ptr[w + 1]; k += 32) dd_add(s, __dsub_rn(m, dist[k]));
+    s = dd_warp_sum(s);
+    if (lane == 0) fsum[w] = dd_value(s);
+}
+
+int64_t cells_count(const eut_cells *c) { return c->M; }
+
+int cells_get_dmax(eut_cells *c, double *host)
+{
+    EUT_TRY(ensure_device(c->plan->device));
+    if (c->M == 0) return EUT_OK;
+    EUT_CUDA(cudaStreamSynchronize(0));
+    EUT_CUDA(cudaMemcpy(host, c->d_dmax, c->M * sizeof(double), cudaMemcpyDeviceToHost));
+    return EUT_OK;
+}
+
+// d_dmax <- the global maxima; fsum_host <- this slab's share of sum(max - dist)
+int cells_partial_fsum(eut_cells *c, const double *dmax_host, double *fsum_host)
+{
+    EUT_TRY(ensure_device(c->plan->device));
+    if (c->M == 0) return EUT_OK;
+    EUT_CUDA(cudaMemcpy(c->d_dmax, dmax_host, c->M * sizeof(double), cudaMemcpyHostToDevice));
+    k_cell_fsum<<<(unsigned)((c->M * 32 + 255) / 256), 256, 0, 0>>>(c->d_cell_ptr, c->d_dist, c->d_dmax, c->d_fsum, (int)c->M);
+    c->launches++;
+    EUT_CUDA(cudaGetLastError());
+    EUT_CUDA(cudaMemcpy(fsum_host, c->d_fsum, c->M * sizeof(double), cudaMemcpyDeviceToHost));
+    return EUT_OK;
+}
+
+int cells_set_fsum(eut_cells *c, const double *fsum_host)
+{
+    EUT_TRY(ensure_device(c->plan->device));
+    if (c->M > 0) EUT_CUDA(cudaMemcpy(c->d_fsum, fsum_host, c->M * sizeof(double), cudaMemcpyHostToDevice));
+    c->t_packed = false;                 // the packed (acc.prop, production share) pairs are stale
+    return EUT_OK;
+}
+
+// the per-cell sums of the last gather (M x C, on the cells' device); nullptr before the first gather
+double *cells_fmol(eut_cells *c) { return c->d_fmol; }
+
+// the buffer cells_fmol() points at now holds the sums over ALL slabs, taken from this state of `f`
+void cells_mark_gathered(eut_cells *c, const eut_field *f, double field_vol)
+{
+    c->fmol_field = f; c->fmol_version = f->version; c->fmol_vol = field_vol;
+}
+
+bool cells_gather_is_current(const eut_cells *c, const eut_field *f, double field_vol)
+{
+    return c->d_fmol && c->fmol_field == f && c->fmol_version == f->version && c->fmol_vol == field_vol;
+}
+
+}  // namespace eut
+
 extern "C" {
 
 int eut_cells_create(eut_cells **out, eut_plan *plan)

@@ -283,6 +283,14 @@ int field_exoenzyme_catalysis(eut_field *cf, eut_field *ef, int32_t exo_col, dou
                               const uint8_t *is_constant, double delta_time);
 int field_scale_column(eut_field *f, int32_t col0, double factor);
 int max_exo_mets();
+// cells.cu: hooks for cells on a slab-sharded field (slab.cu)
+int64_t cells_count(const eut_cells *c);
+int cells_get_dmax(eut_cells *c, double *host);
+int cells_partial_fsum(eut_cells *c, const double *dmax_host, double *fsum_host);
+int cells_set_fsum(eut_cells *c, const double *fsum_host);
+double *cells_fmol(eut_cells *c);
+void cells_mark_gathered(eut_cells *c, const eut_field *f, double field_vol);
+bool cells_gather_is_current(const eut_cells *c, const eut_field *f, double field_vol);
 // meshgen.cu
 int mesh_build_dcm(const double *pts, int64_t ld, int64_t n, double fs, int device, int32_t *mat_in, int64_t cap,
                    int64_t *n_edges_out, int32_t *mat_out);

@@ -592,3 +592,202 @@ int64_t eut_slab_launch_count(const eut_slab *s)
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// Cells on a slab-sharded field ("cells ... their field lists may touch the halo").
+// Every slab keeps, of every cell, the entries that fall on its OWN points: the slab's cell map is built over
+// its local points with the ghosts moved out of every cell's reach, so each (cell, field) entry exists on
+// exactly one slab, in the key order of the global list.  What is per field point -- the claim rescale, the
+// by-(field, compound) sums of the scatter in cell order, NaN -> 0, the clamp -- then happens on the owner
+// exactly as on an unsharded field, bit for bit.  What is per CELL spans the slabs a cell touches and is
+// combined here: max distance and sum(max - dist) of the production shares once per cell map; the
+// accessible amounts (= colSums of the uptake shares) after every gather, by a kernel on every slab's device
+// that adds the partial sums of all slabs in slab order through peer-mapped pointers.  A cell inside one
+// slab gets the unsharded bits; a cell across a cut differs by the rounding of one extra addition (1e-16).
+// ---------------------------------------------------------------------------------------------------------
+namespace eut {
+__global__ void __launch_bounds__(256)
+k_sum_partials(double *__restrict__ out, const double *const *__restrict__ parts, const int n_parts, const int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = parts[0][i];
+    for (int p = 1; p < n_parts; p++) s = __dadd_rn(s, parts[p][i]);
+    out[i] = s;
+}
+}  // namespace eut
+
+struct eut_slab_cells {
+    eut_slab *slab = nullptr;
+    std::vector<eut_cells *> cells;            // one per slab, on the slab's plan
+    std::vector<double *> d_total;             // [M x C] per slab: sums over all slabs
+    std::vector<const double **> d_ptrs;       // per slab: device table of every slab's partial sums
+    int64_t M = 0, total_cap = 0;
+};
+
+extern "C" {
+
+int eut_slab_cells_destroy(eut_slab_cells *sc)
+{
+    if (!sc) return EUT_OK;
+    for (size_t r = 0; r < sc->cells.size(); r++) {
+        cudaSetDevice(sc->slab->parts[r].device);
+        if (r < sc->d_total.size()) cudaFree(sc->d_total[r]);
+        if (r < sc->d_ptrs.size()) cudaFree((void *)sc->d_ptrs[r]);
+        if (sc->cells[r]) eut_cells_destroy(sc->cells[r]);
+    }
+    delete sc;
+    return EUT_OK;
+}
+
+int eut_slab_cells_create(eut_slab_cells **out, eut_slab *slab)
+{
+    clear_error();
+    if (!out || !slab) { set_error("eut_slab_cells_create: NULL argument"); return EUT_ERR_ARG; }
+    *out = nullptr;
+    eut_slab_cells *sc = new eut_slab_cells();
+    sc->slab = slab;
+    const size_t W = slab->parts.size();
+    sc->cells.assign(W, nullptr);
+    sc->d_total.assign(W, nullptr);
+    sc->d_ptrs.assign(W, nullptr);
+    for (size_t r = 0; r < W; r++) {
+        const int rc = eut_cells_create(&sc->cells[r], slab->parts[r].plan);
+        if (rc != EUT_OK) { eut_slab_cells_destroy(sc); return rc; }
+    }
+    *out = sc;
+    return EUT_OK;
+}
+
+// `pts`: the GLOBAL field points (n_pts x 3, column-major, leading dimension ld), cells as eut_cells_build_lists
+int eut_slab_cells_build_lists(eut_slab_cells *sc, const double *pts, int64_t ld, int64_t n_pts, const double *cx, const double *cy,
+                               const double *csize, const double *cscv, int64_t n_cells, int dist_mode)
+{
+    clear_error();
+    if (!sc || !pts || n_pts != sc->slab->N || ld < n_pts || n_cells < 0) { set_error("eut_slab_cells_build_lists: bad argument (points must be the field's %lld)", sc ? (long long)sc->slab->N : 0ll); return EUT_ERR_ARG; }
+    eut_slab *s = sc->slab;
+    const size_t W = s->parts.size();
+    sc->M = n_cells;
+    for (size_t r = 0; r < W; r++) {
+        const eut_slab::Part &P = s->parts[r];
+        // local points in local id order; ghosts are the neighbour's to serve: out of every cell's reach
+        std::vector<double> lp((size_t)3 * P.n_local);
+        const double far = 1e300;
+        for (int64_t k = 0; k < P.n_local; k++) {
+            const int64_t g = P.local_global[k];
+            const bool own = P.is_own[k] != 0;
+            lp[k] = own ? pts[g] : far;
+            lp[P.n_local + k] = own ? pts[ld + g] : far;
+            lp[2 * P.n_local + k] = own ? pts[2 * ld + g] : far;
+        }
+        EUT_TRY(eut_cells_build_lists(sc->cells[r], lp.data(), P.n_local, cx, cy, csize, cscv, n_cells, dist_mode));
+    }
+    if (n_cells == 0) return EUT_OK;
+    // field.frac ingredients per cell over ALL its entries (R/run_simulation.R:729-730)
+    std::vector<double> dmax((size_t)n_cells, -INFINITY), tmp((size_t)n_cells), fsum((size_t)n_cells, 0.0);
+    for (size_t r = 0; r < W; r++) {
+        EUT_TRY(cells_get_dmax(sc->cells[r], tmp.data()));
+        for (int64_t i = 0; i < n_cells; i++) dmax[i] = std::max(dmax[i], tmp[i]);      // NaN distances: not produced by the cell map
+    }
+    for (size_t r = 0; r < W; r++) {
+        EUT_TRY(cells_partial_fsum(sc->cells[r], dmax.data(), tmp.data()));
+        for (int64_t i = 0; i < n_cells; i++) fsum[i] += tmp[i];
+    }
+    for (size_t r = 0; r < W; r++) EUT_TRY(cells_set_fsum(sc->cells[r], fsum.data()));
+    return EUT_OK;
+}
+
+int eut_slab_cells_claim_rescale(eut_slab_cells *sc)
+{
+    clear_error();
+    if (!sc) return EUT_ERR_ARG;
+    for (auto *c : sc->cells) EUT_TRY(eut_cells_claim_rescale(c));       // per field point: the owner sees every claimant
+    return EUT_OK;
+}
+
+int64_t eut_slab_cells_num_entries(const eut_slab_cells *sc)
+{
+    int64_t t = 0;
+    if (sc) for (auto *c : sc->cells) t += eut_cells_num_entries(c);
+    return t;
+}
+
+// entries of one slab with GLOBAL field ids (cell_ptr: n_cells + 1; the other arrays: eut_cells_num_entries of that slab)
+int eut_slab_cells_get_lists(const eut_slab_cells *sc, int slab_index, int64_t *n_entries, int64_t *cell_ptr, int32_t *field_id,
+                             double *field_dist, double *acc_prop)
+{
+    clear_error();
+    if (!sc || slab_index < 0 || slab_index >= (int)sc->cells.size()) { set_error("eut_slab_cells_get_lists: bad slab index"); return EUT_ERR_ARG; }
+    const eut_cells *c = sc->cells[slab_index];
+    const int64_t t = eut_cells_num_entries(c);
+    if (n_entries) *n_entries = t;
+    if (!cell_ptr && !field_id && !field_dist && !acc_prop) return EUT_OK;
+    EUT_TRY(eut_cells_get_lists(c, cell_ptr, field_id, field_dist, acc_prop));
+    if (field_id) {
+        const eut_slab::Part &P = sc->slab->parts[slab_index];
+        for (int64_t k = 0; k < t; k++) field_id[k] = P.local_global[field_id[k] - 1] + 1;
+    }
+    return EUT_OK;
+}
+
+// accessible amounts of every compound for every cell (M x C, column-major; fmol_host may be NULL)
+int eut_slab_cells_gather(eut_slab_cells *sc, double field_vol, double *fmol_host)
+{
+    clear_error();
+    if (!sc) return EUT_ERR_ARG;
+    eut_slab *s = sc->slab;
+    const size_t W = s->parts.size();
+    const int64_t n = sc->M * s->C;
+    if (n == 0) return EUT_OK;
+    for (size_t r = 0; r < W; r++) EUT_TRY(eut_cells_gather(sc->cells[r], s->parts[r].field, field_vol, nullptr));
+    for (size_t r = 0; r < W; r++) { EUT_TRY(ensure_device(s->parts[r].device)); EUT_CUDA(cudaStreamSynchronize(s->parts[r].field->stream)); }
+    std::vector<const double *> h_ptrs(W);
+    for (size_t r = 0; r < W; r++) h_ptrs[r] = cells_fmol(sc->cells[r]);
+    for (size_t r = 0; r < W; r++) {
+        EUT_TRY(ensure_device(s->parts[r].device));
+        if (n > sc->total_cap || !sc->d_total[r]) {
+            cudaFree(sc->d_total[r]); sc->d_total[r] = nullptr;
+            EUT_CUDA(cudaMalloc((void **)&sc->d_total[r], (size_t)(n + n / 8 + 16) * sizeof(double)));
+        }
+        if (!sc->d_ptrs[r]) EUT_CUDA(cudaMalloc((void **)&sc->d_ptrs[r], W * sizeof(double *)));
+        cudaStream_t st = s->parts[r].field->stream;
+        EUT_CUDA(cudaMemcpyAsync((void *)sc->d_ptrs[r], h_ptrs.data(), W * sizeof(double *), cudaMemcpyHostToDevice, st));
+        k_sum_partials<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sc->d_total[r], sc->d_ptrs[r], (int)W, n);
+        EUT_CUDA(cudaGetLastError());
+        s->parts[r].field->launches++;
+    }
+    sc->total_cap = std::max(sc->total_cap, n + n / 8 + 16);
+    // every slab has read every partial sum before any of them is replaced by the total
+    for (size_t r = 0; r < W; r++) { EUT_TRY(ensure_device(s->parts[r].device)); EUT_CUDA(cudaStreamSynchronize(s->parts[r].field->stream)); }
+    for (size_t r = 0; r < W; r++) {
+        EUT_TRY(ensure_device(s->parts[r].device));
+        EUT_CUDA(cudaMemcpyAsync(cells_fmol(sc->cells[r]), sc->d_total[r], (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s->parts[r].field->stream));
+        cells_mark_gathered(sc->cells[r], s->parts[r].field, field_vol);
+    }
+    if (fmol_host) {
+        EUT_TRY(ensure_device(s->parts[0].device));
+        EUT_CUDA(cudaMemcpyAsync(fmol_host, sc->d_total[0], (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s->parts[0].field->stream));
+        EUT_CUDA(cudaStreamSynchronize(s->parts[0].field->stream));
+    }
+    return EUT_OK;
+}
+
+// apply the cells' exchange fluxes to the sharded field and clamp (eut_cells_scatter on every slab, with the
+// colSums over all slabs: a gather that is not current for this state of the field is taken first)
+int eut_slab_cells_scatter(eut_slab_cells *sc, double field_vol, const uint8_t *is_constant, const int64_t *ex_ptr,
+                           const int32_t *ex_cpd, const double *ex_flx)
+{
+    clear_error();
+    if (!sc || !ex_ptr) { set_error("eut_slab_cells_scatter: bad argument"); return EUT_ERR_ARG; }
+    eut_slab *s = sc->slab;
+    const size_t W = s->parts.size();
+    if (sc->M == 0 || ex_ptr[sc->M] == 0) return EUT_OK;
+    bool current = true;
+    for (size_t r = 0; r < W; r++) current = current && cells_gather_is_current(sc->cells[r], s->parts[r].field, field_vol);
+    if (!current) EUT_TRY(eut_slab_cells_gather(sc, field_vol, nullptr));
+    for (size_t r = 0; r < W; r++)
+        EUT_TRY(eut_cells_scatter(sc->cells[r], s->parts[r].field, field_vol, is_constant, ex_ptr, ex_cpd, ex_flx));
+    return EUT_OK;
+}
+
+}  // extern "C"

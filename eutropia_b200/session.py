@@ -345,3 +345,59 @@ class SlabField:
     @property
     def launch_count(self) -> int:
         return int(_lib.lib().eut_slab_launch_count(self._h))
+
+
+class SlabCells:
+    """Cells on a slab-sharded field (`eut_slab_cells_*`): same calls as `Cells`, the field is the `SlabField`
+    given at construction.  Per-field work runs on the slab that owns the point, per-cell quantities are
+    combined over the slabs a cell touches."""
+
+    def __init__(self, slab: SlabField):
+        self.slab = slab
+        self.n_cells = 0
+        h = C.c_void_p()
+        check(_lib.lib().eut_slab_cells_create(C.byref(h), slab._h))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(_lib, "lib", None) and getattr(self.slab, "_h", None):
+            _lib.lib().eut_slab_cells_destroy(self._h)
+        self._h = None
+
+    __del__ = close
+
+    def build_lists(self, pts, cx, cy, csize, cscv, dist_mode=0):
+        p = _colmajor(pts)
+        cx, cy, csize, cscv = (_f64c(a) for a in (cx, cy, csize, cscv))
+        self.n_cells = cx.shape[0]
+        check(_lib.lib().eut_slab_cells_build_lists(self._h, ptr(p), p.shape[0], p.shape[0], ptr(cx), ptr(cy), ptr(csize),
+                                                    ptr(cscv), self.n_cells, int(dist_mode)))
+
+    def claim_rescale(self):
+        check(_lib.lib().eut_slab_cells_claim_rescale(self._h))
+
+    @property
+    def n_entries(self) -> int:
+        return int(_lib.lib().eut_slab_cells_num_entries(self._h))
+
+    def get_lists(self, slab_index: int):
+        """(cell_ptr, global field ids, distances, acc.prop) of the entries one slab holds."""
+        n = C.c_int64()
+        check(_lib.lib().eut_slab_cells_get_lists(self._h, int(slab_index), C.byref(n), None, None, None, None))
+        t = int(n.value)
+        cp = np.zeros(self.n_cells + 1, dtype=np.int64)
+        fid = np.zeros(max(t, 1), dtype=np.int32)
+        fd = np.zeros(max(t, 1)); acc = np.zeros(max(t, 1))
+        check(_lib.lib().eut_slab_cells_get_lists(self._h, int(slab_index), C.byref(n), ptr(cp), ptr(fid), ptr(fd), ptr(acc)))
+        return cp, fid[:t], fd[:t], acc[:t]
+
+    def gather(self, field_vol: float, want_host=True):
+        out = np.zeros((self.n_cells, self.slab.n_cols), dtype=np.float64, order="F") if want_host else None
+        check(_lib.lib().eut_slab_cells_gather(self._h, float(field_vol), ptr(out)))
+        return out
+
+    def scatter(self, field_vol: float, is_constant, ex_ptr, ex_cpd, ex_flx):
+        isc = None if is_constant is None else np.ascontiguousarray(is_constant, dtype=np.uint8)
+        ep = np.ascontiguousarray(ex_ptr, dtype=np.int64)
+        ec, ef = _i32(ex_cpd), _f64c(ex_flx)
+        check(_lib.lib().eut_slab_cells_scatter(self._h, float(field_vol), ptr(isc), ptr(ep), ptr(ec), ptr(ef)))

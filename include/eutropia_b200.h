@@ -327,6 +327,25 @@ EUT_API int eut_slab_diffuse(eut_slab *slab, const int32_t *niter, const int32_t
 EUT_API int eut_slab_sync(eut_slab *slab);
 EUT_API int64_t eut_slab_launch_count(const eut_slab *slab);
 
+/* Cells on a slab-sharded field.  Every slab keeps, of every cell, the entries on its own points;
+ * per-field work (claim rescale, scatter sums in cell order, clamp) runs on the owner exactly as on an
+ * unsharded field, per-cell quantities (production shares, accessible amounts = colSums of the uptake
+ * shares) are combined over the slabs a cell touches.  Same argument meaning as eut_cells_*; `pts` are the
+ * global field points, field ids in eut_slab_cells_get_lists are global. */
+typedef struct eut_slab_cells eut_slab_cells;
+EUT_API int eut_slab_cells_create(eut_slab_cells **out, eut_slab *slab);
+EUT_API int eut_slab_cells_destroy(eut_slab_cells *cells);
+EUT_API int eut_slab_cells_build_lists(eut_slab_cells *cells, const double *pts, int64_t ld, int64_t n_pts,
+                                       const double *cx, const double *cy, const double *csize, const double *cscv,
+                                       int64_t n_cells, int dist_mode);
+EUT_API int eut_slab_cells_claim_rescale(eut_slab_cells *cells);
+EUT_API int64_t eut_slab_cells_num_entries(const eut_slab_cells *cells);
+EUT_API int eut_slab_cells_get_lists(const eut_slab_cells *cells, int slab_index, int64_t *n_entries, int64_t *cell_ptr,
+                                     int32_t *field_id, double *field_dist, double *acc_prop);
+EUT_API int eut_slab_cells_gather(eut_slab_cells *cells, double field_vol, double *fmol_host);
+EUT_API int eut_slab_cells_scatter(eut_slab_cells *cells, double field_vol, const uint8_t *is_constant,
+                                   const int64_t *ex_ptr, const int32_t *ex_cpd, const double *ex_flx);
+
 /* ---- session tier: cells = ragged cell -> field lists + gather / scatter ----------------------
  * Lists follow get_cellFieldEnv_ex's output (R/run_simulation.R:591-624): per cell the field ids
  * (1-based), the cell-field distances and the accessible proportions, in CSR form. */

@@ -108,3 +108,66 @@ def test_slab_errors_mirror_the_field(harbor_mesh):
     sf.close()
     with pytest.raises(eb.EutropiaError):
         eb.SlabField(m.mat_in, m.mat_out, 3, [0, 77])
+
+
+@pytest.mark.parametrize("devices", [[0, 0], [0, 0, 0, 0], "all"])
+def test_cells_on_slabs_match_the_unsharded_round(devices):
+    """eut_slab_cells_*: every slab holds the entries of every cell on its OWN points; per-field work (claim
+    rescale, scatter sums in cell order, clamp) is the owner's, per-cell quantities (production shares,
+    accessible amounts) are combined over the slabs.  Lists: the union over the slabs is the unsharded list,
+    entry for entry, and what only depends on the field point (acc.prop after the claim rescale) has the
+    same bits.  A whole round -- gather, scatter + clamp, substeps, gather -- stays within 1e-12 of the
+    unsharded field (cells across a cut add their partial sums in another order), two rounds in a row."""
+    from eutropia_b200 import synth
+    if devices == "all":                      # one slab per GPU of the box (two on a one-GPU box): partial sums cross NVLink
+        n_dev = _lib.lib().eut_device_count()
+        devices = [k % n_dev for k in range(max(2, n_dev))]
+    m = eb.mesh.make_mesh(eb.mesh.harbor_polygon(90.0), 1.0, 3)
+    n_cols, n_cells = 6, 220
+    conc = synth.synthetic_concentrations(m.field_pts, n_cols, seed=41)
+    cx, cy, size, scv = synth.place_cells(m, n_cells, seed=42)
+    ex_ptr, ex_cpd, ex_flx = synth.synthetic_exchanges(n_cells, n_cols, 3, seed=43)
+    ex_flx = ex_flx * 1e-3
+    is_const = np.array([0, 0, 1, 0, 0, 0], dtype=np.uint8)
+    niter, indvar = [9, 4, 6, 9, 1], [1, 2, 4, 5, 6]
+    # unsharded
+    plan = eb.Plan(m.mat_in, m.mat_out)
+    fld = eb.Field(plan, n_cols)
+    fld.upload(conc)
+    cells = eb.Cells(plan)
+    cells.build_lists(m.field_pts, cx, cy, size, scv)
+    cells.claim_rescale()
+    ptr, fid, fd, acc = cells.get_lists()
+    # sharded
+    sf = eb.SlabField(m.mat_in, m.mat_out, n_cols, devices)
+    sf.upload(conc)
+    sc = eb.SlabCells(sf)
+    sc.build_lists(m.field_pts, cx, cy, size, scv)
+    sc.claim_rescale()
+    assert sc.n_entries == fid.size
+    key = lambda p, f: (np.repeat(np.arange(n_cells), np.diff(p)).astype(np.int64) << 32) | f.astype(np.int64)
+    parts = [sc.get_lists(r) for r in range(len(devices))]
+    k_all = np.concatenate([key(p[0], p[1]) for p in parts])
+    order = np.argsort(k_all, kind="stable")
+    ref_order = np.argsort(key(ptr, fid), kind="stable")
+    assert np.array_equal(k_all[order], key(ptr, fid)[ref_order])                       # same (cell, field) pairs, each once
+    assert np.array_equal(np.concatenate([p[2] for p in parts])[order], fd[ref_order])     # distances: same bits
+    assert np.array_equal(np.concatenate([p[3] for p in parts])[order], acc[ref_order])    # acc.prop after the claim rescale: same bits
+    assert sum(1 for p in parts if p[1].size) == len(devices)                            # every slab serves some cells
+    for _ in range(2):
+        a0, b0 = cells.gather(fld, m.field_vol), sc.gather(m.field_vol)
+        assert np.all(np.abs(a0 - b0) <= 1e-12 * np.abs(a0))
+        cells.scatter(fld, m.field_vol, is_const, ex_ptr, ex_cpd, ex_flx)
+        sc.scatter(m.field_vol, is_const, ex_ptr, ex_cpd, ex_flx)
+        whole, shard = fld.download(), sf.download()
+        assert np.all(np.abs(whole - shard) <= 1e-12 * np.abs(whole)) and np.array_equal(whole == 0, shard == 0)
+        fld.diffuse(niter, indvar)
+        sf.diffuse(niter, indvar)
+        whole, shard = fld.download(), sf.download()
+        assert np.all(np.abs(whole - shard) <= 1e-12 * np.abs(whole))
+    # a scatter without a current gather takes one itself (the colSums must span the slabs)
+    cells.scatter(fld, m.field_vol, is_const, ex_ptr, ex_cpd, ex_flx)
+    sc.scatter(m.field_vol, is_const, ex_ptr, ex_cpd, ex_flx)
+    whole, shard = fld.download(), sf.download()
+    assert np.all(np.abs(whole - shard) <= 1e-12 * np.abs(whole))
+    sc.close(); sf.close()

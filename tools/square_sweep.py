@@ -30,7 +30,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     ms = e0.elapsed_time(e1) / 3
     print(json.dumps({"tile": os.environ.get("EUT_SEG_TILE", "auto"), "cpt": cpt, "tiles": int(plan.info.n_tiles), "us_per_substep": ms, "G_updates_per_s": n * c * s / ms / 1e6}))
     sys.exit(0)
-for tile in ("224", "112", "56"):
+for tile in ("448", "224", "112"):
     for cpt in (0, 8, 4, 2, 1):
         env = dict(os.environ, EUT_SEG_TILE=tile)
         r = subprocess.run([sys.executable, __file__, "child", str(cpt)], env=env, capture_output=True, text=True)
