@@ -452,6 +452,36 @@ def run_ours(args):
     updates_per_step = n * cpg * world * substeps
     value = updates_per_step * args.steps / (ms * 1e-3)
 
+    # ---- BASELINE.json configs[3] as a FIXED problem: 512 compounds over the N GPUs (256 / 128 / 64 columns per
+    # GPU at N = 2 / 4 / 8; the N = 8 case is the weak-scaling run above).  Diffusion only, device time, max over ranks.
+    fixed512 = None
+    if world in (2, 4) and not args.no_extra and args.workload == "harbor1m":
+        cols_f = 512 // world
+        f2 = eb.Field(plan, cols_f)
+        for c0 in range(0, cols_f, cpg):
+            f2.upload(conc, cols=np.arange(c0 + 1, c0 + cpg + 1, dtype=np.int32))
+        nit2, iv2 = np.full(cols_f, substeps, dtype=np.int32), np.arange(1, cols_f + 1, dtype=np.int32)
+        st2 = torch.cuda.ExternalStream(f2.stream, device=dev)
+        for _ in range(2):
+            f2.diffuse(nit2, iv2)
+        f2.sync(); torch.cuda.synchronize(); dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        with torch.cuda.stream(st2):
+            a.record()
+        for _ in range(reps):
+            f2.diffuse(nit2, iv2)
+        with torch.cuda.stream(st2):
+            b.record()
+        f2.sync(); torch.cuda.synchronize()
+        tf = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device=f"cuda:{dev}")
+        dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+        f2.close()
+        v512 = n * 512 * substeps / (float(tf[0]) * 1e-3)
+        fixed512 = {"workload": f"configs[3] as a fixed problem: {n} points x 512 compounds x {substeps} substeps, {cols_f} columns per GPU, diffusion only",
+                    "value": v512, "unit": UNIT, "ms_per_step": float(tf[0]), "columns_per_gpu": cols_f,
+                    "frac_of_hbm_peak_per_gpu": BYTES_PER_UPDATE * v512 / world / 1e9 / peaks()[0]}
+
     # ---- parity gate on the timed configuration (outside the timed regions) -------------------
     parity = parity_gate(eb, mesh, plan, conc, substeps, dev) if (rank == 0 and not args.no_parity) else None
 
@@ -608,6 +638,8 @@ def run_ours(args):
         }
         if e2e_ranks is not None:
             line["e2e_ranks"] = e2e_ranks
+        if fixed512 is not None:
+            line["configs3_fixed_512"] = fixed512
         line.update(extra)
         emit(line)
     if world > 1:
