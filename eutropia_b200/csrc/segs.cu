@@ -288,6 +288,32 @@ int build_segs(eut_plan *p, const SegParams &sp)
             }
         }
     }
+    // Layer of every row, relative: rows linked without the pair flag share a layer, a pair-flagged neighbour with
+    // higher ids lies one layer up (ids are layer major, R/growthEnvironment.R:104-117).  Only used to keep the
+    // residue statistics of the gap rule apart per layer.
+    constexpr int kMaxSegLayers = 16;
+    std::vector<int32_t> layer_of_row(NR, INT32_MIN);
+    int32_t min_layer = 0;
+    {
+        std::vector<int32_t> stack;
+        for (int32_t seed = 0; seed < NR; seed++) {
+            if (layer_of_row[seed] != INT32_MIN) continue;
+            layer_of_row[seed] = 0;
+            stack.push_back(seed);
+            while (!stack.empty()) {
+                const int32_t r = stack.back();
+                stack.pop_back();
+                for (int64_t a = ra.adj_ptr[r]; a < ra.adj_ptr[r + 1]; a++) {
+                    const int32_t rr = ra.adj_row[a];
+                    if (layer_of_row[rr] != INT32_MIN) continue;
+                    layer_of_row[rr] = layer_of_row[r] + (ra.adj_pair[a] ? (rr > r ? 1 : -1) : 0);
+                    stack.push_back(rr);
+                }
+            }
+        }
+        for (int32_t r = 0; r < NR; r++) min_layer = std::min(min_layer, layer_of_row[r]);
+    }
+    const bool balance_residues = !getenv("EUT_SEG_NO_BALANCE");
     // Residue step per strip (pad_rows 3): position - u == step * krow (mod 16).  Full-width pieces
     // (8 segments) pack two rows per half warp with step 8 and need no gaps; narrow strips (polygon
     // border) need more distinct row residues to fill 16 lanes with distinct bank pairs: step 4 / 2 / 1.
@@ -338,16 +364,108 @@ int build_segs(eut_plan *p, const SegParams &sp)
             const int32_t k0 = tile_piece0[t], k1 = tile_piece0[t + 1];
             gap.assign(k1 - k0, 0);
             if (sp.pad_rows == 1 && k1 - k0 > 1) {
-                // chain rule: rho advances by the same step s from piece to piece
-                int64_t best_total = INT64_MAX;
-                int best_s = 8;
-                for (int s = 1; s < 16; s++) {
-                    int64_t total = 0;
-                    for (int32_t k = k0; k + 1 < k1; k++) {
-                        const Piece &a = pieces[ord[k]], &b = pieces[ord[k + 1]];
-                        total += (((s + u_of(b.first) - u_of(a.first) - a.count) % 16) + 16) % 16;
+                // coordinate rule: rho = position - u of a piece is a function of WHERE its row is,
+                //     rho == a * (row index inside its layer) + b * layer + (odd layer ? c : 0)   (mod 16),
+                // so every stream of every segment of the tile's own block keeps the same residue shift against
+                // the segment's own cells -- however many pieces a level has and in whatever order they are
+                // stored (the chain rule below loses that in ragged tiles: rows cut into two pieces, layers
+                // missing at the border) -- and a half warp is conflict free in all seven streams as soon as
+                // its 16 segments start on 16 different residues.  (a, b, c) per tile: the triple that costs the
+                // fewest gap cells plus the extra half-warp passes an unbalanced residue histogram of some layer
+                // would force (16 x R cells each); a = 0 puts all rows of a layer on the same 8 residues and
+                // doubles the tile's time (tools/tile_times.py: 75-86 us against 42 us per 32 columns).
+                const int32_t np_ = k1 - k0;
+                std::vector<int32_t> kr(np_), ly(np_), uu(np_), nseg(np_), dfix(np_, 0);
+                int nl = 0;
+                for (int32_t k = 0; k < np_; k++) {
+                    const Piece &pc = pieces[ord[k0 + k]];
+                    const int32_t r = ra.row_of[pc.first];
+                    kr[k] = krow[r];
+                    ly[k] = std::min(kMaxSegLayers - 1, std::max(0, layer_of_row[r] - min_layer));
+                    nl = std::max(nl, ly[k] + 1);
+                    uu[k] = u_of(pc.first);
+                    nseg[k] = (pc.count + R - 1) / R;
+                    if (k > 0) dfix[k] = uu[k] - uu[k - 1] - pieces[ord[k0 + k - 1]].count;
+                }
+                int64_t best_cost = INT64_MAX;
+                int best_a = 8, best_b = 0, best_c = 0;
+                std::vector<int32_t> want(np_);
+                for (int a = 0; a < 16; a++)
+                    for (int b = 0; b < 16; b++)
+                        for (int c = 0; c < 16; c++) {
+                            int64_t total = 0;
+                            for (int32_t k = 0; k < np_; k++) {
+                                want[k] = a * kr[k] + b * ly[k] + ((ly[k] & 1) ? c : 0);
+                                if (k > 0) total += ((want[k] - want[k - 1] + dfix[k]) % 16 + 16) % 16;
+                            }
+                            if (total >= best_cost) continue;                 // the penalty only adds
+                            int32_t hist[kMaxSegLayers][16] = {};
+                            int32_t n_layer[kMaxSegLayers] = {};
+                            for (int32_t k = 0; k < np_; k++) {
+                                const int32_t r0 = ((want[k] + uu[k]) % 16 + 16) % 16;
+                                for (int32_t j = 0; j < nseg[k]; j++) hist[ly[k]][(r0 + R * j) & 15]++;
+                                n_layer[ly[k]] += nseg[k];
+                            }
+                            int64_t extra = 0;
+                            for (int l = 0; l < nl; l++)
+                                if (n_layer[l]) extra += std::max(0, *std::max_element(hist[l], hist[l] + 16) - (n_layer[l] + 15) / 16);
+                            const int64_t cost = total + extra * 16 * R;
+                            if (cost < best_cost) { best_cost = cost; best_a = a; best_b = b; best_c = c; }
+                        }
+                if (const char *e = getenv("EUT_TRACE_TILE"))
+                    if (atoi(e) == t) {
+                        fprintf(stderr, "[eut] tile %d: a %d b %d c %d cost %lld\n", t, best_a, best_b, best_c, (long long)best_cost);
+                        for (int32_t k = 0; k < np_; k++)
+                            fprintf(stderr, "[eut]   piece %3d: row %5d level %4d layer %d krow %4d u %5d count %3d\n", k, ra.row_of[pieces[ord[k0 + k]].first],
+                                    pieces[ord[k0 + k]].level, ly[k], kr[k], uu[k], pieces[ord[k0 + k]].count);
                     }
-                    if (total < best_total || (total == best_total && s == 8)) { best_total = total; best_s = s; }
+                int64_t tile_pts = 0, tile_gap = 0;
+                for (int32_t k = 0; k < np_; k++) tile_pts += pieces[ord[k0 + k]].count;
+                for (int32_t k = 1; k < np_; k++) {
+                    const int32_t w1 = best_a * kr[k] + best_b * ly[k] + ((ly[k] & 1) ? best_c : 0);
+                    const int32_t w0 = best_a * kr[k - 1] + best_b * ly[k - 1] + ((ly[k - 1] & 1) ? best_c : 0);
+                    gap[k - 1] = ((w1 - w0 + dfix[k]) % 16 + 16) % 16;
+                    tile_gap += gap[k - 1];
+                }
+                // not a lattice (renumbered ids: rows of one or two points): residues cannot be arranged, and the
+                // gap cells would outnumber the points
+                if (tile_gap * 4 > tile_pts) gap.assign(k1 - k0, 0);
+            }
+            if (sp.pad_rows == 2 && k1 - k0 > 1) {
+                // chain rule: rho advances by the same step s from piece to piece.  Which s?  The one that costs
+                // the fewest gap cells -- as long as the segments' start residues stay BALANCED inside every
+                // layer: a half warp is conflict free only if its 16 segments start on 16 different residues, so
+                // a residue that n segments of a layer share forces n half warps however the lanes are dealt.
+                // (A tile whose rows come in an even number of pieces per level has a same-layer step of 0 with
+                // s = 8: every row on the same 8 residues, twice the shared-memory wavefronts and twice the tile
+                // time -- 75-86 us against 42 us per 32 columns on the bench mesh, tools/tile_times.py.)  Cost of
+                // an s = gap cells + the extra half-warp passes its worst residue forces, at 16 x R cells each.
+                int64_t best_cost = INT64_MAX;
+                int best_s = 8;
+                for (int s = 0; s < 16; s++) {
+                    int64_t total = 0;
+                    int32_t hist[kMaxSegLayers][16] = {};
+                    int32_t n_layer[kMaxSegLayers] = {};
+                    int32_t at = 0;                              // position relative to the tile's first cell
+                    for (int32_t k = k0; k < k1; k++) {
+                        const Piece &a = pieces[ord[k]];
+                        const int l = std::min(kMaxSegLayers - 1, std::max(0, layer_of_row[ra.row_of[a.first]] - min_layer));
+                        for (int32_t q = 0; q < a.count; q += R) { hist[l][(at + q) & 15]++; n_layer[l]++; }
+                        at += a.count;
+                        if (k + 1 < k1) {
+                            const Piece &b = pieces[ord[k + 1]];
+                            const int32_t g = (((s + u_of(b.first) - u_of(a.first) - a.count) % 16) + 16) % 16;
+                            total += g; at += g;
+                        }
+                    }
+                    int64_t extra = 0;
+                    for (int l = 0; l < kMaxSegLayers; l++) {
+                        if (n_layer[l] == 0) continue;
+                        const int32_t need = (n_layer[l] + 15) / 16;
+                        extra += std::max(0, *std::max_element(hist[l], hist[l] + 16) - need);
+                    }
+                    const int64_t cost = total + (balance_residues ? extra * 16 * R : 0);
+                    if (cost < best_cost || (cost == best_cost && s == 8)) { best_cost = cost; best_s = s; }
                 }
                 for (int32_t k = k0; k + 1 < k1; k++) {
                     const Piece &a = pieces[ord[k]], &b = pieces[ord[k + 1]];

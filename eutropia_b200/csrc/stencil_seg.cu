@@ -89,6 +89,15 @@ __device__ __forceinline__ void s_bulk_wait_read() { asm volatile("cp.async.bulk
 }  // namespace
 
 
+// debug (dbg & 2048): nanoseconds every CTA of the last launch lived, by (slice, tile); read with eut_debug_tile_ns
+__device__ unsigned long long g_tile_ns[2 * 4096];
+__device__ __forceinline__ unsigned long long s_globaltimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;\n" : "=l"(t));
+    return t;
+}
+
 template <int R, int SPT, int CWARPS, int NBUF, int OB, int MINB>
 __global__ void __launch_bounds__((CWARPS + 1) * 32, MINB)
 k_substep_seg(double *__restrict__ buf, const int64_t col_stride, const int64_t buf_stride,
@@ -109,6 +118,7 @@ k_substep_seg(double *__restrict__ buf, const int64_t col_stride, const int64_t 
     __shared__ long long s_src[kTileMaxCols], s_dst[kTileMaxCols];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
+    const unsigned long long t_start = (dbg & 2048) ? s_globaltimer() : 0ull;
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");    // the next launch of the stream may start its prologue
     const int tile = tile_list ? __ldg(tile_list + blockIdx.x) : (int)blockIdx.x;
     const int a_begin = blockIdx.y * cols_per_cta;
@@ -225,6 +235,7 @@ k_substep_seg(double *__restrict__ buf, const int64_t col_stride, const int64_t 
             }
         }
         if (lane == 0) s_bulk_wait_read<0>();
+        if ((dbg & 2048) && lane == 0 && blockIdx.y < 2 && tile < 4096) g_tile_ns[blockIdx.y * 4096 + tile] = s_globaltimer() - t_start;
         return;
     }
 
@@ -407,6 +418,13 @@ static int launch_seg_t(eut_field *f, int n_act, int substep)
                                 n_act, substep, img_bytes, out_bytes, cols_per_cta, f->opt_debug, tile_list));
     return EUT_OK;
 }
+
+}  // namespace eut
+extern "C" __attribute__((visibility("default"))) int eut_debug_tile_ns(unsigned long long *out, int n)
+{
+    return cudaMemcpyFromSymbol(out, eut::g_tile_ns, sizeof(unsigned long long) * (size_t)std::min(n, 2 * 4096)) == cudaSuccess ? 0 : 1;
+}
+namespace eut {
 
 // Kernel shapes: (R, segments per thread, consumer warps, image slots, result buffers, CTAs per SM).
 // The plan's tile capacity (EUT_SEG_TILE, default 224 segments) picks the shape.
