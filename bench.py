@@ -587,10 +587,17 @@ def run_ours(args):
     peak, peak_src = peaks()
     extra = {}
     if rank == 0 and not args.no_extra:
-        extra["square100k"] = square100k_leg(eb, torch, dev, peak)
+        # a leg that fails (its own parity gate included) reports the failure under its key, without a value; the
+        # headline line above has its own gate and is not affected
+        def leg(fn, *a):
+            try:
+                return fn(*a)
+            except (Exception, SystemExit) as e:
+                return {"error": f"{type(e).__name__}: {e}"[:400]}
+        extra["square100k"] = leg(square100k_leg, eb, torch, dev, peak)
         if world > 1:
             # the other ranks idle on the host barrier below; their GPUs are driven from here
-            extra["slab"] = slab_leg(eb, torch, world, peak)
+            extra["slab"] = leg(slab_leg, eb, torch, world, peak)
     if world > 1:
         host_barrier()
 
