@@ -85,6 +85,7 @@ def lib() -> C.CDLL:
         "eut_field_upload": (C.c_int, [vp, vp, i64, vp, i64]),
         "eut_field_download": (C.c_int, [vp, vp, i64, vp, i64]),
         "eut_field_record": (C.c_int, [vp, vp, i64, vp, i64, C.c_int]),
+        "eut_debug_tile_ns": (C.c_int, [vp, C.c_int]),
         "eut_field_diffuse": (C.c_int, [vp, vp, vp, i64]),
         "eut_field_sync": (C.c_int, [vp]),
         "eut_field_stream": (vp, [vp]),
@@ -140,7 +141,7 @@ EXPORTS = (
     "eut_oneshot_reset eut_build_dcm eut_plan_create eut_plan_destroy eut_plan_get_info eut_plan_get_csr "
     "eut_plan_get_perm eut_plan_get_tiles eut_plan_get_segs eut_field_create eut_field_destroy eut_field_upload eut_field_download eut_field_record "
     "eut_field_diffuse eut_field_sync eut_field_stream eut_field_set_stream "
-    "eut_field_launch_count eut_field_set_option eut_field_column_stats eut_field_fill_column "
+    "eut_field_launch_count eut_field_set_option eut_debug_tile_ns eut_field_column_stats eut_field_fill_column "
     "eut_field_exoenzyme_catalysis eut_field_scale_column "
     "eut_field_halo_set eut_field_set_halo_stream eut_field_halo_pack eut_field_halo_unpack "
     "eut_slab_create eut_slab_destroy eut_slab_get_info eut_slab_part eut_slab_upload eut_slab_download "

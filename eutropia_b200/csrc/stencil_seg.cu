@@ -420,7 +420,7 @@ static int launch_seg_t(eut_field *f, int n_act, int substep)
 }
 
 }  // namespace eut
-extern "C" __attribute__((visibility("default"))) int eut_debug_tile_ns(unsigned long long *out, int n)
+extern "C" EUT_API int eut_debug_tile_ns(unsigned long long *out, int n)
 {
     return cudaMemcpyFromSymbol(out, eut::g_tile_ns, sizeof(unsigned long long) * (size_t)std::min(n, 2 * 4096)) == cudaSuccess ? 0 : 1;
 }

@@ -243,6 +243,10 @@ EUT_API int eut_field_set_stream(eut_field *field, void *cuda_stream);
 EUT_API int64_t eut_field_launch_count(const eut_field *field);
 /* Kernel variant selection for experiments: see DESIGN.md ("kernel variants"). */
 EUT_API int eut_field_set_option(eut_field *field, const char *name, int64_t value);
+/* Diagnostics: with option "debug" bit 2048 set, every CTA of the segment kernel records how long it lived;
+ * this copies the nanoseconds of the last launch, [2][4096] by (column slice 0 / 1, tile), from the current
+ * device (tools/tile_times.py relates them to the tiles' properties).  Returns 0 on success. */
+EUT_API int eut_debug_tile_ns(unsigned long long *out, int n);
 /* Concentration recording (R/run_simulation.R:511-514, `round(COI.rec, digits = 7)`): like
  * eut_field_download, with every value rounded to `digits` (1..15) decimals on the device on its way out, by
  * base R's rule (the decimal neighbour closer to the represented value, ties to even).  The RDS file itself

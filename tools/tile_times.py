@@ -26,7 +26,6 @@ field.diffuse(niter, iv)
 field.sync()
 L = _lib.lib()
 buf = (C.c_ulonglong * 8192)()
-L.eut_debug_tile_ns.argtypes = [C.c_void_p, C.c_int]
 assert L.eut_debug_tile_ns(buf, 8192) == 0
 ns = np.frombuffer(buf, dtype=np.uint64).reshape(2, 4096)[:, :meta.shape[0]].astype(np.float64)
 t = ns[0] / 1e3                                        # us per CTA (slice 0)
