@@ -152,6 +152,31 @@ def build_inputs(workload: str, n_cols: int, seed: int, want_conc=True):
     return mesh, conc, cells, ex, substeps
 
 
+def numa_nodes() -> int:
+    try:
+        return max(1, sum(1 for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()))
+    except OSError:
+        return 1
+
+
+def interleave_host_memory(on: bool) -> bool:
+    """MPOL_INTERLEAVE over all NUMA nodes for the pages this thread touches from now on (what `numactl
+    --interleave=all R` does for an R session): one process feeding N GPUs from a matrix that lives on ONE node is
+    bound by that node's memory channels and the inter-socket link.  Returns whether the policy was set."""
+    try:
+        import ctypes
+        n = numa_nodes()
+        if n < 2 and on:
+            return False
+        libc = ctypes.CDLL(None, use_errno=True)
+        mask = ctypes.c_ulong((1 << n) - 1)
+        mode = 3 if on else 0                                   # MPOL_INTERLEAVE / MPOL_DEFAULT
+        rc = libc.syscall(238, mode, ctypes.byref(mask) if on else None, ctypes.c_ulong(n + 1 if on else 0))   # SYS_set_mempolicy (x86-64)
+        return rc == 0
+    except Exception:
+        return False
+
+
 def host_threads() -> int:
     """Host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which is about torch's
     intra-op threads and not a limit on the box: the reference's policy is `detectCores() - 1`,
@@ -551,6 +576,7 @@ def run_ours(args):
             if rank == 0:
                 os.environ.pop("LOCAL_WORLD_SIZE", None)
                 ct = cpg * world
+                interleaved = interleave_host_memory(True)
                 big_in = torch.empty((ct, n), dtype=torch.float64).pin_memory()
                 for r in range(world):
                     big_in[r * cpg:(r + 1) * cpg].copy_(pin_in)
@@ -570,7 +596,8 @@ def run_ours(args):
                 call, swap = multi(bufs, lambda t: t.data_ptr())
                 dt = time_calls(call, swap)
                 e2e.update(value=updates_per_step * e2e_steps / dt,
-                           api=f"eut_diffchange_par_multi: ONE process, {world} GPUs, {ct} columns in one call (pinned host buffers)")
+                           api=f"eut_diffchange_par_multi: ONE process, {world} GPUs, {ct} columns in one call (pinned host buffers"
+                               + (f", pages interleaved over {numa_nodes()} NUMA nodes)" if interleaved else ")"))
                 # every GPU started from the same 64 columns: the blocks of the result must agree bit for bit
                 e2e["blocks_agree"] = all(bool(torch.equal(bufs[0][:cpg], bufs[0][r * cpg:(r + 1) * cpg])) for r in range(1, world))
                 pg = [bufs[0].numpy().copy(), np.zeros((ct, n))]
@@ -580,6 +607,7 @@ def run_ours(args):
                 e2e["pageable_value"] = updates_per_step * e2e_steps / dt
                 e2e["pageable_note"] = "same call with pageable (numpy) caller buffers"
                 del pg
+                interleave_host_memory(False)
                 L.eut_oneshot_reset()
             host_barrier()
 
@@ -640,6 +668,7 @@ def run_ours(args):
             "e2e": e2e,
             "parity": parity,
             "gpu_launches": int(launches), "clocks": clocks,
+            "host": {"threads": host_threads(), "numa_nodes": numa_nodes()},
             "breakdown_ms_per_step": {"diffusion_substeps": diff_ms / args.steps,
                                       "scatter_clamp_and_gather": (ms - diff_ms) / args.steps},
         }
