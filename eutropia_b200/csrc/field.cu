@@ -287,7 +287,14 @@ int field_diffuse(eut_field *f, const int32_t *niter, const int32_t *indvar, int
     // columns, lanes against one stream: 100 k points 155 vs 189 G updates/s (below the threshold),
     // 300 k 282 vs 251, 420 k 300 vs 246, 600 k 307 vs 262 (tools/cols_scaling.py); bench step at 1 M: 232 vs 213.
     const bool lanes_force = getenv("EUT_DIFFUSE_LANES_FORCE") != nullptr;      // read per call: the tests force lanes on small meshes
+    const bool lanes_ok = lanes_env > 1 && !f->no_split && phase == 0 && f->opt_phase == 0 && f->plan->segmented && f->opt_variant != 1;
     if (L > 1 && !lanes_force && (int64_t)p->n_tiles * L < 148ll * (p->segs.max_tile_segs > 224 ? 1 : 2)) L = 1;
+    // Small fields (configs[1]: 73 tiles, one wave of CTAs per substep whatever the split): two lanes of at least
+    // 8 columns all the same -- not to fill a wave, but because each lane is its own chain of programmatic
+    // dependent launches: a lane's next substep starts when ITS CTAs have retired and does not wait for the
+    // slowest CTA of the other half (100 467 points x 16 columns: 7.96 -> 7.52 us per substep; 4 lanes: no gain).
+    if (L == 1 && lanes_ok && !lanes_force && n_tot >= 16 && f->opt_cpt == 0 &&
+        (int64_t)p->n_tiles * 2 < 148ll * (p->segs.max_tile_segs > 224 ? 1 : 2)) L = 2;
     if (L > 1) {
         for (int l = 1; l < L; l++) {
             if (!f->lane[l - 1]) EUT_CUDA(cudaStreamCreateWithFlags(&f->lane[l - 1], cudaStreamNonBlocking));
