@@ -273,22 +273,31 @@ def test_one_shot_speculation_is_verified(small_mesh):
     assert np.array_equal(d, ref2)
 
 
-def test_one_shot_streaming_pipeline_option(small_mesh, tmp_path):
-    """EUT_ONESHOT_STREAM=1 selects the column-streaming pipeline of the one-shot tier (read once per
-    process, hence the subprocess): same bits as the oracle, mixed substep counts included."""
+@pytest.mark.parametrize("mode", ["0", "1"])
+def test_one_shot_pipeline_modes(small_mesh, tmp_path, mode):
+    """EUT_ONESHOT_STREAM selects the pipeline of the one-shot tier (read once per process, hence the
+    subprocess): 0 the chunk ramp on two compute streams (default), 1 column streaming with a host-paced launch
+    loop.  Same bits as the oracle from both: mixed substep counts, columns in any order, 37 columns so that groups join and
+    leave at different substeps; three calls in a row (the second captures CUDA graphs, the third replays
+    them) with the result fed back in, as R does every round; pinned-like and pageable caller memory."""
     import subprocess
     import sys
     m = small_mesh
-    conc = synth.synthetic_concentrations(m.field_pts, 11, seed=23)
-    niter = [9, 3, 12, 1, 7, 7, 2, 30, 5, 4, 8]
-    indvar = [1, 3, 2, 5, 4, 6, 8, 7, 11, 9, 10]
+    rng = np.random.default_rng(23)
+    conc = synth.synthetic_concentrations(m.field_pts, 40, seed=23)
+    indvar = (rng.permutation(40)[:37] + 1).tolist()
+    niter = rng.integers(1, 31, 37).tolist()
+    niter[:4] = [30, 1, 2, 17]
     inp, outp = tmp_path / "in.npz", tmp_path / "out.npy"
     np.savez(inp, mat_in=m.mat_in, mat_out=m.mat_out, conc=conc, niter=niter, indvar=indvar)
-    code = ("import numpy as np, eutropia_b200 as eb; g = np.load(r'%s'); "
-            "np.save(r'%s', eb.diffChangePar(g['mat_in'], g['mat_out'], g['conc'], g['niter'], g['indvar']))" % (inp, outp))
-    env = dict(os.environ, EUT_ONESHOT_STREAM="1", PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    code = ("import numpy as np, eutropia_b200 as eb; g = np.load(r'%s'); c = g['conc']\n"
+            "for _ in range(3): c = eb.diffChangePar(g['mat_in'], g['mat_out'], c, g['niter'], g['indvar'])\n"
+            "np.save(r'%s', c)" % (inp, outp))
+    env = dict(os.environ, EUT_ONESHOT_STREAM=mode, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=300)
-    ref = oracle.diffChangePar(m.mat_in, m.mat_out, conc, niter, indvar, 2)
+    ref = conc
+    for _ in range(3):
+        ref = oracle.diffChangePar(m.mat_in, m.mat_out, ref, niter, indvar, 2)
     assert_parity(np.load(outp), ref)
 
 
