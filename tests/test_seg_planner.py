@@ -188,3 +188,52 @@ def test_kiel_polygon_of_the_reference():
     plan = eb.Plan(m.mat_in, m.mat_out, order=_lib.ORDER_SEGMENTS, host_only=True)
     inf = replay(m, plan)
     assert inf.n_seg_covered + inf.n_generic == m.nfields
+
+
+def _modelled_conflicts(meta, segs):
+    """Wavefronts per half-warp LDS.64, averaged over the seven streams: the largest number of lanes of a half
+    warp whose cells share a residue mod 16 (same cell or the zero header = broadcast)."""
+    tot = cnt = 0
+    for t in range(meta.shape[0]):
+        g0, ng = meta[t, 8], meta[t, 9]
+        S = segs[g0:g0 + ng].astype(np.int64)
+        pad = (-ng) % 16
+        if pad:
+            S = np.concatenate([S, np.tile(np.array([[8] + [0] * 23]), (pad, 1))])
+        H = S.reshape(-1, 16, 24) // 8
+        for s in range(7):
+            for h in range(H.shape[0]):
+                u = np.unique(H[h, :, s][H[h, :, s] > 0])
+                tot += max(1, np.bincount(u % 16, minlength=16).max())
+                cnt += 1
+    return tot / cnt
+
+
+def test_gap_rule_keeps_residues_apart(monkeypatch):
+    """The coordinate gap rule (segs.cu): position - u of a piece is a function of its row index and layer, chosen
+    per tile for few gap cells and a balanced histogram of segment start residues in every layer.  On a ragged
+    polygon with 448-segment tiles it must beat the chain rule without the balance term on modelled bank
+    conflicts, keep the gap cells below 8 % of the points, and -- the failure it was written for -- leave no
+    layer of a tile with all its segments on half of the residues."""
+    monkeypatch.setenv("EUT_SEG_TILE", "448")
+    m = mesh.make_mesh(mesh.harbor_polygon(260.0), 1.0, 3)
+    res = {}
+    for name, env in (("coordinate", {"EUT_SEG_PAD": "1"}), ("chain", {"EUT_SEG_PAD": "2", "EUT_SEG_NO_BALANCE": "1"})):
+        for k in ("EUT_SEG_PAD", "EUT_SEG_NO_BALANCE"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        plan = eb.Plan(m.mat_in, m.mat_out, order=_lib.ORDER_SEGMENTS, host_only=True)
+        inf = replay(m, plan)
+        meta, _, segs, _ = plan.segs()
+        res[name] = (_modelled_conflicts(meta, segs), inf.n_padded / m.nfields - 1, meta, segs)
+    assert res["coordinate"][0] < res["chain"][0] - 0.1 and res["coordinate"][0] < 1.35
+    assert res["coordinate"][1] < 0.08
+    meta, segs = res["coordinate"][2], res["coordinate"][3]
+    for t in range(meta.shape[0]):
+        S = segs[meta[t, 8]:meta[t, 8] + meta[t, 9]].astype(np.int64)
+        cls = (S[:, 1] > 0).astype(int) + 2 * (S[:, 5] > 0).astype(int)
+        for c in np.unique(cls):
+            own = (S[cls == c, 0] // 8) % 16
+            if own.size >= 64:
+                assert np.bincount(own, minlength=16).max() <= 2.0 * own.size / 16 + 2, (t, c, np.bincount(own, minlength=16))
