@@ -101,7 +101,8 @@ after[I[, 1:2]] <- after[I[, 1:2]] + I[, 3]
 after[I[, 1:2]] <- ifelse(after[I[, 1:2]] < 1e-12, 0, after[I[, 1:2]])
 
 # ---- correct_numbers (R/growthEnvironment.R:199-217), one axis -------------------------------------------
-all_x <- data.table(val = c(0, 0.5, 1, 1.5000000000000002, 2)); all_x[, key := val]; setkey(all_x, key)
+vals  <- c(0, 0.5, 1, 1.5000000000000002, 2)
+all_x <- data.table(s = vals, val = vals); setattr(all_x, "sorted", "s"); setkey(all_x, s)   # as :175, :178
 qn <- c(0.5, 0.49999999999999994, 0.96, 0.89, 1.5, 1.5000000000000004, 2.0000000000000004, -0.05, -0.2)
 new_n <- all_x[J(qn), roll = -Inf]$val
 new_n <- ifelse(abs(new_n - qn) > fs / 10, NA, new_n)
