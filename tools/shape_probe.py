@@ -40,6 +40,6 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     sys.exit(0)
 mesh = sys.argv[1] if len(sys.argv) > 1 else "square:600000"
 cols = sys.argv[2] if len(sys.argv) > 2 else "64"
-for shape in (0, 1, 2, 3, 5, 6, 7):
+for shape in (0, 1, 2, 3, 5):      # image slots x result buffers: 3x3 (default), 3x2, 4x2, 4x3, 3x4
     r = subprocess.run([sys.executable, __file__, "child", mesh, cols, str(shape)], capture_output=True, text=True)
     print(r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-300:], flush=True)
