@@ -69,6 +69,7 @@ struct eut_slab {
         cudaStream_t ps[kSlabGroups] = {};       // high-priority streams of the halo kernels this slab sends
     };
     int64_t N = 0, C = 0;
+    int depth = 1;                               // ghost rings per slab = substeps between two halo exchanges
     std::vector<Part> parts;
     std::vector<Link> links;
     int64_t pushes = 0;
@@ -218,6 +219,12 @@ int eut_slab_create(eut_slab **out, const int32_t *from, const int32_t *to, int6
     }
     eut_slab *s = new eut_slab();
     s->N = N; s->C = n_cols;
+    // ghost rings per slab = substeps between two exchanges.  Two slabs have nobody to wait for but each other and
+    // run best with one ring (2 GPUs x 2 M points x 64: 0.444 ms per substep, 0.449 with four); from three slabs on
+    // every substep otherwise ends in a wait for the slower of two neighbours, whose own pace depends on ITS
+    // neighbours: four rings, a wait every fourth substep (4 GPUs x 2 M points: 0.511 -> 0.484 ms per substep).
+    const int depth = [&] { const char *e = getenv("EUT_SLAB_DEPTH"); return e ? std::min(16, std::max(1, atoi(e))) : (W >= 3 ? 4 : 1); }();
+    s->depth = depth;
     s->parts.resize(W);
     std::vector<int> rcs(W, EUT_OK);
     std::vector<std::string> errs(W);
@@ -226,26 +233,38 @@ int eut_slab_create(eut_slab **out, const int32_t *from, const int32_t *to, int6
     auto build_part = [&](int r) -> int {
         eut_slab::Part &P = s->parts[r];
         P.device = devices[r];
-        std::vector<uint8_t> mark(N, 0);             // 1 own, 2 ghost
+        // mark: 1 own, 2 .. depth + 1 ghost rings.  Ring j holds the in-neighbours of ring j - 1 that are not marked
+        // yet (ring 0 = own points).  With depth 1 the ghosts are plain copies: no in-edges, outflow weight 0, the
+        // halo exchange overwrites them after every substep.  With depth K > 1 the rings 1 .. K-1 are LIVE -- they
+        // keep their in-edges and weights and are diffused like own points -- and only ring K is a copy: after an
+        // exchange all rings are right; one substep later ring K is stale, ring K-1 was computed from it and is
+        // wrong after the second substep, and so on inwards -- the own points stay right for K substeps, so the
+        // slabs exchange (and wait for each other) only every K-th substep, for (K-1) x one lattice row per
+        // side of redundant work.  Every owned point still sums the same values in the same order: bit-identical.
+        std::vector<uint8_t> mark(N, 0);
         for (int64_t i = 0; i < N; i++) mark[i] = owner[i] == r ? 1 : 0;
+        for (int ring = 1; ring <= depth; ring++)
+            for (int64_t j = 0; j < n_edges; j++)
+                if (mark[to[j] - 1] == ring && !mark[from[j] - 1]) mark[from[j] - 1] = (uint8_t)(ring + 1);
         int64_t n_in = 0;
         for (int64_t j = 0; j < n_edges; j++)
-            if (owner[to[j] - 1] == r) { n_in++; if (!mark[from[j] - 1]) mark[from[j] - 1] = 2; }
+            if (mark[to[j] - 1] && mark[to[j] - 1] <= depth) n_in++;          // computed points: own and live rings
         std::vector<int32_t> &map = g2l[r];
         map.assign(N, -1);
+        std::vector<uint8_t> lmark;
         for (int64_t i = 0; i < N; i++)
-            if (mark[i]) { map[i] = (int32_t)P.local_global.size(); P.local_global.push_back((int32_t)i); P.is_own.push_back(mark[i] == 1); }
+            if (mark[i]) { map[i] = (int32_t)P.local_global.size(); P.local_global.push_back((int32_t)i); P.is_own.push_back(mark[i] == 1); lmark.push_back(mark[i]); }
         P.n_local = (int64_t)P.local_global.size();
         P.n_own = std::count(P.is_own.begin(), P.is_own.end(), (uint8_t)1);
         std::vector<int32_t> lf(n_in), lt(n_in), id(P.n_local), cnt(P.n_local);
         int64_t o = 0;
         for (int64_t j = 0; j < n_edges; j++)
-            if (owner[to[j] - 1] == r) { lf[o] = map[from[j] - 1] + 1; lt[o] = map[to[j] - 1] + 1; o++; }
-        for (int64_t k = 0; k < P.n_local; k++) { id[k] = (int32_t)k + 1; cnt[k] = P.is_own[k] ? nn_by_id[P.local_global[k]] : 1; }
+            if (mark[to[j] - 1] && mark[to[j] - 1] <= depth) { lf[o] = map[from[j] - 1] + 1; lt[o] = map[to[j] - 1] + 1; o++; }
+        for (int64_t k = 0; k < P.n_local; k++) { id[k] = (int32_t)k + 1; cnt[k] = lmark[k] <= depth ? nn_by_id[P.local_global[k]] : 1; }
         P.plan = new eut_plan();
-        if (!getenv("EUT_SLAB_LIVE_GHOSTS")) {               // ghosts are overwritten after every substep: no work for them
+        if (!getenv("EUT_SLAB_LIVE_GHOSTS")) {               // the outermost ring is overwritten by every exchange: no work for it
             P.plan->dead.resize(P.n_local);
-            for (int64_t k = 0; k < P.n_local; k++) P.plan->dead[k] = P.is_own[k] ? 0 : 1;
+            for (int64_t k = 0; k < P.n_local; k++) P.plan->dead[k] = lmark[k] == depth + 1 ? 1 : 0;
         }
         EUT_TRY(plan_build(P.plan, lf.data(), lt.data(), n_in, id.data(), cnt.data(), P.n_local, P.n_local, P.device, EUT_ORDER_AUTO));
         EUT_TRY(field_create(&P.field, P.plan, n_cols));
@@ -494,8 +513,12 @@ int eut_slab_diffuse(eut_slab *s, const int32_t *niter, const int32_t *indvar, i
                     f->act_col = f->d_act + gbeg[g]; f->act_par = f->d_act + f->act_cap + gbeg[g];
                     EUT_TRY(launch_substep(f, n_act[g], it));
                 }
-                EUT_TRY(mark_stepped(s, g));
-                EUT_TRY(push_halos(s, g, gbeg[g], n_act[g], it + 1));
+                // the slabs exchange (and wait for each other) every `depth` substeps; after the last substep of
+                // the call nothing is pushed: the next call starts with an exchange of its own
+                if ((it + 1) % s->depth == 0 && it + 1 < max_it) {
+                    EUT_TRY(mark_stepped(s, g));
+                    EUT_TRY(push_halos(s, g, gbeg[g], n_act[g], it + 1));
+                }
             }
         }
         // ... and ends in it: device mirror of "which buffer holds column c", then the joins

@@ -301,7 +301,9 @@ EUT_API int eut_field_halo_unpack(eut_field *field, const int32_t *cols, int64_t
  * its own plan over that local graph.  After every substep the owner of a boundary point stores the
  * new value straight into the neighbour's ghost cell through a peer-mapped pointer (NVLink P2P
  * within the process, one small kernel per ordered pair of neighbouring slabs) -- no pack / send /
- * recv / unpack.  `devices` may name a device more than once (several slabs on one GPU).
+ * recv / unpack.  From three slabs on, every slab keeps four rings of ghost points, the inner three diffused
+ * like its own points, and the slabs exchange (and wait for each other) every fourth substep only
+ * (EUT_SLAB_DEPTH overrides).  `devices` may name a device more than once (several slabs on one GPU).
  * (eutropia_b200/slab.py drives the same partition with one process per GPU and NCCL send / recv
  * through eut_field_halo_*.) */
 typedef struct eut_slab eut_slab;

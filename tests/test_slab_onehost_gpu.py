@@ -171,3 +171,24 @@ def test_cells_on_slabs_match_the_unsharded_round(devices):
     whole, shard = fld.download(), sf.download()
     assert np.all(np.abs(whole - shard) <= 1e-12 * np.abs(whole))
     sc.close(); sf.close()
+
+
+@pytest.mark.parametrize("depth", [2, 3, 5])
+def test_deep_halo_exchanges_every_k_substeps(harbor_mesh, depth, monkeypatch):
+    """EUT_SLAB_DEPTH = K: every slab keeps K rings of ghost points, the inner K - 1 of them live (diffused like own
+    points), and the slabs exchange -- and wait for each other -- only every K-th substep.  The owned points still
+    sum the same values in the same order: bit-identical to the oracle, mixed substep counts (not multiples of
+    K), two rounds on the resident slabs, three and five slabs on one device."""
+    monkeypatch.setenv("EUT_SLAB_DEPTH", str(depth))
+    m = harbor_mesh
+    rng = np.random.default_rng(33)
+    conc = np.asfortranarray(rng.uniform(0, 25, (m.nfields, 6)) * 10.0 ** rng.integers(-5, 4, (m.nfields, 6)))
+    niter, indvar = [14, 0, 5, 13, 9], [6, 2, 1, 3, 4]
+    ref = oracle.diffChangePar(m.mat_in, m.mat_out, conc, niter, indvar, 2)
+    ref2 = oracle.diffChangePar(m.mat_in, m.mat_out, ref, niter, indvar, 2)
+    for devices in ([0, 0, 0], [0, 0, 0, 0, 0]):
+        got, info = _run(m, conc, niter, indvar, devices)
+        assert np.array_equal(got, ref)
+        got2, info2 = _run(m, conc, niter, indvar, devices, rounds=2)
+        assert np.array_equal(got2, ref2)
+        assert info.halo_points > 0
