@@ -337,7 +337,8 @@ EUT_API int64_t eut_slab_launch_count(const eut_slab *slab);
  * per-field work (claim rescale, scatter sums in cell order, clamp) runs on the owner exactly as on an
  * unsharded field, per-cell quantities (production shares, accessible amounts = colSums of the uptake
  * shares) are combined over the slabs a cell touches.  Same argument meaning as eut_cells_*; `pts` are the
- * global field points, field ids in eut_slab_cells_get_lists are global. */
+ * global field points, field ids in eut_slab_cells_get_lists are global.  Destroy the cells before the slab they
+ * were created on. */
 typedef struct eut_slab_cells eut_slab_cells;
 EUT_API int eut_slab_cells_create(eut_slab_cells **out, eut_slab *slab);
 EUT_API int eut_slab_cells_destroy(eut_slab_cells *cells);
