@@ -351,7 +351,9 @@ def slab_leg(eb, torch, world, peak, points_per_gpu=2_000_000, cols=64, substeps
                         f"{world} GPUs from one process (configs[4] shape: 2 M points per GPU)",
             "value": value, "unit": UNIT, "ms_per_substep": dt * 1e3 / substeps, "n_gpus": world,
             "algorithmic_GBps_per_gpu": gbps, "frac_of_hbm_peak_per_gpu": gbps / peak,
-            "halo_points_per_substep": int(info.halo_points), "nvlink_bytes_per_substep": int(info.halo_points) * cols * 8,
+            "ghost_rings": int(info.depth), "substeps_between_exchanges": int(info.depth),
+            "halo_points_per_exchange": int(info.halo_points),
+            "nvlink_bytes_per_substep": int(info.halo_points) * cols * 8 // max(1, int(info.depth)),
             "links": int(info.n_links), "gpu_launches": int(launches), "bit_identical_to_unsharded": same,
             "segment_kernel_on_every_slab": bool(info.segmented), "setup_s": {"mesh": t_mesh, "partition_and_plans": info.build_ms / 1e3},
             "timer": "host wall clock around eut_slab_diffuse + eut_slab_sync"}

@@ -46,7 +46,7 @@ class PlanInfo(C.Structure):
 class SlabInfo(C.Structure):
     _fields_ = [("n_points", C.c_int64), ("n_cols", C.c_int64), ("n_slabs", C.c_int32), ("n_links", C.c_int32),
                 ("max_local", C.c_int64), ("halo_points", C.c_int64), ("max_link", C.c_int64), ("pushes", C.c_int64),
-                ("segmented", C.c_int32), ("build_ms", C.c_double)]
+                ("segmented", C.c_int32), ("depth", C.c_int32), ("build_ms", C.c_double)]
 
 
 _lib = None

@@ -340,6 +340,7 @@ int eut_slab_get_info(const eut_slab *s, eut_slab_info *info)
     for (auto &p : s->parts) { info->max_local = std::max(info->max_local, p.n_local); info->segmented &= p.plan->segmented ? 1 : 0; }
     for (auto &l : s->links) { info->halo_points += l.n; info->max_link = std::max(info->max_link, l.n); }
     info->pushes = s->pushes;
+    info->depth = s->depth;
     info->build_ms = s->build_ms;
     return EUT_OK;
 }

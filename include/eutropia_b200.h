@@ -311,10 +311,11 @@ typedef struct eut_slab_info {
     int64_t n_points, n_cols;
     int32_t n_slabs, n_links;   /* links: ordered pairs of slabs that exchange points */
     int64_t max_local;          /* most points (own + ghost) of any slab */
-    int64_t halo_points;        /* points that travel per substep and column, summed over all links */
+    int64_t halo_points;        /* points that travel per exchange and column, summed over all links */
     int64_t max_link;           /* most points of any link */
     int64_t pushes;             /* halo kernels launched so far */
     int32_t segmented;          /* 1: every slab runs the segment kernel */
+    int32_t depth;              /* ghost rings per slab = substeps between two halo exchanges */
     double  build_ms;
 } eut_slab_info;
 EUT_API int eut_slab_create(eut_slab **out, const int32_t *from, const int32_t *to, int64_t n_edges,

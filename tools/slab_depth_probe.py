@@ -11,4 +11,4 @@ peak, _ = bench.peaks()
 for depth in (sys.argv[1:] or ["1", "2", "4", "8"]):
     os.environ["EUT_SLAB_DEPTH"] = depth
     r = bench.slab_leg(eb, torch, nd, peak)
-    print(json.dumps({"gpus": nd, "depth": int(depth), **{k: r[k] for k in ("value", "ms_per_substep", "frac_of_hbm_peak_per_gpu", "halo_points_per_substep", "gpu_launches", "bit_identical_to_unsharded")}}), flush=True)
+    print(json.dumps({"gpus": nd, "depth": int(depth), **{k: r[k] for k in ("value", "ms_per_substep", "frac_of_hbm_peak_per_gpu", "halo_points_per_exchange", "gpu_launches", "bit_identical_to_unsharded")}}), flush=True)
